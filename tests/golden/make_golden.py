@@ -1,0 +1,131 @@
+"""Generate golden vectors by running the REAL reference class from /root/reference.
+
+Run in the build container only (``python tests/golden/make_golden.py``); /root/reference does not
+exist on the GPU box, which is why the outputs are committed next to this script.
+
+The reference package cannot be imported as-is here (``fulu/__init__.py`` pulls in ``torchbnn`` and
+``matplotlib``, both absent), so the hot-path module ``fulu/gp_aug.py`` is imported through empty stub
+modules for matplotlib and a stub ``fulu`` package whose ``__path__`` points at the reference tree.
+Nothing is copied: the reference source is executed where it lies.
+
+Each ``<case>.npz`` holds the inputs, the fitted state of the reference
+(``ss.mean_/scale_``, ``reg._y_train_mean/_std``, ``reg.kernel_.theta``,
+``reg.log_marginal_likelihood_value_``), ``reg.log_marginal_likelihood(theta, eval_gradient=True)`` at
+the six start points and at theta*, and ``aug.augmentation(...)``.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+REF = "/root/reference"
+
+
+def load_reference():
+    for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors"):
+        sys.modules[m] = types.ModuleType(m)
+    sys.modules["matplotlib.colors"].TABLEAU_COLORS = {}
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    pkg = types.ModuleType("fulu")
+    pkg.__path__ = [os.path.join(REF, "fulu")]
+    sys.modules["fulu"] = pkg
+    import fulu.gp_aug as gp_aug
+
+    return gp_aug.GaussianProcessesAugmentation
+
+
+def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=None, t_max=None):
+    import sklearn.gaussian_process._gpr as gpr_mod
+
+    keys = list(p2l)
+    band = np.array([keys.index(k) for k in passband], dtype=np.int32)
+    loglam = np.array([p2l[k] for k in keys], dtype=np.float64)
+    n_eval = [0]
+    orig = gpr_mod.GaussianProcessRegressor.log_marginal_likelihood
+
+    def counted(self, theta=None, eval_gradient=False, clone_kernel=True):
+        if eval_gradient:
+            n_eval[0] += 1
+        return orig(self, theta, eval_gradient, clone_kernel)
+
+    gpr_mod.GaussianProcessRegressor.log_marginal_likelihood = counted
+    try:
+        aug = cls(p2l, use_err=use_err)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert aug.fit(t, flux, flux_err, passband) is aug
+    finally:
+        gpr_mod.GaussianProcessRegressor.log_marginal_likelihood = orig
+    reg = aug.reg
+    theta_star = reg.kernel_.theta.copy()
+    rng = np.random.RandomState(42)
+    b = reg.kernel_.bounds
+    thetas = [np.zeros(len(theta_star))] + [rng.uniform(b[:, 0], b[:, 1]) for _ in range(5)] + [theta_star]
+    lmls, grads = [], []
+    for th in thetas:
+        l, g = reg.log_marginal_likelihood(th, eval_gradient=True, clone_kernel=True)
+        lmls.append(l)
+        grads.append(g)
+    t = np.asarray(t, np.float64)
+    t_min = float(t.min()) if t_min is None else t_min
+    t_max = float(t.max()) if t_max is None else t_max
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t_aug, f_aug, e_aug, pb_aug = aug.augmentation(t_min, t_max, n_obs)
+        # prediction at fixed (non-optimised) hyperparameters: start point #5 is a well conditioned one
+        reg2 = gpr_mod.GaussianProcessRegressor(kernel=reg.kernel_.clone_with_theta(thetas[5]), optimizer=None, normalize_y=True,
+                                                alpha=reg.alpha)
+        reg2.fit(aug.ss.transform(np.c_[t, loglam[band]]), np.asarray(flux, np.float64))
+        Xq = aug.ss.transform(np.c_[t_aug, np.repeat(loglam, n_obs)])
+        f5, e5 = reg2.predict(Xq, return_std=True)
+    np.savez(
+        os.path.join(HERE, name + ".npz"),
+        t=t, flux=np.asarray(flux, np.float64), flux_err=np.asarray(flux_err, np.float64), band=band, loglam=loglam,
+        use_err=np.array(use_err), n_obs=np.array(n_obs), t_min=np.array(t_min), t_max=np.array(t_max),
+        x_mean=aug.ss.mean_, x_scale=aug.ss.scale_, y_mean=np.array(reg._y_train_mean), y_std=np.array(reg._y_train_std),
+        theta_star=theta_star, lml_star=np.array(reg.log_marginal_likelihood_value_), n_eval=np.array(n_eval[0]),
+        thetas=np.array(thetas), lml=np.array(lmls), grad=np.array(grads),
+        t_aug=t_aug, flux_aug=f_aug, flux_err_aug=e_aug, band_aug=np.repeat(np.arange(len(keys), dtype=np.int32), n_obs),
+        flux_aug_theta5=f5, flux_err_aug_theta5=e5,
+    )
+    print(f"{name}: N={len(t)} use_err={use_err} E={n_eval[0]} lml*={reg.log_marginal_likelihood_value_:.10f} theta*={theta_star}")
+
+
+def main():
+    import pandas as pd
+
+    from fulu_b200 import datasets
+
+    cls = load_reference()
+    p2l, *lc = datasets.readme_example()
+    run_case(cls, "readme", p2l, *lc, use_err=False, n_obs=100)
+    run_case(cls, "readme_err", p2l, *lc, use_err=True, n_obs=100)
+    p2l, *lc = datasets.reference_test_fixture()
+    run_case(cls, "testfixture", p2l, *lc, use_err=False, n_obs=100)
+    run_case(cls, "testfixture_err", p2l, *lc, use_err=True, n_obs=100)
+    df = pd.read_csv(os.path.join(REF, "notebook_examples", "object_34299.csv"))
+    p2l = {i: float(np.log10(v)) for i, v in enumerate(datasets.LSST_LAMBDA)}  # plotting.ipynb:22-23
+    lc = (df.mjd.values, df.flux.values, df.flux_err.values, df.passband.values)
+    run_case(cls, "csv34299", p2l, *lc, use_err=False, n_obs=128)
+    run_case(cls, "csv34299_err", p2l, *lc, use_err=True, n_obs=128)
+    # single-band curve (table lists 6 bands, observations only in band 2): constant log-lambda column
+    sel = df.passband.values == 2
+    run_case(cls, "csv34299_band2", p2l, df.mjd.values[sel], df.flux.values[sel], df.flux_err.values[sel], df.passband.values[sel],
+             use_err=False, n_obs=32)
+    b = datasets.plasticc_like(6)
+    for i in range(b.n_curves):
+        t, f, e, bd = b.curve(i)
+        run_case(cls, f"plasticc_{i}", p2l, t, f, e, bd, use_err=(i % 2 == 1), n_obs=128)
+    z = datasets.ztf_like(6)
+    p2z = {i: float(np.log10(v)) for i, v in enumerate(datasets.ZTF_LAMBDA)}
+    for i in range(z.n_curves):
+        t, f, e, bd = z.curve(i)
+        run_case(cls, f"ztf_{i}", p2z, t, f, e, bd, use_err=False, n_obs=128)
+
+
+if __name__ == "__main__":
+    main()

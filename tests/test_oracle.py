@@ -1,0 +1,85 @@
+"""The oracle against the golden vectors produced by the real reference (tests/golden/make_golden.py)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import gp_oracle as O
+from oracle.fulu_sklearn_port import SklearnGPAugmentation
+
+
+def _prep(g):
+    p2l = {i: float(v) for i, v in enumerate(g["loglam"])}
+    gp = O.ClosedFormGP(p2l, use_err=bool(g["use_err"]))
+    gp.prepare(g["t"], g["flux"], g["flux_err"], g["band"])
+    return p2l, gp
+
+
+def test_closed_form_scaler_and_norm(golden):
+    _, gp = _prep(golden)
+    assert relerr(gp.x_mean, golden["x_mean"]) < 1e-15
+    assert relerr(gp.x_scale, golden["x_scale"]) < 1e-13
+    assert abs(gp.y_mean - golden["y_mean"]) <= 1e-15 * abs(golden["y_mean"])
+    assert abs(gp.y_std - golden["y_std"]) <= 1e-14 * abs(golden["y_std"])
+
+
+def test_closed_form_lml_and_grad(golden):
+    _, gp = _prep(golden)
+    for th, lml, grad in zip(golden["thetas"], golden["lml"], golden["grad"]):
+        l, g, gs = O.lml_and_grad(gp.X, gp.y, gp.alpha, th, return_scale=True)
+        assert abs(l - lml) <= 1e-10 * max(1.0, abs(lml)), (golden["name"], th)
+        # the gradient is a cancelling trace: relative to the larger of |g| and 1e-3 x (sum of |terms|)
+        assert np.max(np.abs(g - grad) / np.maximum(np.maximum(np.abs(grad), 1e-3 * gs), 1e-30)) < 1e-9, (golden["name"], th)
+
+
+def test_closed_form_predict_fixed_theta(golden):
+    _, gp = _prep(golden)
+    g = golden
+    n_obs = int(g["n_obs"])
+    for theta, fm, fs in ((g["thetas"][5], g["flux_aug_theta5"], g["flux_err_aug_theta5"]), (g["theta_star"], g["flux_aug"], g["flux_err_aug"])):
+        gp.fit(g["t"], g["flux"], g["flux_err"], g["band"], theta=theta)
+        t_aug, m, s, pb = gp.augmentation(float(g["t_min"]), float(g["t_max"]), n_obs)
+        np.testing.assert_array_equal(t_aug, g["t_aug"])
+        np.testing.assert_array_equal(pb, g["band_aug"])
+        assert relerr(m, fm, floor=1e-6 * gp.y_std) < 1e-9
+        assert relerr(s, fs, floor=1e-6 * gp.y_std) < 1e-8  # sklearn itself is ~1.5e-10 from an 80-bit evaluation
+
+
+@pytest.mark.parametrize("name", ["readme", "testfixture", "csv34299", "csv34299_err", "plasticc_0", "ztf_0"])
+def test_closed_form_fit_reaches_reference_lml(name):
+    from conftest import load_golden
+
+    g = load_golden(name)
+    _, gp = _prep(g)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        theta, lml, n_eval = O.fit_theta(gp.X, gp.y, gp.alpha)
+    assert lml >= float(g["lml_star"]) - 1e-6
+    assert abs(lml - float(g["lml_star"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["readme", "testfixture_err", "csv34299", "plasticc_1"])
+def test_sklearn_port_is_the_reference(name):
+    """The port performs the same library calls as fulu/gp_aug.py, so it reproduces the fixture bit for bit."""
+    from conftest import load_golden
+
+    g = load_golden(name)
+    p2l = {i: float(v) for i, v in enumerate(g["loglam"])}
+    aug = SklearnGPAugmentation(p2l, use_err=bool(g["use_err"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert aug.fit(g["t"], g["flux"], g["flux_err"], g["band"]) is aug
+        t_aug, f, e, pb = aug.augmentation(float(g["t_min"]), float(g["t_max"]), int(g["n_obs"]))
+    np.testing.assert_array_equal(aug.reg.kernel_.theta, g["theta_star"])
+    assert aug.reg.log_marginal_likelihood_value_ == float(g["lml_star"])
+    np.testing.assert_array_equal(f, g["flux_aug"])
+    np.testing.assert_array_equal(e, g["flux_err_aug"])
+    np.testing.assert_array_equal(t_aug, g["t_aug"])
+
+
+def test_start_points_match_survey():
+    s = O.start_points(4)
+    assert s.shape == (6, 4)
+    np.testing.assert_allclose(s[1], [-2.88882052, 10.37808043, 5.34185792, 2.27169555], atol=1e-8)
+    np.testing.assert_allclose(s[5], [-4.50748893, 0.5700379, -1.56702386, -4.8071267], atol=1e-8)
