@@ -1,0 +1,125 @@
+/* fulu_gp.h — C ABI of the B200-native Gaussian-process light-curve augmentation path.
+ *
+ * Drop-in boundary for the hot path of hse-cs/fulu:
+ *   fulu.GaussianProcessesAugmentation.fit / .predict / .augmentation
+ *   (reference: fulu/gp_aug.py:37-108, fulu/_base_aug.py:9-20,88-114), whose arithmetic is
+ *   sklearn.gaussian_process.GaussianProcessRegressor (sklearn/gaussian_process/_gpr.py:232-368,
+ *   444-500, 541-656) driven by SciPy L-BFGS-B.  The reference has no FFI of its own (pure Python);
+ *   these entry points are what a ctypes binding inside fulu/gp_aug.py would call instead of
+ *   `self.reg.fit(...)` / `self.reg.predict(...)` — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer in fulu_gp_batch and every in/out array is a DEVICE pointer owned by the caller
+ *     (PyTorch tensors); the library allocates nothing and keeps no global state;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), except
+ *     fulu_gp_fit_batch which returns after the optimisation loop has finished on the device;
+ *   - return value: 0 ok, <0 argument error (FULU_GP_E_*), >0 a cudaError_t;
+ *   - per-curve problems never fail the call: they are reported in status[] (FULU_GP_STATUS_* bits).
+ *   - batches are ragged CSR: curve i owns observations offsets[i] .. offsets[i+1]-1.
+ */
+#ifndef FULU_GP_H
+#define FULU_GP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FULU_GP_ABI_VERSION 1
+#define FULU_GP_MAX_PARAMS 6
+#define FULU_GP_MAX_BANDS 16
+
+/* kernel families (theta is log-transformed, sklearn order; kernels.py:739-752) */
+#define FULU_GP_KERNEL_RBF_WHITE 0        /* C*RBF([lt,ll]) + White : theta = log[c, lt, ll, s2]  (fulu/gp_aug.py:29 default) */
+
+/* argument errors */
+#define FULU_GP_E_BADARG (-1)
+#define FULU_GP_E_WORKSPACE (-2)     /* workspace too small */
+#define FULU_GP_E_UNSUPPORTED (-3)   /* kernel family / size not supported by this build */
+#define FULU_GP_E_NOCUDA (-4)
+
+/* per-curve status bits */
+#define FULU_GP_STATUS_OK 0
+#define FULU_GP_STATUS_BAD_INPUT 1       /* NaN/inf in t/flux/flux_err or band out of range (sklearn: ValueError, _gpr.py:257-265) */
+#define FULU_GP_STATUS_NOT_PD 2          /* K(theta*) not positive definite (sklearn: LinAlgError, _gpr.py:349-361) */
+#define FULU_GP_STATUS_NOT_CONVERGED 4   /* best run ended ABNORMAL / at the iteration limit (ConvergenceWarning, utils/optimize.py:436-458) */
+#define FULU_GP_STATUS_AT_BOUND 8        /* theta* numerically on a bound (ConvergenceWarning, kernels.py:436-464) */
+#define FULU_GP_STATUS_NEG_VARIANCE 16   /* a predictive variance was clamped to 0 (_gpr.py:485-491) */
+
+typedef struct fulu_gp_batch {
+  int64_t n_curves;          /* B */
+  int64_t n_obs_total;       /* offsets[B] */
+  int32_t n_max;             /* max curve length in the batch (host-known upper bound) */
+  int32_t n_bands;           /* entries of loglam */
+  const int64_t* offsets;    /* [B+1] */
+  const double* t;           /* [n_obs_total] observation times        (fulu fit arg `t`) */
+  const double* flux;        /* [n_obs_total]                          (`flux`) */
+  const double* flux_err;    /* [n_obs_total]                          (`flux_err`) */
+  const int32_t* band;       /* [n_obs_total] index into loglam        (`passband` through passband2lam, _base_aug.py:9-11) */
+  const double* loglam;      /* [n_bands] log10 wavelength table        (passband2lam values in dict order) */
+  int32_t kernel;            /* FULU_GP_KERNEL_* */
+  int32_t use_err;           /* fulu use_err flag (gp_aug.py:72-73) */
+  double alpha0;             /* regressor alpha when !use_err: 1e-10 (_gpr.py:215) */
+} fulu_gp_batch;
+
+typedef struct fulu_gp_fit_options {
+  int32_t n_params;          /* P (4 for the default kernel) */
+  int32_t n_starts;          /* S = 1 + n_restarts_optimizer = 6 */
+  int32_t m;                 /* L-BFGS history, 10 */
+  int32_t maxiter;           /* 15000 */
+  int32_t maxfun;            /* 15000 */
+  int32_t maxls;             /* 20 */
+  int32_t window;            /* optimiser instances resident at once (0 = default) */
+  int32_t max_rounds;        /* hard cap on evaluation rounds (0 = default) */
+  double factr;              /* 1e7  (ftol = factr * eps) */
+  double pgtol;              /* 1e-5 */
+  double lower[FULU_GP_MAX_PARAMS];   /* log-bounds, ln(1e-5) */
+  double upper[FULU_GP_MAX_PARAMS];   /* ln(1e5) */
+} fulu_gp_fit_options;
+
+int fulu_gp_abi_version(void);
+const char* fulu_gp_strerror(int code);
+
+/* Bytes of device workspace needed by any of the calls below for this batch shape. */
+int fulu_gp_workspace_bytes(const fulu_gp_batch* batch, int32_t n_params, int32_t n_starts, int32_t window, size_t* bytes);
+
+/* Log marginal likelihood and gradient at given hyperparameters, one theta per curve.
+ * Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True) (_gpr.py:541-656).
+ * theta [B,P] in; lml [B], grad [B,P] out; non-PD K gives lml=-inf, grad=0 (_gpr.py:590-593).
+ * scaler [B,4] = (t mean, t scale, loglam mean, loglam scale), ynorm [B,2] = (flux mean, flux std) out (may be NULL). */
+int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad,
+                      double* scaler, double* ynorm, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Hyperparameter optimisation: S bound-constrained L-BFGS-B runs per curve from theta_starts [S,P], best LML wins.
+ * Replaces GaussianProcessRegressor.fit's optimiser loop (_gpr.py:299-340,658-668).
+ * theta_opt [B,P], lml_opt [B], n_eval [B] (LML+gradient evaluations spent on the curve), status [B] out.
+ * run_lml [B,S] (final LML of every run) and run_theta [B,S,P] may be NULL. */
+int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,
+                      double* lml_opt, int32_t* n_eval, int32_t* status, double* run_lml, double* run_theta, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Augmentation: predictive mean / std on the band-major grid linspace(t_min[i], t_max[i], n_obs) x n_bands.
+ * Replaces BaseAugmentation.augmentation -> predict -> reg.predict(return_std=True)
+ * (_base_aug.py:88-114, gp_aug.py:99-108, _gpr.py:444-500), including the final factorisation (_gpr.py:349-367).
+ * theta [B,P] in; t_min/t_max [B] in (NULL = the curve's own min/max); mean/std [B, n_bands, n_obs] out. */
+int fulu_gp_predict_grid_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const double* t_min,
+                               const double* t_max, int32_t n_obs, double* mean, double* std, double* lml, int32_t* status,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Prediction at arbitrary points: curve i is queried at q_t/q_band[q_offsets[i] .. q_offsets[i+1]-1]
+ * (fulu predict(t, passband), gp_aug.py:80-108). mean/std [q_offsets[B]] out. */
+int fulu_gp_predict_points_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const int64_t* q_offsets,
+                                 const double* q_t, const int32_t* q_band, int32_t q_max, double* mean, double* std,
+                                 int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* FP64 roofline probe: runs a register-resident DFMA (mode 0) or DMMA m8n8k4 (mode 1) loop on every SM and returns the
+ * achieved TFLOP/s in *tflops (CUDA-event timed on `stream`).  Used by bench.py for the roofline denominator because
+ * MEASURED_PEAKS.json has no FP64 entry. */
+int fulu_gp_fp64_peak(int32_t mode, int32_t iters, double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FULU_GP_H */
