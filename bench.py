@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the GP fit + augmentation hot path (BASELINE.json metric: light curves/sec, 6 bands, N=100).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--curves B] [--impl reference]
+
+One "step" = one pass of the hot path (6 x L-BFGS-B fit + 128-point x 6-band augmentation) over one batch of
+synthetic PLAsTiCC-like curves (config #3 of BASELINE.json: B=10,000 per GPU, N=100, M=768).  With N>1 (torchrun, one rank per
+GPU) every rank owns its own 10,000 curves (weak scaling); there is no collective on the data path.  Rank 0 prints ONE JSON line.
+
+  value         curves/s with the batch already resident in HBM (CUDA events around K steps, max over ranks)
+  e2e           the same through the public API fit_augment_batch(): pinned host arrays in, host arrays out, H2D+D2H timed
+  roofline      the evaluation kernel (fit_eval_kernel: assemble K, Cholesky, inverse, LML+gradient) against the FP64 pipe:
+                algorithmic flops N^3+12N^2 per evaluation / CUDA-event time of its launches (library-side events on
+                the launching stream); peak = DFMA rate measured in this run by fulu_gp_fp64_peak (MEASURED_PEAKS.json has no FP64)
+  cpu_baseline  the reference path (fulu adapter on scikit-learn, oracle/fulu_sklearn_port.py) on all host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS, N_OBS, N_BANDS = 100, 128, 6
+METRIC = "light curves/sec GP fit+augment (6 bands, N=100)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    first, count, n_points, n_obs = args
+    import warnings
+
+    import numpy as np
+
+    from fulu_b200 import datasets
+    from oracle.fulu_sklearn_port import SklearnGPAugmentation
+
+    hb = datasets.plasticc_like(count, n_points=n_points, first=first)
+    p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
+    out = []
+    for i in range(hb.n_curves):
+        t, f, e, b = hb.curve(i)
+        aug = SklearnGPAugmentation(p2l)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            aug.fit(t, f, e, b)
+            aug.augmentation(t.min(), t.max(), n_obs)
+        out.append(float(aug.reg.log_marginal_likelihood_value_))
+    return out
+
+
+def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4):
+    """curves/s of the reference CPU path (sklearn GaussianProcessRegressor driven exactly as fulu drives it) on `cores` processes."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    cores = cores or os.cpu_count() or 1
+    for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"  # 8 procs x 1 BLAS thread beat 1 x 8 by 6x
+    tasks = [(first + i, min(chunk, n_curves - i), N_POINTS, N_OBS) for i in range(0, n_curves, chunk)]
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+        list(ex.map(_cpu_worker, [(10_000_000 + w, 1, N_POINTS, N_OBS) for w in range(cores)]))  # warm-up: imports + first fit
+        t0 = time.perf_counter()
+        lml = [v for part in ex.map(_cpu_worker, tasks) for v in part]
+        dt = time.perf_counter() - t0
+    return n_curves / dt, dt, cores, lml
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(2 * cores, min(args.ref_curves, 24 * cores))
+    vals, times = [], []
+    for s in range(args.warmup + args.steps):
+        v, dt, cores, _ = cpu_reference_throughput(per_step, cores, first=s * per_step)
+        if s >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = per_step * len(times) / sum(times)
+    sample = f"{per_step} curves of config #3 per step (N={N_POINTS}, 6 bands, M={N_BANDS * N_OBS}), {cores} processes x 1 BLAS thread"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "curves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands)", "curves_per_step": per_step,
+                   "n_points": N_POINTS, "n_bands": N_BANDS, "n_obs": N_OBS},
+        "cpu_baseline": {"value": value, "unit": "curves/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/fulu_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+
+    import fulu_b200
+    from fulu_b200 import datasets
+    from fulu_b200.engine import DeviceBatch, pin_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # CPU baseline first (rank 0, N=1 only), before this process's CUDA context is busy
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_n = max(2 * cores, min(args.ref_curves, 24 * cores))
+        v, dt, cores, _ = cpu_reference_throughput(sample_n, cores)
+        cpu_base = {"value": v, "unit": "curves/s", "cores": cores, "kind": "port",
+                    "sample": f"{sample_n} curves of config #3 (N={N_POINTS}, 6 bands, M={N_BANDS * N_OBS}) in {dt:.1f} s, {cores} processes x 1 BLAS thread, "
+                              "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"}
+
+    engine = fulu_b200.GPEngine(torch.device("cuda", local))
+    B = args.curves
+    host = datasets.plasticc_like(B, n_points=N_POINTS, first=rank * B)   # each rank: its own B curves (weak scaling)
+    pinned = pin_batch(host)
+    dev = DeviceBatch.from_host(host, engine.device, pinned=pinned)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=engine.device)   # > 126 MB L2
+
+    def step_resident(profile=False):
+        flush.zero_()   # L2 flush between timed iterations (inputs are 28 MB, smaller than L2)
+        fit = engine.fit(dev, profile=profile)
+        pred = engine.predict_grid(dev, fit["theta"], N_OBS)
+        return fit, pred
+
+    def step_e2e():
+        flush.zero_()
+        return fulu_b200.fit_augment_batch(host, n_obs=N_OBS, engine=engine, pinned=pinned)
+
+    for _ in range(args.warmup):
+        step_resident()
+    peak_dfma = engine.fp64_peak(0)
+    peak_dmma = engine.fp64_peak(1)
+
+    # ---- timed: resident inputs
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0.record()
+    evals, eval_ms, step_ms, rounds, launches = 0, 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        fit, pred = step_resident(profile=True)
+        pr = fit["profile"]
+        eval_ms += pr["eval_ms"]; step_ms += pr["step_ms"]; rounds += int(pr["rounds"]); launches += int(pr["launches"]) + 3
+        evals += int(fit["n_eval"].sum().item())
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=engine.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- timed: end to end through the public API (pinned host in, host out)
+    for _ in range(1):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=engine.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+
+    status = res.status
+    flagged = float(np.count_nonzero(status & ~8))   # anything but "theta on a bound"
+    stats = torch.tensor([evals, eval_ms, flagged], dtype=torch.float64, device=engine.device)
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    evals_all, eval_ms_all = float(stats[0]), float(stats[1]) / world
+    f_eval = N_POINTS ** 3 + 12 * N_POINTS ** 2
+    achieved = (evals_all / world) * f_eval / (eval_ms_all * 1e-3) / 1e12   # TFLOP/s of the evaluation kernel on one GPU
+    pr = fit["profile"]
+    line = {
+        "metric": METRIC, "value": value, "unit": "curves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands), one batch per GPU per step",
+                   "curves_per_gpu_per_step": B, "n_points": N_POINTS, "n_bands": N_BANDS, "n_obs": N_OBS, "n_starts": 6,
+                   "l2": "flushed between steps (256 MiB memset); inputs 28 MB", "parallelism": f"curve-sharded x{world}, no collective"},
+        "e2e": {"value": e2e_value, "unit": "curves/s", "h2d_bytes_per_step": int(res.h2d_bytes), "d2h_bytes_per_step": int(res.d2h_bytes)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
+                     "frac": achieved / peak_dfma if peak_dfma else None, "traffic": None,
+                     "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",
+                     "peak_dmma": peak_dmma, "flops_per_eval": f_eval, "evals_per_curve": evals_all / (world * B * args.steps),
+                     "eval_kernel_ms_per_step": eval_ms_all / args.steps, "eval_kernel_share_of_step": eval_ms_all / ms_max,
+                     "step_kernel_ms_per_step": step_ms / args.steps, "rounds_per_step": rounds / args.steps,
+                     "hbm_gbs_algorithmic": value / world * (28 * N_POINTS + 8 + 16 * N_BANDS * N_OBS + 8 * 4 + 16) / 1e9,
+                     "grid": int(pr["grid_eval"]), "smem_per_cta": int(pr["smem_eval"])},
+        "cpu_baseline": cpu_base,
+        "parity": {"curves_flagged": int(stats[2]), "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)]))},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--curves", type=int, default=10000, help="curves per GPU per step (config #3: 10,000)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-curves", type=int, default=256, help="CPU sample size per step (bounded)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,8 +24,10 @@
 
 #if defined(__CUDACC__)
 #define GP_DEV __device__ __forceinline__
+#define GP_HD __host__ __device__ __forceinline__
 #else
 #define GP_DEV inline
+#define GP_HD inline
 #endif
 
 #define GP_NB 4
@@ -55,11 +57,11 @@ struct GpSmem {
   int np, ld;
 };
 
-GP_DEV int gp_pad(int n) { return (n + GP_NB - 1) / GP_NB * GP_NB; }
-GP_DEV int gp_ld(int np) { return (np + GP_NB) | 1; }
+GP_HD int gp_pad(int n) { return (n + GP_NB - 1) / GP_NB * GP_NB; }
+GP_HD int gp_ld(int np) { return (np + GP_NB) | 1; }
 
 // number of doubles of shared memory needed for a curve of n observations
-GP_DEV size_t gp_smem_doubles(int n, int nthr) {
+GP_HD size_t gp_smem_doubles(int n, int nthr) {
   size_t np = (size_t)gp_pad(n), ld = (size_t)gp_ld((int)np);
   size_t red = nthr > 64 ? nthr : 64;
   return np * ld + 6 * np + (np / GP_NB) * 16 + np * GP_NB + red + 2;

@@ -1,0 +1,729 @@
+// CUDA kernels and C-ABI entry points of libfulu_gp (sm_100a).  See include/fulu_gp.h for the contract and
+// gp_block.cuh / lbfgsb.cuh for the algorithms.
+//
+// Execution model
+//   prep kernel      one CTA per curve: StandardScaler statistics, y normalisation, noise diagonal  (a1-a3)
+//   eval kernel      persistent CTAs; each takes one (curve, start) optimiser slot, builds K in shared memory,
+//                    factors it and returns -LML and its gradient                                   (a4, a5)
+//   step kernel      one thread per active slot: advances its L-BFGS-B state machine, and when a run finishes pulls the
+//                    next (curve, start) task into the freed slot ("continuous batching")            (a6)
+//   select kernel    best of the S runs per curve                                                    (a6)
+//   predict kernel   one CTA per curve: final factorisation + augmentation grid / query points       (a7-a9)
+// There is no collective anywhere: curves are independent, multi-GPU runs shard the batch.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fulu_gp.h"
+#include "gp_block.cuh"
+#include "lbfgsb.cuh"
+
+namespace {
+
+struct DevCtx {
+  int tid, nthr;
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+constexpr int kEvalThreads = 256;
+constexpr int kPredictThreads = 128;
+constexpr int kPrepThreads = 128;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct WsLayout {
+  size_t xs, y, al, lam, stats, pstatus;                                      // prepared curves
+  size_t slots, slot_task, slot_nev, f_out, g_out, list, counts, next_task;   // optimiser window
+  size_t run_f, run_x, run_nev, run_end, starts;                              // per (curve, start) results
+  size_t gA, gV;                                                              // per-CTA global scratch
+  size_t total;
+  int window, max_rounds, grid_eval, grid_predict;
+  size_t gA_stride, gV_stride;   // doubles per CTA
+  bool globalA;
+  size_t smem_eval, smem_predict;
+};
+
+struct DeviceInfo {
+  int sms;
+};
+
+int device_info(DeviceInfo& di) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}
+
+constexpr int kDefaultWindow = 16384;
+constexpr int kDefaultMaxRounds = 200000;
+
+void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int sms, WsLayout& w) {
+  const size_t B = (size_t)b.n_curves, NT = (size_t)b.n_obs_total;
+  const int nmax = b.n_max < 1 ? 1 : b.n_max;
+  const size_t np = (size_t)gp_pad(nmax), ld = (size_t)gp_ld((int)np);
+  size_t full = gp_smem_doubles(nmax, kEvalThreads) * sizeof(double);
+  w.globalA = full > kMaxSmem;
+  size_t vec = (gp_smem_doubles(nmax, kEvalThreads) - np * ld) * sizeof(double) + 16;
+  w.smem_eval = w.globalA ? vec : full + 16;
+  w.smem_predict = w.smem_eval;
+  int occ = w.globalA ? (np <= 512 ? 2 : 1) : (int)(kMaxSmem / (w.smem_eval + 1024));
+  if (occ < 1) occ = 1;
+  if (occ > 8) occ = 8;
+  w.grid_eval = sms * occ;
+  w.grid_predict = sms * occ;
+  if (window <= 0) window = kDefaultWindow;
+  size_t tasks = B * (size_t)(S > 0 ? S : 1);
+  if ((size_t)window > tasks) window = (int)(tasks > 0 ? tasks : 1);
+  w.window = window;
+  w.max_rounds = max_rounds > 0 ? max_rounds : kDefaultMaxRounds;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  w.xs = take(NT * 8); w.y = take(NT * 8); w.al = take(NT * 8);
+  w.lam = take(B * (size_t)b.n_bands * 8);
+  w.stats = take(B * 6 * 8);
+  w.pstatus = take(B * 4);
+  w.slots = take((size_t)window * sizeof(FgState));
+  w.slot_task = take((size_t)window * 8);
+  w.slot_nev = take((size_t)window * 4);
+  w.f_out = take((size_t)window * 8);
+  w.g_out = take((size_t)window * FG_MAXP * 8);
+  w.list = take((size_t)window * 2 * 4);
+  w.counts = take(((size_t)w.max_rounds + 2) * 4);
+  w.next_task = take(8);
+  w.run_f = take(tasks * 8);
+  w.run_x = take(tasks * (size_t)FG_MAXP * 8);
+  w.run_nev = take(tasks * 4);
+  w.run_end = take(tasks * 4);
+  w.starts = take((size_t)(S > 0 ? S : 1) * FG_MAXP * 8);
+  w.gA_stride = w.globalA ? np * ld : 0;
+  w.gA = take((size_t)w.grid_eval * w.gA_stride * 8);
+  w.gV_stride = np * GP_QC;
+  w.gV = take((size_t)w.grid_predict * w.gV_stride * 8);
+  w.total = o;
+}
+
+template <class T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct PrepArgs {
+  int64_t B;
+  const int64_t* offsets;
+  const double *t, *flux, *ferr, *loglam;
+  const int32_t* band;
+  int n_bands, use_err;
+  double alpha0;
+  double *xs, *y, *al, *lam, *stats;
+  int32_t* pstatus;
+};
+
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
+  __shared__ double red[kPrepThreads];
+  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
+    const int64_t o = a.offsets[cu];
+    const int n = (int)(a.offsets[cu + 1] - o);
+    int st = gp_prepare_curve(c, n, a.t + o, a.flux + o, a.ferr + o, a.band + o, a.loglam, a.n_bands, a.use_err, a.alpha0, a.xs + o,
+                              a.y + o, a.al + o, a.lam + cu * a.n_bands, a.stats + cu * 6, red);
+    if (threadIdx.x == 0) a.pstatus[cu] = st;
+    __syncthreads();
+  }
+}
+
+struct CurveTable {
+  const int64_t* offsets;
+  const double *xs, *y, *al, *lam, *stats;
+  const int32_t* band;
+  const int32_t* pstatus;
+  int n_bands;
+};
+
+__device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t cu) {
+  const int64_t o = t.offsets[cu];
+  GpCurveView v;
+  v.n = (int)(t.offsets[cu + 1] - o);
+  v.xs = t.xs + o; v.band = t.band + o; v.y = t.y + o; v.al = t.al + o; v.lam = t.lam + cu * t.n_bands;
+  return v;
+}
+
+template <bool kGlobalA>
+__device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
+  if (!kGlobalA) return gp_carve(smem, n, kEvalThreads);
+  // vectors in shared memory, the matrix in this CTA's global slab (stays in L2)
+  GpSmem s;
+  s.np = gp_pad(n);
+  s.ld = gp_ld(s.np);
+  s.A = gA + (size_t)blockIdx.x * gA_stride;
+  double* p = smem;
+  s.u = p; p += s.np; s.v = p; p += s.np; s.y = p; p += s.np; s.al = p; p += s.np; s.alpha = p; p += s.np; s.z = p; p += s.np;
+  s.dinv = p; p += (s.np / GP_NB) * 16;
+  s.panel = p; p += s.np * GP_NB;
+  s.red = p; p += kEvalThreads;
+  s.flag = (int*)p;
+  return s;
+}
+
+// LML + gradient at one theta per curve (fixed-theta parity entry point)
+template <bool kGlobalA>
+__global__ void __launch_bounds__(kEvalThreads) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
+                                                            double* gA, size_t gA_stride) {
+  extern __shared__ __align__(16) double smem[];
+  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  for (int64_t cu = blockIdx.x; cu < B; cu += gridDim.x) {
+    if (tab.pstatus[cu] != 0) {
+      if (threadIdx.x == 0) { lml[cu] = NAN; for (int k = 0; k < P; ++k) grad[cu * P + k] = NAN; }
+      continue;
+    }
+    GpCurveView cv = curve_view(tab, cu);
+    GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
+    double l, g[4];
+    bool ok;
+    gp_eval_lml_grad(c, cv, theta + cu * P, s, l, g, ok);
+    if (threadIdx.x == 0) { lml[cu] = l; for (int k = 0; k < 4; ++k) grad[cu * P + k] = g[k]; }
+    __syncthreads();
+  }
+}
+
+struct FitDev {
+  CurveTable tab;
+  FgOptions opt;
+  int64_t n_tasks;
+  int S, P, window;
+  FgState* slots;
+  int64_t* slot_task;
+  int32_t* slot_nev;
+  double *f_out, *g_out;
+  int32_t* list;     // [2][window]
+  int32_t* counts;   // [max_rounds + 2]
+  unsigned long long* next_task;
+  double *run_f, *run_x;
+  int32_t *run_nev, *run_end;
+  const double* starts;
+  double* gA;
+  size_t gA_stride;
+};
+
+// pulls the next runnable task into `slot`; returns false when the queue is empty
+__device__ bool acquire_task(const FitDev& d, int slot) {
+  for (;;) {
+    unsigned long long nt = atomicAdd(d.next_task, 1ULL);
+    if (nt >= (unsigned long long)d.n_tasks) { d.slot_task[slot] = -1; d.slots[slot].task = FG_TASK_IDLE; return false; }
+    const int64_t cu = (int64_t)(nt / d.S);
+    const int st = (int)(nt % d.S);
+    if (d.tab.pstatus[cu] != 0) {   // unusable curve: record and move on
+      d.run_f[nt] = INFINITY;
+      for (int k = 0; k < d.P; ++k) d.run_x[nt * FG_MAXP + k] = d.starts[st * FG_MAXP + k];
+      d.run_nev[nt] = 0;
+      d.run_end[nt] = FG_TASK_ABNORMAL;
+      continue;
+    }
+    lbfgsb_init(d.slots[slot], d.opt, d.starts + st * FG_MAXP);
+    d.slot_task[slot] = (int64_t)nt;
+    d.slot_nev[slot] = 0;
+    return true;
+  }
+}
+
+__global__ void fit_init_kernel(FitDev d) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= d.window) return;
+  if (acquire_task(d, slot)) {
+    const int pos = atomicAdd(&d.counts[0], 1);
+    d.list[pos] = slot;
+  }
+}
+
+template <bool kGlobalA>
+__global__ void __launch_bounds__(kEvalThreads) fit_eval_kernel(FitDev d, int round) {
+  extern __shared__ __align__(16) double smem[];
+  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  const int count = d.counts[round];
+  const int32_t* list = d.list + (size_t)(round & 1) * d.window;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int slot = list[i];
+    const int64_t cu = d.slot_task[slot] / d.S;
+    GpCurveView cv = curve_view(d.tab, cu);
+    GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
+    double l, g[4];
+    bool ok;
+    gp_eval_lml_grad(c, cv, d.slots[slot].x, s, l, g, ok);
+    if (threadIdx.x == 0) {
+      d.f_out[slot] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
+      for (int k = 0; k < 4; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void fit_step_kernel(FitDev d, int round) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.counts[round]) return;
+  const int slot = d.list[(size_t)(round & 1) * d.window + i];
+  FgState& st = d.slots[slot];
+  lbfgsb_advance(st, d.opt, d.f_out[slot], d.g_out + slot * FG_MAXP);
+  d.slot_nev[slot] += 1;
+  bool live = true;
+  if (fg_task_done(st.task)) {
+    const int64_t task = d.slot_task[slot];
+    d.run_f[task] = st.f;
+    for (int k = 0; k < FG_MAXP; ++k) d.run_x[task * FG_MAXP + k] = st.x[k];
+    d.run_nev[task] = d.slot_nev[slot];
+    d.run_end[task] = st.task;
+    live = acquire_task(d, slot);
+  }
+  if (live) {
+    const int pos = atomicAdd(&d.counts[round + 1], 1);
+    d.list[(size_t)((round + 1) & 1) * d.window + pos] = slot;
+  }
+}
+
+// Runs that were still alive when the round cap hit: record where they are.
+__global__ void fit_flush_kernel(FitDev d) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= d.window) return;
+  const int64_t task = d.slot_task[slot];
+  FgState& st = d.slots[slot];
+  if (task < 0 || fg_task_done(st.task)) return;
+  const bool in_search = (st.task == FG_TASK_LNSRCH);
+  d.run_f[task] = in_search ? st.fold : INFINITY;
+  for (int k = 0; k < FG_MAXP; ++k) d.run_x[task * FG_MAXP + k] = in_search ? st.t[k] : st.x[k];
+  d.run_nev[task] = d.slot_nev[slot];
+  d.run_end[task] = FG_TASK_MAXITER;
+}
+
+struct SelectArgs {
+  int64_t B;
+  int S, P;
+  const double *run_f, *run_x;
+  const int32_t *run_nev, *run_end, *pstatus;
+  double lo[FG_MAXP], hi[FG_MAXP];
+  double *theta_opt, *lml_opt, *run_lml, *run_theta;
+  int32_t *n_eval, *status;
+};
+
+__global__ void fit_select_kernel(SelectArgs a) {
+  const int64_t cu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (cu >= a.B) return;
+  int best = 0, nev = 0;
+  double fb = a.run_f[cu * a.S];
+  for (int s = 0; s < a.S; ++s) {
+    const double f = a.run_f[cu * a.S + s];
+    if (f < fb) { fb = f; best = s; }   // np.argmin: first minimum (_gpr.py:336-340)
+    nev += a.run_nev[cu * a.S + s];
+    if (a.run_lml) a.run_lml[cu * a.S + s] = -f;
+    if (a.run_theta)
+      for (int k = 0; k < a.P; ++k) a.run_theta[(cu * a.S + s) * a.P + k] = a.run_x[(cu * a.S + s) * FG_MAXP + k];
+  }
+  int st = 0;
+  if (a.pstatus[cu] != 0) st |= FULU_GP_STATUS_BAD_INPUT;
+  const int end = a.run_end[cu * a.S + best];
+  if (end == FG_TASK_ABNORMAL || end == FG_TASK_MAXITER) st |= FULU_GP_STATUS_NOT_CONVERGED;
+  for (int k = 0; k < a.P; ++k) {
+    const double th = a.run_x[(cu * a.S + best) * FG_MAXP + k];
+    a.theta_opt[cu * a.P + k] = th;
+    const double tol = 1e-8 + 1e-5 * fabs(th);   // np.isclose(bound, theta)  (kernels.py:436-464)
+    if (fabs(a.lo[k] - th) <= tol || fabs(a.hi[k] - th) <= tol) st |= FULU_GP_STATUS_AT_BOUND;
+  }
+  a.lml_opt[cu] = -fb;
+  a.n_eval[cu] = nev;
+  a.status[cu] = st;
+}
+
+struct PredictArgs {
+  CurveTable tab;
+  int64_t B;
+  int P;
+  const double* theta;
+  int n_obs;                  // grid mode if > 0
+  const double *t_min, *t_max;
+  const double* t_raw;        // raw times (for default t_min/t_max)
+  const int64_t* q_offsets;   // explicit mode
+  const double* q_t;
+  const int32_t* q_band;
+  double *mean, *stdv, *lml;
+  int32_t* status;
+  double *gA, *gV;
+  size_t gA_stride, gV_stride;
+};
+
+template <bool kGlobalA>
+__global__ void __launch_bounds__(kPredictThreads) predict_kernel(PredictArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double tlim[2];
+  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  double* V = a.gV + (size_t)blockIdx.x * a.gV_stride;
+  for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
+    GpCurveView cv = curve_view(a.tab, cu);
+    GpQuery qd;
+    int64_t out0;
+    if (a.n_obs > 0) {
+      qd.n_obs = a.n_obs; qd.m = a.n_obs * a.tab.n_bands; qd.qt = nullptr; qd.qband = nullptr;
+      out0 = cu * (int64_t)qd.m;
+      if (a.t_min && a.t_max) { qd.t_min = a.t_min[cu]; qd.t_max = a.t_max[cu]; }
+      else {
+        // default: the curve's own time span
+        if (threadIdx.x == 0) {
+          const double* tr = a.t_raw + a.tab.offsets[cu];
+          double lo = tr[0], hi = tr[0];
+          for (int i = 1; i < cv.n; ++i) { lo = fmin(lo, tr[i]); hi = fmax(hi, tr[i]); }
+          tlim[0] = lo; tlim[1] = hi;
+        }
+        __syncthreads();
+        qd.t_min = tlim[0]; qd.t_max = tlim[1];
+      }
+    } else {
+      out0 = a.q_offsets[cu];
+      qd.n_obs = 0; qd.m = (int)(a.q_offsets[cu + 1] - out0); qd.qt = a.q_t + out0; qd.qband = a.q_band + out0;
+      qd.t_min = qd.t_max = 0.0;
+    }
+    int st = a.tab.pstatus[cu] != 0 ? FULU_GP_STATUS_BAD_INPUT : 0;
+    double l = NAN;
+    if (st) {
+      for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }
+    } else {
+      GpSmem s = carve<kGlobalA>(smem, a.gA, a.gA_stride, cv.n);
+      st = gp_predict_curve(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, s, V, a.mean + out0, a.stdv + out0, l);
+    }
+    if (threadIdx.x == 0) {
+      if (a.status) a.status[cu] = st;
+      if (a.lml) a.lml[cu] = l;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void export_stats_kernel(int64_t B, const double* stats, double* scaler, double* ynorm) {
+  const int64_t cu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (cu >= B) return;
+  if (scaler) for (int k = 0; k < 4; ++k) scaler[cu * 4 + k] = stats[cu * 6 + k];
+  if (ynorm) { ynorm[cu * 2] = stats[cu * 6 + 4]; ynorm[cu * 2 + 1] = stats[cu * 6 + 5]; }
+}
+
+__global__ void copy_status_kernel(int64_t B, const int32_t* src, int32_t* dst) {
+  const int64_t cu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (cu < B) dst[cu] = src[cu] ? FULU_GP_STATUS_BAD_INPUT : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ FP64 peak probes
+__global__ void __launch_bounds__(256) dfma_probe(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void __launch_bounds__(256) dmma_probe(double* out, int iters, double a, double b) {
+  double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+  double fa = a + threadIdx.x * 1e-9, fb = b;
+  for (int i = 0; i < iters; ++i) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(fa), "d"(fb));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(fa), "d"(fb));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2[0]), "+d"(c2[1]) : "d"(fa), "d"(fb));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c3[0]), "+d"(c3[1]) : "d"(fa), "d"(fb));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (c0[0] + c0[1]) + (c1[0] + c1[1]) + (c2[0] + c2[1]) + (c3[0] + c3[1]);
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+#define CU_TRY(x)                          \
+  do {                                     \
+    cudaError_t e__ = (x);                 \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+
+int check_batch(const fulu_gp_batch* b, int P) {
+  if (!b) return FULU_GP_E_BADARG;
+  if (b->n_curves < 0 || b->n_obs_total < 0 || b->n_bands < 1 || b->n_bands > FULU_GP_MAX_BANDS) return FULU_GP_E_BADARG;
+  if (b->n_curves > 0 && (!b->offsets || !b->t || !b->flux || !b->flux_err || !b->band || !b->loglam)) return FULU_GP_E_BADARG;
+  if (b->kernel != FULU_GP_KERNEL_RBF_WHITE) return FULU_GP_E_UNSUPPORTED;
+  if (P != 4) return FULU_GP_E_UNSUPPORTED;
+  if (b->n_max < 1 && b->n_curves > 0) return FULU_GP_E_BADARG;
+  return 0;
+}
+
+int run_prep(const fulu_gp_batch& b, const WsLayout& w, void* ws, int sms, cudaStream_t st, CurveTable& tab) {
+  PrepArgs a;
+  a.B = b.n_curves; a.offsets = b.offsets; a.t = b.t; a.flux = b.flux; a.ferr = b.flux_err; a.loglam = b.loglam; a.band = b.band;
+  a.n_bands = b.n_bands; a.use_err = b.use_err; a.alpha0 = b.alpha0;
+  a.xs = at<double>(ws, w.xs); a.y = at<double>(ws, w.y); a.al = at<double>(ws, w.al); a.lam = at<double>(ws, w.lam);
+  a.stats = at<double>(ws, w.stats); a.pstatus = at<int32_t>(ws, w.pstatus);
+  int64_t grid = b.n_curves < (int64_t)sms * 16 ? b.n_curves : (int64_t)sms * 16;
+  if (grid > 0) prep_kernel<<<(unsigned)grid, kPrepThreads, 0, st>>>(a);
+  CU_TRY(cudaGetLastError());
+  tab.offsets = b.offsets; tab.xs = a.xs; tab.y = a.y; tab.al = a.al; tab.lam = a.lam; tab.stats = a.stats; tab.band = b.band;
+  tab.pstatus = a.pstatus; tab.n_bands = b.n_bands;
+  return 0;
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int fulu_gp_abi_version(void) { return FULU_GP_ABI_VERSION; }
+
+const char* fulu_gp_strerror(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case FULU_GP_E_BADARG: return "fulu_gp: bad argument";
+    case FULU_GP_E_WORKSPACE: return "fulu_gp: workspace too small";
+    case FULU_GP_E_UNSUPPORTED: return "fulu_gp: kernel family or size not supported by this build";
+    case FULU_GP_E_NOCUDA: return "fulu_gp: no CUDA device";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "fulu_gp: unknown error";
+  }
+}
+
+int fulu_gp_workspace_bytes(const fulu_gp_batch* batch, int32_t n_params, int32_t n_starts, int32_t window, size_t* bytes) {
+  int rc = check_batch(batch, n_params);
+  if (rc) return rc;
+  if (!bytes) return FULU_GP_E_BADARG;
+  DeviceInfo di;
+  if (device_info(di)) return FULU_GP_E_NOCUDA;
+  WsLayout w;
+  plan(*batch, n_params, n_starts, window, 0, di.sms, w);
+  *bytes = w.total;
+  return 0;
+}
+
+int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad, double* scaler,
+                      double* ynorm, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_batch(batch, n_params);
+  if (rc) return rc;
+  if (batch->n_curves == 0) return 0;
+  if (!theta || !lml || !grad || !workspace) return FULU_GP_E_BADARG;
+  DeviceInfo di;
+  if (device_info(di)) return FULU_GP_E_NOCUDA;
+  WsLayout w;
+  plan(*batch, n_params, 1, 1, 0, di.sms, w);
+  if (workspace_bytes < w.total) return FULU_GP_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  CurveTable tab;
+  rc = run_prep(*batch, w, workspace, di.sms, st, tab);
+  if (rc) return rc;
+  const int64_t B = batch->n_curves;
+  unsigned grid = (unsigned)(B < w.grid_eval ? B : w.grid_eval);
+  if (w.globalA) {
+    rc = set_smem(lml_kernel<true>, w.smem_eval);
+    if (rc) return rc;
+    lml_kernel<true><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, at<double>(workspace, w.gA), w.gA_stride);
+  } else {
+    rc = set_smem(lml_kernel<false>, w.smem_eval);
+    if (rc) return rc;
+    lml_kernel<false><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, nullptr, 0);
+  }
+  CU_TRY(cudaGetLastError());
+  const unsigned g1 = (unsigned)((B + 255) / 256);
+  if (scaler || ynorm) export_stats_kernel<<<g1, 256, 0, st>>>(B, tab.stats, scaler, ynorm);
+  if (status) copy_status_kernel<<<g1, 256, 0, st>>>(B, tab.pstatus, status);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,
+                      double* lml_opt, int32_t* n_eval, int32_t* status, double* run_lml, double* run_theta, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!opt) return FULU_GP_E_BADARG;
+  int rc = check_batch(batch, opt->n_params);
+  if (rc) return rc;
+  if (batch->n_curves == 0) return 0;
+  if (!theta_starts || !theta_opt || !lml_opt || !n_eval || !status || !workspace) return FULU_GP_E_BADARG;
+  if (opt->n_starts < 1 || opt->m < 1 || opt->m > FG_LBFGS_M) return FULU_GP_E_BADARG;
+  DeviceInfo di;
+  if (device_info(di)) return FULU_GP_E_NOCUDA;
+  WsLayout w;
+  plan(*batch, opt->n_params, opt->n_starts, opt->window, opt->max_rounds, di.sms, w);
+  if (workspace_bytes < w.total) return FULU_GP_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  CurveTable tab;
+  rc = run_prep(*batch, w, workspace, di.sms, st, tab);
+  if (rc) return rc;
+
+  const int P = opt->n_params, S = opt->n_starts;
+  FitDev d;
+  d.tab = tab;
+  d.opt.n = P; d.opt.m = opt->m; d.opt.maxiter = opt->maxiter; d.opt.maxfun = opt->maxfun; d.opt.maxls = opt->maxls; d.opt.pad = 0;
+  d.opt.factr = opt->factr; d.opt.pgtol = opt->pgtol;
+  for (int k = 0; k < FG_MAXP; ++k) { d.opt.lo[k] = k < P ? opt->lower[k] : 0.0; d.opt.hi[k] = k < P ? opt->upper[k] : 0.0; }
+  d.n_tasks = batch->n_curves * (int64_t)S;
+  d.S = S; d.P = P; d.window = w.window;
+  d.slots = at<FgState>(workspace, w.slots);
+  d.slot_task = at<int64_t>(workspace, w.slot_task);
+  d.slot_nev = at<int32_t>(workspace, w.slot_nev);
+  d.f_out = at<double>(workspace, w.f_out);
+  d.g_out = at<double>(workspace, w.g_out);
+  d.list = at<int32_t>(workspace, w.list);
+  d.counts = at<int32_t>(workspace, w.counts);
+  d.next_task = at<unsigned long long>(workspace, w.next_task);
+  d.run_f = at<double>(workspace, w.run_f);
+  d.run_x = at<double>(workspace, w.run_x);
+  d.run_nev = at<int32_t>(workspace, w.run_nev);
+  d.run_end = at<int32_t>(workspace, w.run_end);
+  double* starts = at<double>(workspace, w.starts);
+  d.starts = starts;
+  d.gA = at<double>(workspace, w.gA);
+  d.gA_stride = w.gA_stride;
+
+  // starts [S,P] -> padded [S,FG_MAXP] (device-to-device strided copy)
+  CU_TRY(cudaMemsetAsync(starts, 0, (size_t)S * FG_MAXP * 8, st));
+  CU_TRY(cudaMemcpy2DAsync(starts, FG_MAXP * 8, theta_starts, (size_t)P * 8, (size_t)P * 8, S, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(cudaMemsetAsync(d.counts, 0, ((size_t)w.max_rounds + 2) * 4, st));
+  CU_TRY(cudaMemsetAsync(d.next_task, 0, 8, st));
+  fit_init_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
+  CU_TRY(cudaGetLastError());
+  if (w.globalA) rc = set_smem(fit_eval_kernel<true>, w.smem_eval);
+  else rc = set_smem(fit_eval_kernel<false>, w.smem_eval);
+  if (rc) return rc;
+
+  const unsigned step_grid = (unsigned)((w.window + 127) / 128);
+  constexpr int kMaxGroup = 16;
+  const bool prof = opt->profile != nullptr;
+  cudaEvent_t ev[3 * kMaxGroup];
+  if (prof)
+    for (int i = 0; i < 3 * kMaxGroup; ++i) CU_TRY(cudaEventCreate(&ev[i]));
+  double eval_ms = 0.0, step_ms = 0.0;
+  int round = 0, group = 4;
+  bool finished = false;
+  while (round < w.max_rounds) {
+    int upto = round + group;
+    if (upto > w.max_rounds) upto = w.max_rounds;
+    const int first = round;
+    for (; round < upto; ++round) {
+      const int e = 3 * (round - first);
+      if (prof) cudaEventRecord(ev[e], st);
+      if (w.globalA) fit_eval_kernel<true><<<w.grid_eval, kEvalThreads, w.smem_eval, st>>>(d, round);
+      else fit_eval_kernel<false><<<w.grid_eval, kEvalThreads, w.smem_eval, st>>>(d, round);
+      if (prof) cudaEventRecord(ev[e + 1], st);
+      fit_step_kernel<<<step_grid, 128, 0, st>>>(d, round);
+      if (prof) cudaEventRecord(ev[e + 2], st);
+    }
+    CU_TRY(cudaGetLastError());
+    int32_t remaining = 0;
+    CU_TRY(cudaMemcpyAsync(&remaining, d.counts + round, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (prof)
+      for (int r = first; r < round; ++r) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[3 * (r - first)], ev[3 * (r - first) + 1]);
+        cudaEventElapsedTime(&b, ev[3 * (r - first) + 1], ev[3 * (r - first) + 2]);
+        eval_ms += a;
+        step_ms += b;
+      }
+    if (remaining == 0) { finished = true; break; }
+    if (group < kMaxGroup) group *= 2;
+  }
+  if (prof) {
+    for (int i = 0; i < 3 * kMaxGroup; ++i) cudaEventDestroy(ev[i]);
+    double* pr = opt->profile;
+    pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = 2.0 * round + 4.0; pr[4] = w.window; pr[5] = w.grid_eval;
+    pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0;
+  }
+  if (!finished) {
+    fit_flush_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
+    CU_TRY(cudaGetLastError());
+  }
+  SelectArgs sa;
+  sa.B = batch->n_curves; sa.S = S; sa.P = P;
+  sa.run_f = d.run_f; sa.run_x = d.run_x; sa.run_nev = d.run_nev; sa.run_end = d.run_end; sa.pstatus = tab.pstatus;
+  for (int k = 0; k < FG_MAXP; ++k) { sa.lo[k] = d.opt.lo[k]; sa.hi[k] = d.opt.hi[k]; }
+  sa.theta_opt = theta_opt; sa.lml_opt = lml_opt; sa.run_lml = run_lml; sa.run_theta = run_theta; sa.n_eval = n_eval; sa.status = status;
+  fit_select_kernel<<<(unsigned)((batch->n_curves + 127) / 128), 128, 0, st>>>(sa);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int predict_common(const fulu_gp_batch* batch, int32_t n_params, PredictArgs& a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_batch(batch, n_params);
+  if (rc) return rc;
+  if (batch->n_curves == 0) return 0;
+  if (!a.theta || !a.mean || !a.stdv || !workspace) return FULU_GP_E_BADARG;
+  DeviceInfo di;
+  if (device_info(di)) return FULU_GP_E_NOCUDA;
+  WsLayout w;
+  plan(*batch, n_params, 1, 1, 0, di.sms, w);
+  if (workspace_bytes < w.total) return FULU_GP_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  CurveTable tab;
+  rc = run_prep(*batch, w, workspace, di.sms, st, tab);
+  if (rc) return rc;
+  a.tab = tab; a.B = batch->n_curves; a.P = n_params; a.t_raw = batch->t;
+  a.gA = at<double>(workspace, w.gA); a.gV = at<double>(workspace, w.gV);
+  a.gA_stride = w.gA_stride; a.gV_stride = w.gV_stride;
+  unsigned grid = (unsigned)(a.B < w.grid_predict ? a.B : w.grid_predict);
+  if (w.globalA) {
+    rc = set_smem(predict_kernel<true>, w.smem_predict);
+    if (rc) return rc;
+    predict_kernel<true><<<grid, kPredictThreads, w.smem_predict, st>>>(a);
+  } else {
+    rc = set_smem(predict_kernel<false>, w.smem_predict);
+    if (rc) return rc;
+    predict_kernel<false><<<grid, kPredictThreads, w.smem_predict, st>>>(a);
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int fulu_gp_predict_grid_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const double* t_min, const double* t_max,
+                               int32_t n_obs, double* mean, double* std, double* lml, int32_t* status, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (n_obs < 1) return FULU_GP_E_BADARG;
+  PredictArgs a = {};
+  a.theta = theta; a.n_obs = n_obs; a.t_min = t_min; a.t_max = t_max; a.mean = mean; a.stdv = std; a.lml = lml; a.status = status;
+  return predict_common(batch, n_params, a, workspace, workspace_bytes, stream);
+}
+
+int fulu_gp_predict_points_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const int64_t* q_offsets, const double* q_t,
+                                 const int32_t* q_band, int32_t q_max, double* mean, double* std, int32_t* status, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  (void)q_max;
+  if (!q_offsets || !q_t || !q_band) return FULU_GP_E_BADARG;
+  PredictArgs a = {};
+  a.theta = theta; a.n_obs = 0; a.q_offsets = q_offsets; a.q_t = q_t; a.q_band = q_band; a.mean = mean; a.stdv = std; a.status = status;
+  return predict_common(batch, n_params, a, workspace, workspace_bytes, stream);
+}
+
+int fulu_gp_fp64_peak(int32_t mode, int32_t iters, double* tflops, void* stream) {
+  if (!tflops || iters < 1) return FULU_GP_E_BADARG;
+  DeviceInfo di;
+  if (device_info(di)) return FULU_GP_E_NOCUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = di.sms * 8;
+  double* out = nullptr;
+  CU_TRY(cudaMalloc(&out, (size_t)blocks * 256 * 8));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU_TRY(cudaEventRecord(e0, st));
+    if (mode == 0) dfma_probe<<<blocks, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
+    else dmma_probe<<<blocks, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
+    CU_TRY(cudaEventRecord(e1, st));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    // DFMA: 8 FMA per thread per iteration; DMMA m8n8k4: 4 x 256 FMA per warp per iteration
+    const double fma_count = mode == 0 ? (double)blocks * 256.0 * 8.0 * iters : (double)blocks * 8.0 * 4.0 * 256.0 * iters;
+    const double tf = 2.0 * fma_count / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+"""Host side of the batched GP path: device-resident ragged batches and the calls into libfulu_gp.
+
+PyTorch is plumbing here (device memory, streams, pinned host buffers, torch.distributed for sharding); every
+floating-point operation of the path runs in the hand-written CUDA kernels behind the C ABI (include/fulu_gp.h).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi
+from .datasets import CurveBatch
+
+LOG_BOUND = math.log(1e5)  # sklearn's default (1e-5, 1e5) hyperparameter bounds, log space (kernels.py:1236,1366,1511)
+KERNEL_RBF_WHITE = 0
+
+STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NOT_CONVERGED, STATUS_AT_BOUND, STATUS_NEG_VARIANCE = 1, 2, 4, 8, 16
+
+
+@dataclass
+class KernelSpec:
+    """The covariance family and its optimiser configuration (what sklearn derives from the kernel object)."""
+
+    family: int = KERNEL_RBF_WHITE
+    theta0: np.ndarray = None  # start 0 = the kernel's own hyperparameters (log)
+    lower: np.ndarray = None
+    upper: np.ndarray = None
+    n_restarts: int = 5  # fulu/gp_aug.py:69
+    seed: int = 42  # fulu/gp_aug.py:69 random_state
+
+    def __post_init__(self):
+        p = 4
+        if self.theta0 is None:
+            self.theta0 = np.zeros(p)
+        if self.lower is None:
+            self.lower = np.full(p, -LOG_BOUND)
+        if self.upper is None:
+            self.upper = np.full(p, LOG_BOUND)
+        self.theta0 = np.asarray(self.theta0, np.float64)
+        self.lower = np.asarray(self.lower, np.float64)
+        self.upper = np.asarray(self.upper, np.float64)
+
+    @property
+    def n_params(self):
+        return len(self.theta0)
+
+    def start_points(self):
+        """theta0, then n_restarts draws of RandomState(seed).uniform(lower, upper) (_gpr.py:251,312-333)."""
+        rng = np.random.RandomState(self.seed)
+        pts = [self.theta0.copy()]
+        for _ in range(self.n_restarts):
+            pts.append(rng.uniform(self.lower, self.upper))
+        return np.ascontiguousarray(np.array(pts), np.float64)
+
+
+def kernel_spec_from_sklearn(kernel):
+    """Map an sklearn kernel object onto a supported family; anything else is refused (there is no CPU fallback)."""
+    if kernel is None:
+        return KernelSpec()
+    names = lambda k: type(k).__name__
+    try:
+        ok = (names(kernel) == "Sum" and names(kernel.k1) == "Product" and names(kernel.k1.k1) == "ConstantKernel"
+              and names(kernel.k1.k2) == "RBF" and names(kernel.k2) == "WhiteKernel" and np.size(kernel.k1.k2.length_scale) == 2)
+        fixed = any(isinstance(b, str) for b in (kernel.k1.k1.constant_value_bounds, kernel.k1.k2.length_scale_bounds,
+                                                 kernel.k2.noise_level_bounds)) if ok else False
+    except AttributeError:
+        ok, fixed = False, False
+    if not ok or fixed:
+        raise NotImplementedError(
+            "fulu_b200 supports kernel = ConstantKernel * RBF([l_t, l_lambda]) + WhiteKernel (the fulu default) on the GPU path; "
+            f"got {kernel!r}")
+    b = np.asarray(kernel.bounds, np.float64)
+    return KernelSpec(KERNEL_RBF_WHITE, np.asarray(kernel.theta, np.float64), b[:, 0].copy(), b[:, 1].copy())
+
+
+def _require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _capi.FuluGpError("fulu_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+class DeviceBatch:
+    """A ragged CSR batch of light curves resident in HBM (layout of SURVEY 8b / include/fulu_gp.h)."""
+
+    def __init__(self, offsets, t, flux, flux_err, band, loglam, n_max, use_err=False, alpha0=1e-10, family=KERNEL_RBF_WHITE):
+        self.offsets, self.t, self.flux, self.flux_err, self.band, self.loglam = offsets, t, flux, flux_err, band, loglam
+        self.n_curves = int(offsets.numel() - 1)
+        self.n_obs_total = int(t.numel())
+        self.n_max = int(n_max)
+        self.n_bands = int(loglam.numel())
+        self.use_err = bool(use_err)
+        self.device = t.device
+        c = _capi.Batch()
+        c.n_curves, c.n_obs_total, c.n_max, c.n_bands = self.n_curves, self.n_obs_total, max(self.n_max, 1), self.n_bands
+        c.offsets, c.t, c.flux, c.flux_err = offsets.data_ptr(), t.data_ptr(), flux.data_ptr(), flux_err.data_ptr()
+        c.band, c.loglam = band.data_ptr(), loglam.data_ptr()
+        c.kernel, c.use_err, c.alpha0 = family, int(use_err), alpha0
+        self.c = c
+
+    @staticmethod
+    def from_host(b: CurveBatch, device=None, use_err=False, pinned=None):
+        """H2D copy of a host batch.  `pinned`: optional dict of pinned staging tensors (see HostStaging)."""
+        device = _require_cuda(device)
+        n_max = int(b.lengths().max()) if b.n_curves else 0
+        if pinned is None:
+            src = dict(offsets=torch.from_numpy(b.offsets), t=torch.from_numpy(b.t), flux=torch.from_numpy(b.flux),
+                       flux_err=torch.from_numpy(b.flux_err), band=torch.from_numpy(b.band), loglam=torch.from_numpy(b.loglam))
+        else:
+            src = pinned
+        dev = {k: v.to(device, non_blocking=True) for k, v in src.items()}
+        return DeviceBatch(dev["offsets"], dev["t"], dev["flux"], dev["flux_err"], dev["band"], dev["loglam"], n_max, use_err)
+
+    def h2d_bytes(self):
+        return sum(x.numel() * x.element_size() for x in (self.offsets, self.t, self.flux, self.flux_err, self.band, self.loglam))
+
+
+def pin_batch(b: CurveBatch):
+    """Pinned host staging copy of a CurveBatch (what a production ingest thread would fill)."""
+    out = {}
+    for k in ("offsets", "t", "flux", "flux_err", "band", "loglam"):
+        a = torch.from_numpy(getattr(b, k))
+        p = torch.empty(a.shape, dtype=a.dtype, pin_memory=True)
+        p.copy_(a)
+        out[k] = p
+    return out
+
+
+class GPEngine:
+    """Thin owner of the library handle, the workspace and the stream for one GPU."""
+
+    def __init__(self, device=None):
+        self.lib = _capi.load()
+        self.device = _require_cuda(device)
+        self._ws = None
+        self.launches = 0  # evaluation rounds are counted by the library caller below
+
+    # ---- plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, batch, n_params, n_starts, window):
+        need = ctypes.c_size_t()
+        _capi.check(self.lib.fulu_gp_workspace_bytes(ctypes.byref(batch.c), n_params, n_starts, window, ctypes.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = None
+            self._ws = torch.empty(int(need.value * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _p(x):
+        return None if x is None else ctypes.c_void_p(x.data_ptr())
+
+    def _new(self, *shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ---- a5: LML + gradient at fixed hyperparameters
+    def lml(self, batch: DeviceBatch, theta):
+        """theta [B,P] (device) -> dict(lml [B], grad [B,P], scaler [B,4], ynorm [B,2], status [B])."""
+        with torch.cuda.device(self.device):
+            B, P = batch.n_curves, theta.shape[1]
+            theta = theta.to(self.device, torch.float64).contiguous()
+            out = dict(lml=self._new(B), grad=self._new(B, P), scaler=self._new(B, 4), ynorm=self._new(B, 2), status=self._new(B, dtype=torch.int32))
+            ws = self._workspace(batch, P, 1, 1)
+            _capi.check(self.lib.fulu_gp_lml_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(out["lml"]), self._p(out["grad"]),
+                                                   self._p(out["scaler"]), self._p(out["ynorm"]), self._p(out["status"]), self._p(ws),
+                                                   ws.numel(), self._stream()))
+            return out
+
+    # ---- a6: optimiser
+    def fit(self, batch: DeviceBatch, spec: KernelSpec = None, window=0, max_rounds=0, factr=1e7, pgtol=1e-5, maxiter=15000,
+            maxfun=15000, maxls=20, m=10, return_runs=False, profile=False):
+        """S = 1 + n_restarts L-BFGS-B runs per curve -> dict(theta [B,P], lml [B], n_eval [B], status [B])."""
+        spec = spec or KernelSpec()
+        with torch.cuda.device(self.device):
+            B, P = batch.n_curves, spec.n_params
+            starts_h = spec.start_points()
+            S = starts_h.shape[0]
+            starts = torch.from_numpy(starts_h).to(self.device)
+            o = _capi.FitOptions()
+            o.n_params, o.n_starts, o.m, o.maxiter, o.maxfun, o.maxls, o.window, o.max_rounds = P, S, m, maxiter, maxfun, maxls, window, max_rounds
+            o.factr, o.pgtol = factr, pgtol
+            for k in range(P):
+                o.lower[k], o.upper[k] = spec.lower[k], spec.upper[k]
+            out = dict(theta=self._new(B, P), lml=self._new(B), n_eval=self._new(B, dtype=torch.int32), status=self._new(B, dtype=torch.int32))
+            if return_runs:
+                out["run_lml"] = self._new(B, S)
+                out["run_theta"] = self._new(B, S, P)
+            prof = (ctypes.c_double * 8)() if profile else None
+            if profile:
+                o.profile = ctypes.cast(prof, ctypes.POINTER(ctypes.c_double))
+            ws = self._workspace(batch, P, S, window)
+            _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts), self._p(out["theta"]),
+                                                   self._p(out["lml"]), self._p(out["n_eval"]), self._p(out["status"]),
+                                                   self._p(out.get("run_lml")), self._p(out.get("run_theta")), self._p(ws), ws.numel(),
+                                                   self._stream()))
+            if profile:
+                keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a")
+                out["profile"] = {k: float(prof[i]) for i, k in enumerate(keys)}
+            return out
+
+    # ---- a7-a9: augmentation grid / arbitrary points
+    def predict_grid(self, batch: DeviceBatch, theta, n_obs, t_min=None, t_max=None):
+        """-> dict(mean [B,n_bands,n_obs], std [...], lml [B], status [B]); t_min/t_max [B] default to each curve's span."""
+        with torch.cuda.device(self.device):
+            B, P = batch.n_curves, theta.shape[1]
+            theta = theta.to(self.device, torch.float64).contiguous()
+            if (t_min is None) != (t_max is None):
+                raise ValueError("give both t_min and t_max or neither")
+            if t_min is not None:
+                t_min = torch.as_tensor(t_min, dtype=torch.float64).to(self.device).contiguous().reshape(B)
+                t_max = torch.as_tensor(t_max, dtype=torch.float64).to(self.device).contiguous().reshape(B)
+            out = dict(mean=self._new(B, batch.n_bands, n_obs), std=self._new(B, batch.n_bands, n_obs), lml=self._new(B),
+                       status=self._new(B, dtype=torch.int32))
+            ws = self._workspace(batch, P, 1, 1)
+            _capi.check(self.lib.fulu_gp_predict_grid_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(t_min), self._p(t_max), n_obs,
+                                                            self._p(out["mean"]), self._p(out["std"]), self._p(out["lml"]),
+                                                            self._p(out["status"]), self._p(ws), ws.numel(), self._stream()))
+            return out
+
+    def predict_points(self, batch: DeviceBatch, theta, q_offsets, q_t, q_band):
+        """Ragged queries: curve i at q_t/q_band[q_offsets[i]:q_offsets[i+1]] -> dict(mean [sum M], std [sum M], status [B])."""
+        with torch.cuda.device(self.device):
+            B, P = batch.n_curves, theta.shape[1]
+            theta = theta.to(self.device, torch.float64).contiguous()
+            q_offsets = torch.as_tensor(q_offsets, dtype=torch.int64).to(self.device).contiguous()
+            q_t = torch.as_tensor(q_t, dtype=torch.float64).to(self.device).contiguous()
+            q_band = torch.as_tensor(q_band, dtype=torch.int32).to(self.device).contiguous()
+            M = int(q_t.numel())
+            out = dict(mean=self._new(M), std=self._new(M), status=self._new(B, dtype=torch.int32))
+            ws = self._workspace(batch, P, 1, 1)
+            _capi.check(self.lib.fulu_gp_predict_points_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(q_offsets), self._p(q_t),
+                                                              self._p(q_band), 0, self._p(out["mean"]), self._p(out["std"]),
+                                                              self._p(out["status"]), self._p(ws), ws.numel(), self._stream()))
+            return out
+
+    def fp64_peak(self, mode=0, iters=20000):
+        """Measured FP64 TFLOP/s of a register-resident DFMA (mode 0) or DMMA (mode 1) loop on this GPU."""
+        with torch.cuda.device(self.device):
+            v = ctypes.c_double()
+            _capi.check(self.lib.fulu_gp_fp64_peak(mode, iters, ctypes.byref(v), self._stream()))
+            return v.value
+
+
+# ------------------------------------------------------------------------------------------------ batched entry point
+N_BUCKETS = (32, 64, 100, 128, 156, 256, 512, 1024, 2048, 4096)
+
+
+@dataclass
+class AugmentResult:
+    flux_aug: np.ndarray  # [B, n_bands, n_obs]
+    flux_err_aug: np.ndarray  # [B, n_bands, n_obs]
+    theta: np.ndarray  # [B, P]
+    lml: np.ndarray  # [B]
+    n_eval: np.ndarray  # [B]
+    status: np.ndarray  # [B]
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+
+def bucket_curves(lengths, buckets=N_BUCKETS):
+    """Group curve indices by padded length so one kernel launch sees similar N (cost ~ N^3)."""
+    lengths = np.asarray(lengths)
+    which = np.searchsorted(np.asarray(buckets), lengths, side="left")
+    return [(int(buckets[min(k, len(buckets) - 1)]), np.nonzero(which == k)[0]) for k in np.unique(which)]
+
+
+def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use_err=False, spec: KernelSpec = None, engine: GPEngine = None,
+                      device=None, window=0, pinned=None):
+    """The batched ragged entry point: GP fit + augmentation for every curve of `curves` (host arrays in, host arrays out).
+
+    Equivalent to, for each curve i:  aug = fulu.GaussianProcessesAugmentation(passband2lam, use_err=use_err).fit(t, flux, flux_err, band);
+    aug.augmentation(t_min[i], t_max[i], n_obs)  (t_min/t_max default to the curve's own span).
+    """
+    engine = engine or GPEngine(device)
+    spec = spec or KernelSpec()
+    B, nb, P = curves.n_curves, curves.n_bands, spec.n_params
+    res = AugmentResult(np.empty((B, nb, n_obs)), np.empty((B, nb, n_obs)), np.empty((B, P)), np.empty(B), np.zeros(B, np.int32), np.zeros(B, np.int32))
+    lengths = curves.lengths()
+    groups = bucket_curves(lengths) if B else []
+    single = len(groups) == 1 and len(groups[0][1]) == B
+    for _, idx in groups:
+        sub = curves if single else curves.take(idx)
+        db = DeviceBatch.from_host(sub, engine.device, use_err=use_err, pinned=pinned if single else None)
+        fit = engine.fit(db, spec, window=window)
+        tmn = None if t_min is None else np.asarray(t_min, np.float64)[idx]
+        tmx = None if t_max is None else np.asarray(t_max, np.float64)[idx]
+        pred = engine.predict_grid(db, fit["theta"], n_obs, tmn, tmx)
+        res.flux_aug[idx] = pred["mean"].cpu().numpy()
+        res.flux_err_aug[idx] = pred["std"].cpu().numpy()
+        res.theta[idx] = fit["theta"].cpu().numpy()
+        res.lml[idx] = fit["lml"].cpu().numpy()
+        res.n_eval[idx] = fit["n_eval"].cpu().numpy()
+        res.status[idx] = (fit["status"] | pred["status"]).cpu().numpy()
+        res.h2d_bytes += db.h2d_bytes()
+        res.d2h_bytes += len(idx) * (2 * nb * n_obs * 8 + P * 8 + 8 + 8)
+    return res

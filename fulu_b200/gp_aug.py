@@ -1,0 +1,170 @@
+"""Drop-in for fulu.GaussianProcessesAugmentation (reference: fulu/gp_aug.py:10-108, fulu/_base_aug.py:23-114).
+
+Same constructor, ``fit`` / ``predict`` / ``augmentation`` signatures, argument meaning, return types and error behaviour; the
+work runs on the GPU through libfulu_gp (one-curve batches).  For many curves use :func:`fulu_b200.fit_augment_batch`.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+
+from .datasets import CurveBatch
+from .engine import (STATUS_AT_BOUND, STATUS_BAD_INPUT, STATUS_NEG_VARIANCE, STATUS_NOT_CONVERGED, STATUS_NOT_PD, DeviceBatch, GPEngine,
+                     kernel_spec_from_sklearn)
+
+
+class ConvergenceWarning(UserWarning):
+    """Raised where sklearn raises sklearn.exceptions.ConvergenceWarning (optimiser ended abnormally / theta on a bound)."""
+
+
+def add_log_lam(passband, passband2lam):
+    """fulu/_base_aug.py:9-11 (raises KeyError for an unknown passband, like the reference)."""
+    return np.array([passband2lam[i] for i in passband])
+
+
+def create_aug_data(t_min, t_max, passband_ids, n_obs=1000):
+    """Band-major augmentation grid, fulu/_base_aug.py:14-20."""
+    t = []
+    passband = []
+    for band in passband_ids:
+        t += list(np.linspace(t_min, t_max, n_obs))
+        passband += [band] * n_obs
+    return np.array(t), np.array(passband)
+
+
+class _Scaler:
+    """What the reference exposes as ``aug.ss`` (a fitted StandardScaler): mean_, scale_, transform."""
+
+    def __init__(self, mean, scale):
+        self.mean_, self.scale_ = np.asarray(mean), np.asarray(scale)
+        self.var_ = self.scale_ ** 2
+
+    def transform(self, X):
+        return (np.asarray(X, np.float64) - self.mean_) / self.scale_
+
+
+class _KernelView:
+    def __init__(self, theta, bounds):
+        self.theta, self.bounds = np.asarray(theta), bounds
+
+    def __repr__(self):
+        c, lt, ll, s2 = np.exp(self.theta)
+        return f"{np.sqrt(c):.3g}**2 * RBF(length_scale=[{lt:.3g}, {ll:.3g}]) + WhiteKernel(noise_level={s2:.3g})"
+
+
+class _FittedGP:
+    """What the reference exposes as ``aug.reg``: kernel_.theta, log_marginal_likelihood_value_, log_marginal_likelihood()."""
+
+    def __init__(self, owner, theta, lml, n_eval):
+        self._owner = owner
+        self.kernel_ = _KernelView(theta, np.c_[owner._spec.lower, owner._spec.upper])
+        self.log_marginal_likelihood_value_ = float(lml)
+        self.n_eval_ = int(n_eval)
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        if theta is None:
+            if eval_gradient:
+                raise ValueError("Gradient can only be evaluated for theta!=None")
+            return self.log_marginal_likelihood_value_
+        o = self._owner
+        th = torch.as_tensor(np.asarray(theta, np.float64).reshape(1, -1))
+        out = o._engine.lml(o._batch, th)
+        lml = float(out["lml"].cpu()[0])
+        return (lml, out["grad"].cpu().numpy()[0]) if eval_gradient else lml
+
+
+class GaussianProcessesAugmentation:
+    """
+    Light Curve Augmentation based on Gaussian Processes Regression (GPU, batched kernels underneath).
+
+    Parameters:
+    -----------
+    passband2lam : dict
+        A dictionary, where key is a passband ID and value is Log10 of its wave length.
+    kernel : kernel object from sklearn, optional
+        Only the reference's default family ``C(1.0) * RBF([1.0, 1.0]) + WhiteKernel()`` runs on the GPU path (its initial values and
+        bounds are honoured); other kernels raise NotImplementedError.
+    use_err : bool
+        Flag responsible for using flux error by GP Regressor.
+    """
+
+    def __init__(self, passband2lam, kernel=None, use_err=False, device=None):
+        self.passband2lam = passband2lam
+        self.t_train = None
+        self.flux_train = None
+        self.flux_err_train = None
+        self.passband_train = None
+        self.ss = None
+        self.reg = None
+        self.kernel = kernel
+        self.use_err = use_err
+        self._spec = kernel_spec_from_sklearn(kernel)
+        self._device = device
+        self._engine = None
+        self._batch = None
+        self._theta = None
+
+    # -- helpers
+    def _band_index(self, passband):
+        lut = {k: i for i, k in enumerate(self.passband2lam)}
+        return np.array([lut[b] for b in passband], dtype=np.int32)
+
+    def fit(self, t, flux, flux_err, passband):
+        """Fit an augmentation model (same arguments as fulu/gp_aug.py:37-78)."""
+        self.t_train = np.asarray(t)
+        self.flux_train = np.asarray(flux)
+        self.flux_err_train = np.asarray(flux_err)
+        self.passband_train = np.asarray(passband)
+        t = np.array(t, dtype=np.float64).reshape(-1)
+        flux = np.array(flux, dtype=np.float64).reshape(-1)
+        flux_err = np.array(flux_err, dtype=np.float64).reshape(-1)
+        add_log_lam(np.array(passband), self.passband2lam)  # KeyError for unknown bands, as in the reference
+        band = self._band_index(np.array(passband))
+        if not (np.all(np.isfinite(t)) and np.all(np.isfinite(flux))):
+            raise ValueError("Input contains NaN or infinity.")  # sklearn validate_data (_gpr.py:257-265)
+        loglam = np.array([self.passband2lam[k] for k in self.passband2lam], dtype=np.float64)
+        if self._engine is None:
+            self._engine = GPEngine(self._device)
+        host = CurveBatch(np.array([0, len(t)], np.int64), t, flux, flux_err, band, loglam)
+        self._batch = DeviceBatch.from_host(host, self._engine.device, use_err=self.use_err)
+        fit = self._engine.fit(self._batch, self._spec)
+        status = int(fit["status"].cpu()[0])
+        if status & STATUS_BAD_INPUT:
+            raise ValueError("Input contains NaN, infinity or an unusable noise term.")
+        theta = fit["theta"].cpu().numpy()[0]
+        self._theta = fit["theta"]
+        stats = self._engine.lml(self._batch, fit["theta"])
+        self.ss = _Scaler(stats["scaler"].cpu().numpy()[0, [0, 2]], stats["scaler"].cpu().numpy()[0, [1, 3]])
+        self.reg = _FittedGP(self, theta, float(fit["lml"].cpu()[0]), int(fit["n_eval"].cpu()[0]))
+        self.reg._y_train_mean, self.reg._y_train_std = (float(v) for v in stats["ynorm"].cpu().numpy()[0])
+        if status & STATUS_NOT_CONVERGED:
+            warnings.warn("lbfgs failed to converge: abnormal termination in the line search or iteration limit reached.", ConvergenceWarning)
+        if status & STATUS_AT_BOUND:
+            warnings.warn("The optimal value found for a hyperparameter is close to its bound; changing the bound might give a better fit.",
+                          ConvergenceWarning)
+        return self
+
+    def predict(self, t, passband):
+        """Apply the augmentation model to the given observation time moments (fulu/gp_aug.py:80-108)."""
+        if self._batch is None:
+            raise RuntimeError("fit must be called before predict")
+        t = np.array(t, dtype=np.float64).reshape(-1)
+        passband = np.array(passband)
+        add_log_lam(passband, self.passband2lam)
+        band = self._band_index(passband)
+        out = self._engine.predict_points(self._batch, self._theta, np.array([0, len(t)], np.int64), t, band)
+        status = int(out["status"].cpu()[0])
+        if status & STATUS_NOT_PD:
+            raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix. Try gradually increasing the 'alpha' "
+                                        "parameter of your GaussianProcessRegressor estimator.")  # _gpr.py:353-361
+        if status & STATUS_NEG_VARIANCE:
+            warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")  # _gpr.py:485-491
+        return out["mean"].cpu().numpy(), out["std"].cpu().numpy()
+
+    def augmentation(self, t_min, t_max, n_obs=100):
+        """The light curve augmentation (fulu/_base_aug.py:88-114): band-major grid of n_obs points per passband."""
+        t_aug, passband_aug = create_aug_data(t_min, t_max, tuple(self.passband2lam), n_obs)
+        flux_aug, flux_err_aug = self.predict(t_aug, passband_aug)
+        return t_aug, flux_aug, flux_err_aug, passband_aug

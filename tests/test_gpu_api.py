@@ -1,0 +1,187 @@
+"""The drop-in class and the batched entry point: the reference's own test (tests/test_aug.py:52-67) plus edge cases."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_test_aug_with_sample_data():
+    """Port of /root/reference/tests/test_aug.py:52-67 for the GP parametrisations (default and use_err=True)."""
+    from numpy.testing import assert_allclose
+
+    from fulu_b200 import GaussianProcessesAugmentation, datasets
+
+    for init_kwargs in ({}, dict(use_err=True)):
+        n_aug = 100
+        passband2lam, *lc = datasets.reference_test_fixture()
+        n_band = len(passband2lam)
+        t, *_ = lc
+        aug = GaussianProcessesAugmentation(passband2lam, **init_kwargs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            aug_fit = aug.fit(*lc)
+        assert aug_fit is aug, ".fit() must return self"
+        t_aug, flux_aug, flux_err_aug, passband_aug = aug.augmentation(t.min(), t.max(), n_aug)
+        assert_allclose(t_aug, np.tile(np.linspace(t.min(), t.max(), n_aug), n_band))
+        assert flux_aug.size == n_aug * n_band
+        assert np.all(flux_aug >= 0.0)
+        assert flux_err_aug.size == n_aug * n_band
+        assert np.all(flux_err_aug >= 0.0)
+        assert passband_aug.size == n_aug * n_band
+        assert set(passband_aug) == set(passband2lam)
+
+
+@pytest.mark.parametrize("name", ["readme", "csv34299", "csv34299_err", "testfixture"])
+def test_drop_in_class_matches_reference_outputs(name):
+    from fulu_b200 import ConvergenceWarning, GaussianProcessesAugmentation
+
+    g = load_golden(name)
+    p2l = {i: float(v) for i, v in enumerate(g["loglam"])}
+    aug = GaussianProcessesAugmentation(p2l, use_err=bool(g["use_err"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", ConvergenceWarning)
+        aug.fit(g["t"], g["flux"], g["flux_err"], g["band"])
+    assert aug.reg.log_marginal_likelihood_value_ >= float(g["lml_star"]) - 1e-6
+    np.testing.assert_allclose(aug.ss.mean_, g["x_mean"], rtol=1e-14)
+    np.testing.assert_allclose(aug.ss.scale_, g["x_scale"], rtol=1e-12)
+    t_aug, f, e, pb = aug.augmentation(float(g["t_min"]), float(g["t_max"]), int(g["n_obs"]))
+    np.testing.assert_array_equal(t_aug, g["t_aug"])
+    np.testing.assert_array_equal(pb, g["band_aug"])
+    # after optimisation theta agrees to ~1e-5, so the curves agree to ~1e-4 of the flux scale
+    ystd = float(g["y_std"])
+    if np.max(np.abs(aug.reg.kernel_.theta - g["theta_star"])) < 1e-3:
+        assert relerr(f, g["flux_aug"], floor=ystd) < 1e-3
+        assert relerr(e, g["flux_err_aug"], floor=1e-2 * ystd) < 1e-2
+    # reg shim: LML at a given theta, with gradient
+    l, gr = aug.reg.log_marginal_likelihood(g["thetas"][1], eval_gradient=True)
+    assert abs(l - g["lml"][1]) <= 1e-9 * abs(g["lml"][1])
+    assert gr.shape == (4,)
+    # predict at arbitrary points == the same points of the grid
+    fp, ep = aug.predict(t_aug[::7], pb[::7])
+    np.testing.assert_allclose(fp, f[::7], rtol=1e-12, atol=1e-12 * ystd)
+    np.testing.assert_allclose(ep, e[::7], rtol=1e-10)
+
+
+def test_string_passband_keys_and_key_error():
+    from fulu_b200 import GaussianProcessesAugmentation, datasets
+
+    p2l, t, flux, err, pb = datasets.readme_example()
+    aug = GaussianProcessesAugmentation(p2l)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        aug.fit(t, flux, err, pb)
+    t_aug, f, e, pba = aug.augmentation(t.min(), t.max(), 10)
+    assert list(pba[:10]) == ["u"] * 10 and f.shape == (30,)
+    with pytest.raises(KeyError):
+        aug.fit(t, flux, err, np.array(["q"] * len(t)))
+    with pytest.raises(ValueError):
+        aug.fit(t, np.where(np.arange(len(t)) == 3, np.nan, flux), err, pb)
+
+
+def test_batched_entry_point_equals_per_curve_and_is_batch_independent():
+    import fulu_b200
+    from fulu_b200 import datasets
+
+    eng = fulu_b200.GPEngine()
+    hb = datasets.ztf_like(40, first=200, n_lo=20, n_hi=180)  # ragged: several N buckets incl. the global-memory one
+    res = fulu_b200.fit_augment_batch(hb, n_obs=32, engine=eng)
+    assert res.flux_aug.shape == (40, 2, 32) and np.all(np.isfinite(res.flux_aug)) and np.all(res.flux_err_aug >= 0)
+    # every curve alone gives bit-identical results: no cross-curve coupling, deterministic reductions
+    for i in (0, 7, 23, 39):
+        one = fulu_b200.fit_augment_batch(hb.slice(i, i + 1), n_obs=32, engine=eng)
+        np.testing.assert_array_equal(one.theta[0], res.theta[i])
+        np.testing.assert_array_equal(one.flux_aug[0], res.flux_aug[i])
+        np.testing.assert_array_equal(one.flux_err_aug[0], res.flux_err_aug[i])
+        assert one.n_eval[0] == res.n_eval[i]
+    # small window (forces slot recycling) does not change anything either
+    res2 = fulu_b200.fit_augment_batch(hb, n_obs=32, engine=eng, window=7)
+    np.testing.assert_array_equal(res2.theta, res.theta)
+    np.testing.assert_array_equal(res2.lml, res.lml)
+
+
+def test_edge_cases():
+    import fulu_b200
+    from fulu_b200 import CurveBatch, DeviceBatch
+
+    eng = fulu_b200.GPEngine()
+    loglam = np.log10([3751.36, 4741.64, 6173.23])
+    rng = np.random.default_rng(3)
+    curves = [
+        (np.array([5.0]), np.array([2.0]), np.array([0.1]), np.array([1])),                           # N = 1
+        (np.array([1.0, 2.0]), np.array([2.0, 3.0]), np.array([0.1, 0.1]), np.array([0, 2])),         # N = 2
+        (np.arange(12.0), 5 + np.sin(np.arange(12.0)), np.full(12, 0.2), np.full(12, 1)),             # single band
+        (np.repeat(np.arange(6.0), 2), np.repeat(3 + np.cos(np.arange(6.0)), 2) + rng.normal(0, 0.01, 12), np.full(12, 0.1),
+         np.tile([0, 0], 6)),                                                                         # duplicate (t, band) rows
+        (np.arange(10.0), np.full(10, 7.0), np.full(10, 0.3), rng.integers(0, 3, 10)),                # constant flux
+        (np.arange(8.0), np.array([1, 2, np.nan, 4, 5, 6, 7, 8.0]), np.full(8, 0.1), rng.integers(0, 3, 8)),  # NaN flux
+        (np.arange(8.0), -50 + 10 * np.sin(np.arange(8.0)), np.zeros(8), rng.integers(0, 3, 8)),      # negative flux, zero errors
+    ]
+    hb = CurveBatch.from_curves(curves, loglam)
+    res = fulu_b200.fit_augment_batch(hb, n_obs=5, engine=eng)
+    assert res.status[5] & 1 and np.all(np.isnan(res.flux_aug[5]))                 # bad input flagged, batch not poisoned
+    ok = [0, 1, 2, 3, 4, 6]
+    assert np.all(np.isfinite(res.flux_aug[ok])) and np.all(res.flux_err_aug[ok] >= 0)
+    np.testing.assert_allclose(res.flux_aug[4], 7.0, atol=1e-6)                    # constant flux predicts the constant
+    assert np.any(res.flux_aug[6] < 0)                                             # GP output is not clipped at zero
+    assert abs(res.theta[2][2]) < 1e-12                                            # single band: wavelength scale is a flat direction
+    res_e = fulu_b200.fit_augment_batch(hb, n_obs=5, use_err=True, engine=eng)
+    assert res_e.status[4] & 1                                                     # constant flux + use_err: alpha = inf -> flagged
+    assert np.all(np.isfinite(res_e.flux_aug[[0 + 1, 2, 3, 6]]))
+    # empty batch
+    empty = CurveBatch.from_curves([], loglam)
+    r0 = fulu_b200.fit_augment_batch(empty, n_obs=5, engine=eng)
+    assert r0.flux_aug.shape == (0, 3, 5)
+    # compare the small cases with sklearn
+    from oracle.fulu_sklearn_port import SklearnGPAugmentation
+
+    p2l = {i: float(v) for i, v in enumerate(loglam)}
+    for i in (1, 2, 3, 6):
+        t, f, e, b = hb.curve(i)
+        ref = SklearnGPAugmentation(p2l)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref.fit(t, f, e, b)
+        assert res.lml[i] >= ref.reg.log_marginal_likelihood_value_ - 1e-6, i
+
+
+def test_invariances_at_full_size():
+    """Size-independent properties on the headline shape (N=100, 6 bands, M=768): observation order and a time shift of the
+    whole curve do not change LML / predictions beyond rounding."""
+    import fulu_b200
+    from fulu_b200 import CurveBatch, DeviceBatch, datasets
+
+    eng = fulu_b200.GPEngine()
+    hb = datasets.plasticc_like(256, first=5000)
+    rng = np.random.default_rng(0)
+    perm_curves, shift_curves = [], []
+    for i in range(hb.n_curves):
+        t, f, e, b = hb.curve(i)
+        p = rng.permutation(len(t))
+        perm_curves.append((t[p], f[p], e[p], b[p]))
+        shift_curves.append((t + 1000.0, f, e, b))
+    theta = torch.tensor(np.tile([0.2, -1.5, 2.5, -4.5], (hb.n_curves, 1)))
+    base = DeviceBatch.from_host(hb, eng.device)
+    a = eng.lml(base, theta)
+    pa = eng.predict_grid(base, theta, 128)
+    b_ = eng.lml(DeviceBatch.from_host(CurveBatch.from_curves(perm_curves, hb.loglam), eng.device), theta)
+    pb_ = eng.predict_grid(DeviceBatch.from_host(CurveBatch.from_curves(perm_curves, hb.loglam), eng.device), theta, 128)
+    c_ = eng.lml(DeviceBatch.from_host(CurveBatch.from_curves(shift_curves, hb.loglam), eng.device), theta)
+    np.testing.assert_allclose(b_["lml"].cpu().numpy(), a["lml"].cpu().numpy(), rtol=1e-11)
+    np.testing.assert_allclose(c_["lml"].cpu().numpy(), a["lml"].cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(pb_["std"].cpu().numpy(), pa["std"].cpu().numpy(), rtol=1e-9)
+    ystd = a["ynorm"].cpu().numpy()[:, 1][:, None, None]
+    assert np.max(np.abs(pb_["mean"].cpu().numpy() - pa["mean"].cpu().numpy()) / ystd) < 1e-10
+    # gradient vs central finite differences of the LML (sklearn's own test_lml_gradient pattern)
+    h = 1e-5
+    for k in range(4):
+        d = torch.zeros(4, dtype=torch.float64)
+        d[k] = h
+        up = eng.lml(base, theta + d)["lml"].cpu().numpy()
+        dn = eng.lml(base, theta - d)["lml"].cpu().numpy()
+        fd = (up - dn) / (2 * h)
+        np.testing.assert_allclose(a["grad"].cpu().numpy()[:, k], fd, rtol=2e-5, atol=2e-5)
