@@ -1,23 +1,29 @@
 // Block-level FP64 GP algebra: one CTA owns one light curve's N x N kernel matrix in shared memory.
 //
-// Functions here are written against a tiny "block context" (tid, nthr, sync()) so the very same code
-// can be executed by a CUDA thread block (DevCtx, gp_kernels.cu) and, for tests without a GPU, by a
-// pool of host threads with a barrier (tests/_host/host_gp_block.cpp).  Nothing in here is a CPU
-// fallback of the product: the host build exists only under tests/.
+// Functions here are written against a small "block context" (tid/lane/warp, sync(), warp_sync(), mma(), shfl_xor()) so the
+// very same code is executed by a CUDA thread block (DevCtx in gp_kernels.cu: __syncthreads, mma.sync.m8n8k4.f64, shuffles)
+// and, for tests without a GPU, by host threads with barriers standing in for the warp/block primitives
+// (tests/_host/host_gp_block.cpp).  Nothing in here is a CPU fallback of the product: the host build exists only under tests/.
 //
 // What is computed (reference lines: sklearn/gaussian_process/_gpr.py:583-651, kernels.py:1558-1585):
 //   K   = c * exp(-1/2 |x_i/l - x_j/l|^2) + (s2 + alpha_i) I            (a4)
-//   L   = chol(K)                       blocked right-looking, NB = 4    (a5, LAPACK dpotrf in the reference)
+//   L   = chol(K)                       blocked right-looking, NB = 8    (a5; LAPACK dpotrf in the reference)
 //   X   = L^-1                          blocked in-place triangular inverse (replaces the identity-RHS dpotrs)
-//   a   = X^T (X y), LML = -1/2 y.a - sum log L_ii - N/2 log 2pi
-//   K^-1 = X^T X is never stored: each 4x4 tile is reduced straight into the gradient traces
+//   a   = X^T z, z = L^-1 y;  LML = -1/2 z.z - sum log L_ii - N/2 log 2pi
+//   K^-1 = X^T X is never stored: each 8x8 tile is reduced straight into the gradient traces
 //   g_k = 1/2 sum_ij (a_i a_j - K^-1_ij) dK_ij/dtheta_k                  (Eq. 5.9)
 //
-// Storage: A is column-major with leading dimension ld (odd, so rows and columns are both conflict-free
-// for 64-bit accesses).  The strict upper triangle keeps K for the gradient pass while the lower
-// triangle is overwritten by L and then L^-1.  N is padded to a multiple of 4 (np) with an identity block,
-// and four extra rows np..np+3 are appended below the square: row np carries y^T, so the panel solves and
-// trailing updates of the Cholesky turn it into z^T = (L^-1 y)^T for free (bordered factorisation).
+// Every O(N^3) piece runs on 8x8 tiles through the FP64 tensor-core instruction (DMMA m8n8k4; on B200 it sustains the full
+// FP64 rate with an eighth of the issue slots of a DFMA loop, measured 37.2 vs 33.9 TFLOP/s).  The inherently serial part of
+// the Cholesky - the chain of N reciprocal square roots down the diagonal - is done by one thread on an 8x8 block *while* the
+// other warps apply the previous panel to the rest of the trailing matrix (lookahead), so a step costs two barriers.
+//
+// Storage: A is column-major, np = N padded to a multiple of 8 (identity padding), np columns of ld rows with
+// ld = np + 12 (= 4 mod 8): lane (g, t) of a fragment load touches row g/column t (or row t/column g), i.e. 64-bit bank
+// (g + 4t) mod 16 - conflict free for both orientations.  The strict upper triangle keeps K for the gradient pass while the lower
+// triangle is overwritten by L and then L^-1.  Rows np..np+7 are a border tile-row: row np carries y^T, so the panel solves and
+// trailing updates of the Cholesky turn it into z^T = (L^-1 y)^T for free (bordered factorisation); after that the border
+// rows are reused as the 8-wide panel scratch of the triangular inverse.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -30,7 +36,7 @@
 #define GP_HD inline
 #endif
 
-#define GP_NB 4
+#define GP_NB 8
 #define GP_LOG_2PI 1.8378770664093453
 
 struct GpCurveView {
@@ -43,88 +49,74 @@ struct GpCurveView {
 };
 
 struct GpSmem {
-  double* A;      // np columns of ld >= np + 4 rows
+  double* A;      // np columns of ld rows
   double* u;      // np   x_i0 / l_t
   double* v;      // np   x_i1 / l_lambda
   double* y;      // np
   double* al;     // np
   double* alpha;  // np   K^-1 y
   double* z;      // np   L^-1 y
-  double* dinv;   // (np/4) * 16   inverses of the 4x4 diagonal blocks of L
-  double* panel;  // np * 4
-  double* red;    // reduction scratch, >= max(nthr, 64)
+  double* rdiag;  // np   1 / L_ii
+  double* red;    // reduction scratch, 64 doubles
   int* flag;      // [0] = Cholesky breakdown
   int np, ld;
 };
 
 GP_HD int gp_pad(int n) { return (n + GP_NB - 1) / GP_NB * GP_NB; }
-GP_HD int gp_ld(int np) { return (np + GP_NB) | 1; }
-
-// number of doubles of shared memory needed for a curve of n observations
-GP_HD size_t gp_smem_doubles(int n, int nthr) {
-  size_t np = (size_t)gp_pad(n), ld = (size_t)gp_ld((int)np);
-  size_t red = nthr > 64 ? nthr : 64;
-  return np * ld + 6 * np + (np / GP_NB) * 16 + np * GP_NB + red + 2;
+GP_HD int gp_ld(int np) { return np + GP_NB + 4; }
+GP_HD size_t gp_vec_doubles(int np) { return 7 * (size_t)np + 64 + 2; }
+// doubles of shared memory needed for a curve of n observations (matrix + vectors)
+GP_HD size_t gp_smem_doubles(int n) {
+  const size_t np = (size_t)gp_pad(n);
+  return np * (size_t)gp_ld((int)np) + gp_vec_doubles((int)np);
 }
 
-GP_DEV GpSmem gp_carve(double* base, int n, int nthr) {
+// vectors at `vec`, matrix at `mat` (shared memory, or a per-CTA global slab for long curves)
+GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
   GpSmem s;
   s.np = gp_pad(n);
   s.ld = gp_ld(s.np);
-  double* p = base;
-  s.A = p; p += (size_t)s.np * s.ld;
+  s.A = mat;
+  double* p = vec;
   s.u = p; p += s.np;
   s.v = p; p += s.np;
   s.y = p; p += s.np;
   s.al = p; p += s.np;
   s.alpha = p; p += s.np;
   s.z = p; p += s.np;
-  s.dinv = p; p += (s.np / GP_NB) * 16;
-  s.panel = p; p += s.np * GP_NB;
-  s.red = p; p += (nthr > 64 ? nthr : 64);
+  s.rdiag = p; p += s.np;
+  s.red = p; p += 64;
   s.flag = (int*)p;
   return s;
 }
 
+// column permutation of the accumulator fragment: register c0 of lane (g, t) holds tile column t, c1 holds column 4 + t
+// (instead of 2t, 2t+1), so that accumulator loads/stores hit banks (g + 4t) as well.  B-fragment lane g must then supply
+// tile column gp_perm(g).
+GP_HD int gp_perm(int g) { return (g & 1) ? 4 + (g >> 1) : (g >> 1); }
+
 // ---------------------------------------------------------------------------------------------- reductions
-#if defined(__CUDA_ARCH__)
+// Sum of v[k] over the block (result in every thread).  Warp shuffles for the column reduction, one smem hop across warps.
 template <class Ctx, int K>
 GP_DEV void gp_block_sum(Ctx& c, double (&v)[K], double* red) {
-  // column reductions by warp shuffles, then one shared-memory hop across warps
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double x = v[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    for (int o = 16; o > 0; o >>= 1) x += c.shfl_xor(x, o);
     v[k] = x;
   }
-  const int lane = c.tid & 31, warp = c.tid >> 5, nwarp = (c.nthr + 31) >> 5;
   c.sync();
-  if (lane == 0)
-    for (int k = 0; k < K; ++k) red[warp * K + k] = v[k];
+  if (c.lane == 0)
+    for (int k = 0; k < K; ++k) red[c.warp * K + k] = v[k];
   c.sync();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double x = 0.0;
-    for (int w = 0; w < nwarp; ++w) x += red[w * K + k];
+    for (int w = 0; w < c.nwarp; ++w) x += red[w * K + k];
     v[k] = x;
   }
   c.sync();
 }
-#else
-template <class Ctx, int K>
-GP_DEV void gp_block_sum(Ctx& c, double (&v)[K], double* red) {
-  for (int k = 0; k < K; ++k) {
-    c.sync();
-    red[c.tid] = v[k];
-    c.sync();
-    double x = 0.0;
-    for (int t = 0; t < c.nthr; ++t) x += red[t];
-    v[k] = x;
-  }
-  c.sync();
-}
-#endif
 
 // ---------------------------------------------------------------------------------------------- load + assemble
 template <class Ctx>
@@ -142,67 +134,113 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, double
   if (c.tid == 0) s.flag[0] = 0;
 }
 
-// K into the lower triangle (to be factored) and, if keep_upper, a copy into the strict upper triangle.
+// K into the lower triangle (to be factored), a copy into the strict upper triangle if keep_upper, and the border rows.
+// One warp per column, lanes down the rows: conflict-free stores for the lower triangle.
 template <class Ctx>
 GP_DEV void gp_assemble(Ctx& c, const GpSmem& s, int n, double cst, double s2, bool keep_upper) {
   const int np = s.np, ld = s.ld;
-  for (int idx = c.tid; idx < np * np; idx += c.nthr) {
-    const int j = idx / np, i = idx - j * np;
-    if (i > j) {
-      double val = 0.0;
-      if (i < n) {
-        const double du = s.u[i] - s.u[j], dv = s.v[i] - s.v[j];
-        val = cst * exp(-0.5 * (du * du + dv * dv));
+  for (int j = c.warp; j < np; j += c.nwarp) {
+    const double uj = s.u[j], vj = s.v[j];
+    double* col = s.A + (size_t)j * ld;
+    for (int i = j + c.lane; i < np + GP_NB; i += 32) {
+      double val;
+      if (i == j) {
+        val = (j < n) ? (cst + s2) + s.al[j] : 1.0;    // White on the diagonal, then K[diag] += alpha (_gpr.py:589)
+      } else if (i < np) {
+        val = 0.0;
+        if (i < n) {   // j < i < n
+          const double du = s.u[i] - uj, dv = s.v[i] - vj;
+          val = cst * exp(-0.5 * (du * du + dv * dv));
+        }
+        if (keep_upper) s.A[j + (size_t)i * ld] = val;
+      } else {
+        val = (i == np) ? s.y[j] : 0.0;                // border: y^T then seven zero rows
       }
-      s.A[i + j * ld] = val;
-      if (keep_upper) s.A[j + i * ld] = val;
-    } else if (i == j) {
-      s.A[i + i * ld] = (i < n) ? (cst + s2) + s.al[i] : 1.0;   // White on the diagonal, then K[diag] += alpha (_gpr.py:589)
+      col[i] = val;
     }
-  }
-  // border rows: y^T then three zero rows
-  for (int idx = c.tid; idx < np * GP_NB; idx += c.nthr) {
-    const int j = idx / GP_NB, r = idx - j * GP_NB;
-    s.A[(np + r) + j * ld] = (r == 0) ? s.y[j] : 0.0;
   }
 }
 
 // ---------------------------------------------------------------------------------------------- Cholesky
-// 4x4 diagonal block: a (lower) -> L in place, li = L^-1 (lower, row-major [r*4+c]).  false on a non-positive pivot.
-GP_DEV bool gp_chol4(double a[4][4], double* li) {
+// 8x8 diagonal block at A[j0.., j0..] (lower) -> L in place, rdiag[j0..] = 1/L_jj.  Division-free: r = rsqrt(d), L_jj = d r.
+// Executed by ONE thread; everything is unrolled into registers so the scheduler starts column j+1's rsqrt as early as possible.
+GP_DEV bool gp_chol8(double* A, int ld, int j0, double* rdiag) {
+  double a[8][8];
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+    for (int r = cc; r < 8; ++r) a[r][cc] = A[(j0 + r) + (size_t)(j0 + cc) * ld];
   bool ok = true;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     double d = a[j][j];
+    if (!(d > 0.0) || !(d < 1.0e300)) { ok = false; d = 1.0; }
+#if defined(__CUDA_ARCH__)
+    const double r = rsqrt(d);
+#else
+    const double r = 1.0 / sqrt(d);
+#endif
+    a[j][j] = d * r;
+    rdiag[j0 + j] = r;
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= a[j][k] * a[j][k];
-    if (!(d > 0.0)) { ok = false; d = 1.0; }
-    d = sqrt(d);
-    a[j][j] = d;
-    const double r = 1.0 / d;
+    for (int i = j + 1; i < 8; ++i) a[i][j] *= r;
 #pragma unroll
-    for (int i = j + 1; i < 4; ++i) {
-      double v = a[i][j];
+    for (int cc = j + 1; cc < 8; ++cc)
 #pragma unroll
-      for (int k = 0; k < j; ++k) v -= a[i][k] * a[j][k];
-      a[i][j] = v * r;
-    }
+      for (int i = cc; i < 8; ++i) a[i][cc] -= a[i][j] * a[cc][j];
   }
-  // inverse of the lower-triangular 4x4
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    li[j * 4 + j] = 1.0 / a[j][j];
+  for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
-    for (int i = j + 1; i < 4; ++i) {
-      double v = 0.0;
-#pragma unroll
-      for (int k = j; k < i; ++k) v -= a[i][k] * li[k * 4 + j];
-      li[i * 4 + j] = v / a[i][i];
-    }
-#pragma unroll
-    for (int i = 0; i < j; ++i) li[i * 4 + j] = 0.0;
-  }
+    for (int r = cc; r < 8; ++r) A[(j0 + r) + (size_t)(j0 + cc) * ld] = a[r][cc];
   return ok;
+}
+
+// rows below the diagonal block j0 (border included): solve x L_D^T = p by forward substitution, one row per thread
+template <class Ctx>
+GP_DEV void gp_panel_solve(Ctx& c, const GpSmem& s, int j0) {
+  const int ld = s.ld, rem = s.np - j0;   // rows j0+8 .. np+7
+  if (c.tid >= rem) return;
+  double* A = s.A;
+  double l[8][8], r[8];
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    r[cc] = s.rdiag[j0 + cc];
+#pragma unroll
+    for (int k = 0; k < cc; ++k) l[cc][k] = A[(j0 + cc) + (size_t)(j0 + k) * ld];
+  }
+  for (int i = c.tid; i < rem; i += c.nthr) {
+    double* row = A + (j0 + GP_NB + i) + (size_t)j0 * ld;
+    double x[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      double acc = row[(size_t)cc * ld];
+#pragma unroll
+      for (int k = 0; k < cc; ++k) acc -= x[k] * l[cc][k];
+      x[cc] = acc * r[cc];
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) row[(size_t)cc * ld] = x[cc];
+  }
+}
+
+// trailing tile (ta, tb) of step j0:  C -= P_ta P_tb^T  with P = the solved panel (8 columns at j0).  Warp-wide.
+template <class Ctx>
+GP_DEV void gp_chol_update_tile(Ctx& c, const GpSmem& s, int j0, int ta, int tb) {
+  const int ld = s.ld, g = c.lane >> 2, t = c.lane & 3;
+  double* A = s.A;
+  const int r0 = j0 + GP_NB + 8 * ta, c0 = j0 + GP_NB + 8 * tb;
+  double* C0 = A + (r0 + g) + (size_t)(c0 + t) * ld;
+  double* C1 = A + (r0 + g) + (size_t)(c0 + 4 + t) * ld;
+  const bool diag = (ta == tb);
+  double c0v = *C0, c1v = *C1;
+  const double* Pa = A + (r0 + g) + (size_t)(j0 + t) * ld;
+  const double* Pb = A + (c0 + gp_perm(g)) + (size_t)(j0 + t) * ld;
+  c.mma(c0v, c1v, -Pa[0], Pb[0]);
+  c.mma(c0v, c1v, -Pa[(size_t)4 * ld], Pb[(size_t)4 * ld]);
+  // the strict upper triangle of a diagonal tile belongs to K: store the lower part only
+  if (!diag || g >= t) *C0 = c0v;
+  if (!diag || g >= 4 + t) *C1 = c1v;
 }
 
 GP_DEV void gp_tile_index(int q, int& a, int& b) {
@@ -212,199 +250,203 @@ GP_DEV void gp_tile_index(int q, int& a, int& b) {
   b = q - a * (a + 1) / 2;
 }
 
-// Blocked right-looking Cholesky of the lower triangle of A (np x np, np % 4 == 0).  Sets flag on breakdown.
+// Blocked right-looking Cholesky with one-step lookahead.  Sets flag on breakdown.  On exit the lower triangle holds L,
+// rdiag holds 1/L_ii and border row np holds z^T = (L^-1 y)^T.
 template <class Ctx>
 GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s) {
-  const int np = s.np, ld = s.ld, nblk = np / GP_NB;
-  double* A = s.A;
-  for (int kb = 0; kb < nblk; ++kb) {
+  const int np = s.np, nblk = np / GP_NB;
+  if (c.tid == 0) {
+    if (!gp_chol8(s.A, s.ld, 0, s.rdiag)) s.flag[0] = 1;
+  }
+  c.sync();
+  gp_panel_solve(c, s, 0);
+  c.sync();
+  for (int kb = 0; kb + 1 < nblk; ++kb) {
     const int j0 = kb * GP_NB;
-    // (A) diagonal block: factor + invert (one thread; the dependent sqrt/div chain is the critical path anyway)
-    if (c.tid == 0) {
-      double a[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= r; ++cc) a[r][cc] = A[(j0 + r) + (j0 + cc) * ld];
-      if (!gp_chol4(a, s.dinv + kb * 16)) s.flag[0] = 1;
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= r; ++cc) A[(j0 + r) + (j0 + cc) * ld] = a[r][cc];
-    }
-    c.sync();
-    const int rem = np - j0;   // rows below the diagonal block, border rows included
-    // (B) panel: rows below solve x L_D^T = p by forward substitution
-    {
-      const double l00 = A[(j0) + (j0) * ld], l10 = A[(j0 + 1) + (j0) * ld], l11 = A[(j0 + 1) + (j0 + 1) * ld];
-      const double l20 = A[(j0 + 2) + (j0) * ld], l21 = A[(j0 + 2) + (j0 + 1) * ld], l22 = A[(j0 + 2) + (j0 + 2) * ld];
-      const double l30 = A[(j0 + 3) + (j0) * ld], l31 = A[(j0 + 3) + (j0 + 1) * ld], l32 = A[(j0 + 3) + (j0 + 2) * ld];
-      const double l33 = A[(j0 + 3) + (j0 + 3) * ld];
-      const double r0 = 1.0 / l00, r1 = 1.0 / l11, r2 = 1.0 / l22, r3 = 1.0 / l33;
-      for (int i = c.tid; i < rem; i += c.nthr) {
-        double* row = A + (j0 + GP_NB + i) + j0 * ld;
-        const double x0 = row[0] * r0;
-        const double x1 = (row[ld] - x0 * l10) * r1;
-        const double x2 = (row[2 * ld] - x0 * l20 - x1 * l21) * r2;
-        const double x3 = (row[3 * ld] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
-        row[0] = x0; row[ld] = x1; row[2 * ld] = x2; row[3 * ld] = x3;
+    // trailing matrix: T x T lower tiles plus the border tile-row (ta = T) over the T tile-columns
+    const int T = nblk - kb - 1, ntile = T * (T + 1) / 2 + T;
+    if (c.warp == 0) {
+      // critical path first: the next diagonal tile, then its factorisation by one thread
+      gp_chol_update_tile(c, s, j0, 0, 0);
+      c.warp_sync();
+      if (c.lane == 0) {
+        if (!gp_chol8(s.A, s.ld, j0 + GP_NB, s.rdiag)) s.flag[0] = 1;
       }
-    }
-    c.sync();
-    // (C) trailing update A22 -= P P^T on 4x4 register tiles (lower tiles only; the upper triangle holds K)
-    {
-      // square part: T x T lower tiles; border: one more tile-row (ta = T) over the T remaining tile-columns
-      const int T = rem / GP_NB - 1, ntile = T * (T + 1) / 2 + T;
-      const double* P = A + (j0 + GP_NB) + j0 * ld;   // P[i + k*ld], i in [0,rem), k in [0,4)
-      for (int q = c.tid; q < ntile; q += c.nthr) {
+      if (c.nwarp == 1) {
+        c.warp_sync();
+        for (int q = 1; q < ntile; ++q) {
+          int ta, tb;
+          gp_tile_index(q, ta, tb);
+          gp_chol_update_tile(c, s, j0, ta, tb);
+        }
+      }
+    } else {
+      for (int q = c.warp; q < ntile; q += c.nwarp - 1) {
         int ta, tb;
         gp_tile_index(q, ta, tb);
-        double pa[4][4], pb[4][4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) { pa[r][k] = P[(4 * ta + r) + k * ld]; pb[r][k] = P[(4 * tb + r) + k * ld]; }
-        double* C = A + (j0 + GP_NB + 4 * ta) + (j0 + GP_NB + 4 * tb) * ld;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (ta != tb || r >= cc) {
-              double acc = C[r + cc * ld];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) acc -= pa[r][k] * pb[cc][k];
-              C[r + cc * ld] = acc;
-            }
-          }
+        gp_chol_update_tile(c, s, j0, ta, tb);
       }
     }
     c.sync();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- triangular inverse
-// In place: lower triangle L -> X = L^-1 (blocked, last block column first).  Uses s.dinv from gp_cholesky.
-template <class Ctx>
-GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
-  const int np = s.np, ld = s.ld, nblk = np / GP_NB;
-  double* A = s.A;
-  for (int kb = nblk - 1; kb >= 0; --kb) {
-    const int j0 = kb * GP_NB;
-    const int rem = np - j0 - GP_NB;
-    const double* D = s.dinv + kb * 16;
-    // (1) panel <- -(A21 * D)   (right-multiply by the inverse of the diagonal block), staged in scratch
-    for (int i = c.tid; i < rem; i += c.nthr) {
-      const double* row = A + (j0 + GP_NB + i) + j0 * ld;
-      const double p0 = row[0], p1 = row[ld], p2 = row[2 * ld], p3 = row[3 * ld];
-      s.panel[i * 4 + 0] = -(p0 * D[0] + p1 * D[4] + p2 * D[8] + p3 * D[12]);
-      s.panel[i * 4 + 1] = -(p1 * D[5] + p2 * D[9] + p3 * D[13]);
-      s.panel[i * 4 + 2] = -(p2 * D[10] + p3 * D[14]);
-      s.panel[i * 4 + 3] = -(p3 * D[15]);
-    }
-    c.sync();
-    // (2) A21 <- X22 * panel  (X22 = already inverted trailing block), diagonal block <- D
-    for (int w = c.tid; w < rem * 4; w += c.nthr) {
-      const int cc = w / rem, i = w - cc * rem;
-      const double* xrow = A + (j0 + GP_NB + i) + (j0 + GP_NB) * ld;   // X22[i][k] at xrow[k*ld]
-      double acc = 0.0;
-      for (int k = 0; k <= i; ++k) acc += xrow[k * ld] * s.panel[k * 4 + cc];
-      A[(j0 + GP_NB + i) + (j0 + cc) * ld] = acc;
-    }
-    if (c.tid < 16) {
-      const int r = c.tid >> 2, cc = c.tid & 3;
-      if (r >= cc) A[(j0 + r) + (j0 + cc) * ld] = D[r * 4 + cc];
-    }
+    gp_panel_solve(c, s, j0 + GP_NB);
     c.sync();
   }
 }
 
-// After gp_cholesky: z^T sits in border row np.  Copies it to s.z and returns this thread's share of z.z (= y^T K^-1 y) and of
-// sum log L_ii.  Must run before gp_trtri overwrites the diagonal.
+// After gp_cholesky: copies z (border row np) to s.z and returns this thread's share of z.z (= y^T K^-1 y) and of sum log L_ii.
 template <class Ctx>
 GP_DEV void gp_collect_z(Ctx& c, const GpSmem& s, double& quad, double& logdet) {
   const int np = s.np, ld = s.ld;
   quad = 0.0;
   logdet = 0.0;
   for (int i = c.tid; i < np; i += c.nthr) {
-    const double zi = s.A[np + i * ld];
+    const double zi = s.A[np + (size_t)i * ld];
     s.z[i] = zi;
     quad += zi * zi;
-    logdet += log(s.A[i + i * ld]);
+    logdet += log(s.A[i + (size_t)i * ld]);
   }
   c.sync();
 }
 
-// alpha = X^T z  (X = L^-1 in the lower triangle)
+// ---------------------------------------------------------------------------------------------- triangular inverse
+// inverse of every 8x8 diagonal block in place (one thread per block, division-free thanks to rdiag)
+template <class Ctx>
+GP_DEV void gp_invert_diag_blocks(Ctx& c, const GpSmem& s) {
+  const int ld = s.ld, nblk = s.np / GP_NB;
+  for (int kb = c.tid; kb < nblk; kb += c.nthr) {
+    const int j0 = kb * GP_NB;
+    double l[8][8], r[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      r[cc] = s.rdiag[j0 + cc];
+#pragma unroll
+      for (int i = cc + 1; i < 8; ++i) l[i][cc] = s.A[(j0 + i) + (size_t)(j0 + cc) * ld];
+    }
+    // column by column; L stays in registers, so X can overwrite it in memory as soon as a column is done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double x[8];
+      x[j] = r[j];
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = j; k < i; ++k) acc -= l[i][k] * x[k];
+        x[i] = acc * r[i];
+      }
+#pragma unroll
+      for (int i = j; i < 8; ++i) s.A[(j0 + i) + (size_t)(j0 + j) * ld] = x[i];
+    }
+  }
+}
+
+// In place: lower triangle L -> X = L^-1, block columns from the last to the first:  X21 = -X22 (L21 X11).
+template <class Ctx>
+GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
+  const int np = s.np, ld = s.ld, nblk = np / GP_NB, g = c.lane >> 2, t = c.lane & 3;
+  double* A = s.A;
+  gp_invert_diag_blocks(c, s);
+  c.sync();
+  for (int kb = nblk - 2; kb >= 0; --kb) {
+    const int j0 = kb * GP_NB, T = nblk - kb - 1;   // T row-tiles below the diagonal block
+    // (1) W = -(L21 X11), stored transposed in the border rows: W[i][cc] at A[(np + cc) + (j0 + 8 + i) * ld]
+    for (int I = c.warp; I < T; I += c.nwarp) {
+      const int r0 = j0 + GP_NB + 8 * I;
+      double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const double a = A[(r0 + g) + (size_t)(j0 + 4 * kc + t) * ld];
+        const int n = gp_perm(g);   // tile column supplied by this lane
+        const double b = (4 * kc + t >= n) ? A[(j0 + 4 * kc + t) + (size_t)(j0 + n) * ld] : 0.0;   // X11 is lower triangular
+        c.mma(w0, w1, -a, b);
+      }
+      A[(np + t) + (size_t)(r0 + g) * ld] = w0;
+      A[(np + 4 + t) + (size_t)(r0 + g) * ld] = w1;
+    }
+    c.sync();
+    // (2) X21[I] = sum_{K <= I} X22[I][K] W[K]   (two accumulator chains to hide the DMMA latency)
+    for (int I = T - 1 - c.warp; I >= 0; I -= c.nwarp) {
+      const int r0 = j0 + GP_NB + 8 * I;
+      double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+      for (int K = 0; K <= I; ++K) {
+        const int k0 = j0 + GP_NB + 8 * K;
+        const double* Xa = A + (r0 + g) + (size_t)(k0 + t) * ld;
+        const double* Wb = A + (np + gp_perm(g)) + (size_t)(k0 + t) * ld;
+        double a0 = Xa[0], a1 = Xa[(size_t)4 * ld];
+        if (K == I) {   // diagonal block of X22: lower triangular
+          if (g < t) a0 = 0.0;
+          if (g < 4 + t) a1 = 0.0;
+        }
+        c.mma(p0, p1, a0, Wb[0]);
+        c.mma(q0, q1, a1, Wb[(size_t)4 * ld]);
+      }
+      A[(r0 + g) + (size_t)(j0 + t) * ld] = p0 + q0;
+      A[(r0 + g) + (size_t)(j0 + 4 + t) * ld] = p1 + q1;
+    }
+    c.sync();
+  }
+}
+
+// alpha = X^T z  (X = L^-1 in the lower triangle): one warp per column, lanes down the rows, shuffle reduction
 template <class Ctx>
 GP_DEV void gp_alpha_from_inverse(Ctx& c, const GpSmem& s) {
   const int np = s.np, ld = s.ld;
-  for (int j = c.tid; j < np; j += c.nthr) {
+  for (int j = c.warp; j < np; j += c.nwarp) {
+    const double* col = s.A + (size_t)j * ld;
     double acc = 0.0;
-    for (int i = j; i < np; ++i) acc += s.A[i + j * ld] * s.z[i];
-    s.alpha[j] = acc;
+    for (int i = j + c.lane; i < np; i += 32) acc += col[i] * s.z[i];
+    for (int o = 16; o > 0; o >>= 1) acc += c.shfl_xor(acc, o);
+    if (c.lane == 0) s.alpha[j] = acc;
   }
   c.sync();
 }
 
-// Fused K^-1 = X^T X (4x4 tiles) and gradient traces.  tr[0] = sum_{i>j} W_ij K_ij, tr[1]/tr[2] the same weighted by the
+// Fused K^-1 = X^T X (8x8 DMMA tiles) and gradient traces.  tr[0] = sum_{i>j} W_ij K_ij, tr[1]/tr[2] the same weighted by the
 // squared scaled time / wavelength differences, tr[3] = sum_i W_ii  (W = alpha alpha^T - K^-1).
 template <class Ctx>
 GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double tr[4]) {
-  const int np = s.np, ld = s.ld, T = np / GP_NB, ntile = T * (T + 1) / 2;
+  const int np = s.np, ld = s.ld, T = np / GP_NB, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const double* A = s.A;
   tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
-  for (int q = c.tid; q < ntile; q += c.nthr) {
-    int ta, tb;
-    gp_tile_index(q, ta, tb);
-    const int i0 = 4 * ta, j0 = 4 * tb;
-    double acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) acc[r][cc] = 0.0;
-    // head: rows k inside the diagonal block of tile-row ta need the triangular mask
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int k = i0 + kk;
-      double xi[4], xj[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) xi[r] = (kk >= r) ? A[k + (i0 + r) * ld] : 0.0;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) xj[cc] = (ta != tb || kk >= cc) ? A[k + (j0 + cc) * ld] : 0.0;
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] += xi[r] * xj[cc];
+  for (int q = c.warp; q < ntile; q += c.nwarp) {
+    int I, J;
+    gp_tile_index(q, I, J);
+    const int i0 = 8 * I, j0 = 8 * J;
+    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+    // K^-1[i][j] = sum_{k >= i} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X[k0 + t][i0 + g], B (k = t, n = g) = X[k0 + t][j0 + g]
+    const double* Xi = A + t + (size_t)(i0 + g) * ld;
+    const double* Xj = A + t + (size_t)(j0 + g) * ld;
+    {
+      // k-block K = I: X[k][i] is lower triangular there (k >= i), and so is X[k][j] when J == I
+      const int k0 = i0;
+      double a0 = Xi[k0], a1 = Xi[k0 + 4], b0 = Xj[k0], b1 = Xj[k0 + 4];
+      if (t < g) a0 = 0.0;
+      if (4 + t < g) a1 = 0.0;
+      if (I == J) { b0 = a0; b1 = a1; }
+      c.mma(p0, p1, a0, b0);
+      c.mma(q0, q1, a1, b1);
     }
-    for (int k = i0 + 4; k < np; ++k) {
-      double xi[4], xj[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) xi[r] = A[k + (i0 + r) * ld];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) xj[cc] = A[k + (j0 + cc) * ld];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] += xi[r] * xj[cc];
+    for (int k0 = i0 + 8; k0 < np; k0 += 8) {
+      c.mma(p0, p1, Xi[k0], Xj[k0]);
+      c.mma(q0, q1, Xi[k0 + 4], Xj[k0 + 4]);
     }
+    // epilogue: lane (g, t) owns (i, j) = (i0 + g, j0 + 2t) and (i0 + g, j0 + 2t + 1)
+    const int i = i0 + g;
+    const double ai = s.alpha[i], ui = s.u[i], vi = s.v[i];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = i0 + r;
-      const double ai = s.alpha[i], ui = s.u[i], vi = s.v[i];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int j = j0 + cc;
-        const double w = ai * s.alpha[j] - acc[r][cc];
-        if (i > j) {
-          const double kij = A[j + i * ld];   // K kept in the strict upper triangle
-          const double du = ui - s.u[j], dv = vi - s.v[j];
-          const double wk = w * kij;
-          tr[0] += wk;
-          tr[1] += wk * (du * du);
-          tr[2] += wk * (dv * dv);
-        } else if (i == j && i < n) {
-          tr[3] += w;
-        }
+    for (int e = 0; e < 2; ++e) {
+      const int j = j0 + 2 * t + e;
+      const double kinv = e ? (p1 + q1) : (p0 + q0);
+      const double w = ai * s.alpha[j] - kinv;
+      if (i > j) {
+        const double kij = A[j + (size_t)i * ld];   // K kept in the strict upper triangle
+        const double du = ui - s.u[j], dv = vi - s.v[j];
+        const double wk = w * kij;
+        tr[0] += wk;
+        tr[1] += wk * (du * du);
+        tr[2] += wk * (dv * dv);
+      } else if (i == j && i < n) {
+        tr[3] += w;
       }
     }
   }
@@ -486,8 +528,8 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
       acc[r] = k;
     }
     for (int j = 0; j < i0; ++j) {
-      const double vj = V[j * ldv];
-      const double* col = A + i0 + j * ld;
+      const double vj = V[(size_t)j * ldv];
+      const double* col = A + i0 + (size_t)j * ld;
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] -= col[r] * vj;
     }
@@ -497,10 +539,10 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
       const int i = i0 + r;
       double a = acc[r];
 #pragma unroll
-      for (int k = 0; k < r; ++k) a -= A[i + (i0 + k) * ld] * acc[k];
-      a = a / A[i + i * ld];
+      for (int k = 0; k < r; ++k) a -= A[i + (size_t)(i0 + k) * ld] * acc[k];
+      a = a * s.rdiag[i];
       acc[r] = a;
-      V[i * ldv] = a;
+      V[(size_t)i * ldv] = a;
       m += a * s.z[i];
       q2 += a * a;
     }
@@ -512,8 +554,7 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
 // ---------------------------------------------------------------------------------------------- per-curve preparation (a1-a3)
 // StandardScaler statistics with the corrected two-pass variance (sklearn/utils/extmath.py:1203-1262), near-constant
 // columns -> scale 1 (sklearn/preprocessing/_data.py:83-98,1073-1078); y normalisation (_gpr.py:275-280);
-// noise diagonal (fulu/gp_aug.py:64,72-73).  Serial helper used by one thread per statistic is enough: N is small and this
-// runs once per curve, not once per evaluation.
+// noise diagonal (fulu/gp_aug.py:64,72-73).
 GP_DEV void gp_scaler_stats(double sum, double csum, double csq, int n, double& mean, double& scale) {
   const double eps = 2.220446049250313e-16;
   mean = sum / n;
@@ -542,7 +583,7 @@ GP_DEV int gp_prepare_curve(Ctx& c, int n, const double* t, const double* flux, 
   gp_block_sum(c, v, red);
   if (v[3] > 0.0 || n <= 0) return 1;  // FULU_GP_STATUS_BAD_INPUT
   const double mt0 = v[0] / n, ml0 = v[1] / n, mf = v[2] / n;
-  double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // centred sums: t, t^2, l, l^2, f^2
+  double w[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // centred sums: t, t^2, l, l^2, f^2
   for (int i = c.tid; i < n; i += c.nthr) {
     const double dt = t[i] - mt0, dl = loglam[band[i]] - ml0, df = flux[i] - mf;
     w[0] += dt; w[1] += dt * dt; w[2] += dl; w[3] += dl * dl; w[4] += df * df;

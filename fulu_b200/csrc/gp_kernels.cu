@@ -22,8 +22,16 @@
 namespace {
 
 struct DevCtx {
-  int tid, nthr;
+  int tid, nthr, lane, warp, nwarp;
+  __device__ __forceinline__ DevCtx() : tid((int)threadIdx.x), nthr((int)blockDim.x), lane((int)threadIdx.x & 31),
+                                        warp((int)threadIdx.x >> 5), nwarp(((int)blockDim.x + 31) >> 5) {}
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void warp_sync() { __syncwarp(); }
+  // FP64 tensor-core tile: C(8x8) += A(8x4, row) * B(4x8, col); lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
+  __device__ __forceinline__ void mma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  }
+  __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 };
 
 constexpr int kEvalThreads = 256;
@@ -66,10 +74,10 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   const size_t B = (size_t)b.n_curves, NT = (size_t)b.n_obs_total;
   const int nmax = b.n_max < 1 ? 1 : b.n_max;
   const size_t np = (size_t)gp_pad(nmax), ld = (size_t)gp_ld((int)np);
-  size_t full = gp_smem_doubles(nmax, kEvalThreads) * sizeof(double);
+  size_t full = gp_smem_doubles(nmax) * sizeof(double) + 16;
   w.globalA = full > kMaxSmem;
-  size_t vec = (gp_smem_doubles(nmax, kEvalThreads) - np * ld) * sizeof(double) + 16;
-  w.smem_eval = w.globalA ? vec : full + 16;
+  size_t vec = gp_vec_doubles((int)np) * sizeof(double) + 16;
+  w.smem_eval = w.globalA ? vec : full;
   w.smem_predict = w.smem_eval;
   int occ = w.globalA ? (np <= 512 ? 2 : 1) : (int)(kMaxSmem / (w.smem_eval + 1024));
   if (occ < 1) occ = 1;
@@ -123,8 +131,8 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
-  __shared__ double red[kPrepThreads];
-  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  __shared__ double red[64];
+  DevCtx c;
   for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
     const int64_t o = a.offsets[cu];
     const int n = (int)(a.offsets[cu + 1] - o);
@@ -153,27 +161,20 @@ __device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t c
 
 template <bool kGlobalA>
 __device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
-  if (!kGlobalA) return gp_carve(smem, n, kEvalThreads);
+  if (!kGlobalA) {
+    const int np = gp_pad(n);
+    return gp_carve(smem, smem + (size_t)np * gp_ld(np), n);
+  }
   // vectors in shared memory, the matrix in this CTA's global slab (stays in L2)
-  GpSmem s;
-  s.np = gp_pad(n);
-  s.ld = gp_ld(s.np);
-  s.A = gA + (size_t)blockIdx.x * gA_stride;
-  double* p = smem;
-  s.u = p; p += s.np; s.v = p; p += s.np; s.y = p; p += s.np; s.al = p; p += s.np; s.alpha = p; p += s.np; s.z = p; p += s.np;
-  s.dinv = p; p += (s.np / GP_NB) * 16;
-  s.panel = p; p += s.np * GP_NB;
-  s.red = p; p += kEvalThreads;
-  s.flag = (int*)p;
-  return s;
+  return gp_carve(gA + (size_t)blockIdx.x * gA_stride, smem, n);
 }
 
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
 template <bool kGlobalA>
-__global__ void __launch_bounds__(kEvalThreads) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
+__global__ void __launch_bounds__(kEvalThreads, 2) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
                                                             double* gA, size_t gA_stride) {
   extern __shared__ __align__(16) double smem[];
-  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  DevCtx c;
   for (int64_t cu = blockIdx.x; cu < B; cu += gridDim.x) {
     if (tab.pstatus[cu] != 0) {
       if (threadIdx.x == 0) { lml[cu] = NAN; for (int k = 0; k < P; ++k) grad[cu * P + k] = NAN; }
@@ -239,9 +240,9 @@ __global__ void fit_init_kernel(FitDev d) {
 }
 
 template <bool kGlobalA>
-__global__ void __launch_bounds__(kEvalThreads) fit_eval_kernel(FitDev d, int round) {
+__global__ void __launch_bounds__(kEvalThreads, 2) fit_eval_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
-  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  DevCtx c;
   const int count = d.counts[round];
   const int32_t* list = d.list + (size_t)(round & 1) * d.window;
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
@@ -355,7 +356,7 @@ template <bool kGlobalA>
 __global__ void __launch_bounds__(kPredictThreads) predict_kernel(PredictArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double tlim[2];
-  DevCtx c{(int)threadIdx.x, (int)blockDim.x};
+  DevCtx c;
   double* V = a.gV + (size_t)blockIdx.x * a.gV_stride;
   for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
     GpCurveView cv = curve_view(a.tab, cu);

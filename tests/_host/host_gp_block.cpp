@@ -1,30 +1,65 @@
-// TEST HARNESS ONLY: runs fulu_b200/csrc/gp_block.cuh (the code a CUDA thread block executes) on a pool of host threads with
-// a barrier standing in for __syncthreads, so the block algorithm can be checked against the oracle without a GPU.
+// TEST HARNESS ONLY: runs fulu_b200/csrc/gp_block.cuh (the code a CUDA thread block executes) on host threads.  A block barrier
+// stands in for __syncthreads, a per-warp barrier for __syncwarp, and the warp-collective DMMA / shuffle instructions are
+// emulated through a per-warp scratch area, so the block algorithm can be checked against the oracle without a GPU.
 #include <barrier>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
 #include "../../fulu_b200/csrc/gp_block.cuh"
 
+struct WarpShared {
+  std::barrier<> bar{32};
+  double a[32], b[32], x[32];
+};
+
 struct HostCtx {
-  int tid, nthr;
-  std::barrier<>* bar;
-  void sync() { bar->arrive_and_wait(); }
+  int tid, nthr, lane, warp, nwarp;
+  std::barrier<>* block_bar;
+  WarpShared* ws;
+  void sync() { block_bar->arrive_and_wait(); }
+  void warp_sync() { ws->bar.arrive_and_wait(); }
+  // D = A(8x4, row) * B(4x8, col) + C; lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
+  void mma(double& c0, double& c1, double a, double b) {
+    ws->a[lane] = a;
+    ws->b[lane] = b;
+    ws->bar.arrive_and_wait();
+    const int g = lane >> 2, t = lane & 3;
+    for (int k = 0; k < 4; ++k) {
+      c0 = fma(ws->a[4 * g + k], ws->b[4 * (2 * t) + k], c0);
+      c1 = fma(ws->a[4 * g + k], ws->b[4 * (2 * t + 1) + k], c1);
+    }
+    ws->bar.arrive_and_wait();
+  }
+  double shfl_xor(double v, int m) {
+    ws->x[lane] = v;
+    ws->bar.arrive_and_wait();
+    double r = ws->x[lane ^ m];
+    ws->bar.arrive_and_wait();
+    return r;
+  }
 };
 
 template <class F>
 static void run_block(int nthr, F&& body) {
+  const int nwarp = nthr / 32;
   std::barrier<> bar(nthr);
+  std::vector<std::unique_ptr<WarpShared>> ws;
+  for (int w = 0; w < nwarp; ++w) ws.emplace_back(new WarpShared);
   std::vector<std::thread> th;
-  for (int t = 0; t < nthr; ++t) th.emplace_back([&, t] { HostCtx c{t, nthr, &bar}; body(c); });
+  for (int t = 0; t < nthr; ++t)
+    th.emplace_back([&, t] {
+      HostCtx c{t, nthr, t & 31, t >> 5, nwarp, &bar, ws[t >> 5].get()};
+      body(c);
+    });
   for (auto& t : th) t.join();
 }
 
 extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const double* ferr, const int32_t* band, const double* loglam,
                                int n_bands, int use_err, double alpha0, int nthr, double* xs, double* y, double* al, double* lam,
                                double* stats) {
-  std::vector<double> red(nthr > 64 ? nthr : 64);
+  std::vector<double> red(64);
   int status = 0;
   run_block(nthr, [&](HostCtx& c) {
     int st = gp_prepare_curve(c, n, t, flux, ferr, band, loglam, n_bands, use_err, alpha0, xs, y, al, lam, stats, red.data());
@@ -35,11 +70,12 @@ extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const
 
 extern "C" int host_gp_lml(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
                            const double* theta, int nthr, double* lml, double* grad) {
-  std::vector<double> smem(gp_smem_doubles(n, nthr));
+  std::vector<double> smem(gp_smem_doubles(n));
   GpCurveView cv{n, xs, band, y, al, lam};
   int okout = 0;
+  const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
-    GpSmem s = gp_carve(smem.data(), n, nthr);
+    GpSmem s = gp_carve(smem.data(), smem.data() + (size_t)np * gp_ld(np), n);
     double l, g[4];
     bool ok;
     gp_eval_lml_grad(c, cv, theta, s, l, g, ok);
@@ -51,13 +87,14 @@ extern "C" int host_gp_lml(int n, const double* xs, const int32_t* band, const d
 extern "C" int host_gp_predict(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
                                const double* theta, const double* stats, int m, int n_obs, double t_min, double t_max,
                                const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
-  std::vector<double> smem(gp_smem_doubles(n, nthr));
+  std::vector<double> smem(gp_smem_doubles(n));
   std::vector<double> V((size_t)gp_pad(n) * GP_QC);
   GpCurveView cv{n, xs, band, y, al, lam};
   GpQuery qd{m, n_obs, t_min, t_max, qt, qband};
   int status = 0;
+  const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
-    GpSmem s = gp_carve(smem.data(), n, nthr);
+    GpSmem s = gp_carve(smem.data(), smem.data() + (size_t)np * gp_ld(np), n);
     double l;
     int st = gp_predict_curve(c, cv, theta, stats, qd, s, V.data(), mean, stdv, l);
     if (c.tid == 0) { status = st; *lml = l; }
