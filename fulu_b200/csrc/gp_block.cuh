@@ -141,7 +141,7 @@ GP_DEV void gp_assemble(Ctx& c, const GpSmem& s, int n, double cst, double s2, b
   const int np = s.np, ld = s.ld;
   for (int j = c.warp; j < np; j += c.nwarp) {
     const double uj = s.u[j], vj = s.v[j];
-    double* col = s.A + (size_t)j * ld;
+    double* col = s.A + j * ld;
     for (int i = j + c.lane; i < np + GP_NB; i += 32) {
       double val;
       if (i == j) {
@@ -152,7 +152,7 @@ GP_DEV void gp_assemble(Ctx& c, const GpSmem& s, int n, double cst, double s2, b
           const double du = s.u[i] - uj, dv = s.v[i] - vj;
           val = cst * exp(-0.5 * (du * du + dv * dv));
         }
-        if (keep_upper) s.A[j + (size_t)i * ld] = val;
+        if (keep_upper) s.A[j + i * ld] = val;
       } else {
         val = (i == np) ? s.y[j] : 0.0;                // border: y^T then seven zero rows
       }
@@ -169,7 +169,7 @@ GP_DEV bool gp_chol8(double* A, int ld, int j0, double* rdiag) {
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
-    for (int r = cc; r < 8; ++r) a[r][cc] = A[(j0 + r) + (size_t)(j0 + cc) * ld];
+    for (int r = cc; r < 8; ++r) a[r][cc] = A[(j0 + r) + (j0 + cc) * ld];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -192,7 +192,7 @@ GP_DEV bool gp_chol8(double* A, int ld, int j0, double* rdiag) {
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
-    for (int r = cc; r < 8; ++r) A[(j0 + r) + (size_t)(j0 + cc) * ld] = a[r][cc];
+    for (int r = cc; r < 8; ++r) A[(j0 + r) + (j0 + cc) * ld] = a[r][cc];
   return ok;
 }
 
@@ -207,47 +207,52 @@ GP_DEV void gp_panel_solve(Ctx& c, const GpSmem& s, int j0) {
   for (int cc = 0; cc < 8; ++cc) {
     r[cc] = s.rdiag[j0 + cc];
 #pragma unroll
-    for (int k = 0; k < cc; ++k) l[cc][k] = A[(j0 + cc) + (size_t)(j0 + k) * ld];
+    for (int k = 0; k < cc; ++k) l[cc][k] = A[(j0 + cc) + (j0 + k) * ld];
   }
   for (int i = c.tid; i < rem; i += c.nthr) {
-    double* row = A + (j0 + GP_NB + i) + (size_t)j0 * ld;
+    double* row = A + (j0 + GP_NB + i) + j0 * ld;
     double x[8];
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
-      double acc = row[(size_t)cc * ld];
+      double acc = row[cc * ld];
 #pragma unroll
       for (int k = 0; k < cc; ++k) acc -= x[k] * l[cc][k];
       x[cc] = acc * r[cc];
     }
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) row[(size_t)cc * ld] = x[cc];
+    for (int cc = 0; cc < 8; ++cc) row[cc * ld] = x[cc];
   }
 }
 
-// trailing tile (ta, tb) of step j0:  C -= P_ta P_tb^T  with P = the solved panel (8 columns at j0).  Warp-wide.
+// Trailing update of step j0 for the tiles q0, q0 + stride, ... of the linear lower-triangular enumeration
+// (q = ta (ta + 1) / 2 + tb):  C(ta, tb) -= P_ta P_tb^T  with P = the solved panel (8 columns at j0).  Warp-wide.
+// Lane (g, t): A-fragment = P[row g][col t], B-fragment = P[row perm(g)][col t], accumulator c0/c1 = C[g][t], C[g][4 + t].
 template <class Ctx>
-GP_DEV void gp_chol_update_tile(Ctx& c, const GpSmem& s, int j0, int ta, int tb) {
+GP_DEV void gp_chol_update_tiles(Ctx& c, const GpSmem& s, int j0, int q0, int stride, int ntile) {
   const int ld = s.ld, g = c.lane >> 2, t = c.lane & 3;
   double* A = s.A;
-  const int r0 = j0 + GP_NB + 8 * ta, c0 = j0 + GP_NB + 8 * tb;
-  double* C0 = A + (r0 + g) + (size_t)(c0 + t) * ld;
-  double* C1 = A + (r0 + g) + (size_t)(c0 + 4 + t) * ld;
-  const bool diag = (ta == tb);
-  double c0v = *C0, c1v = *C1;
-  const double* Pa = A + (r0 + g) + (size_t)(j0 + t) * ld;
-  const double* Pb = A + (c0 + gp_perm(g)) + (size_t)(j0 + t) * ld;
-  c.mma(c0v, c1v, -Pa[0], Pb[0]);
-  c.mma(c0v, c1v, -Pa[(size_t)4 * ld], Pb[(size_t)4 * ld]);
-  // the strict upper triangle of a diagonal tile belongs to K: store the lower part only
-  if (!diag || g >= t) *C0 = c0v;
-  if (!diag || g >= 4 + t) *C1 = c1v;
-}
-
-GP_DEV void gp_tile_index(int q, int& a, int& b) {
-  a = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-  while (a * (a + 1) / 2 > q) --a;
-  while ((a + 1) * (a + 2) / 2 <= q) ++a;
-  b = q - a * (a + 1) / 2;
+  const int base = j0 + GP_NB;
+  const double* Pa0 = A + base + g + (j0 + t) * ld;            // + 8 ta
+  const double* Pb0 = A + base + gp_perm(g) + (j0 + t) * ld;   // + 8 tb
+  double* C00 = A + base + g + (base + t) * ld;                // + 8 ta + 8 tb ld
+  const int ld4 = 4 * ld, ld8 = 8 * ld;
+  // locate the first tile: ta (ta + 1) / 2 <= q0
+  int ta = 0, tb = q0;
+  while (tb > ta) { tb -= ta + 1; ++ta; }
+  for (int q = q0; q < ntile; q += stride) {
+    const double* Pa = Pa0 + 8 * ta;
+    const double* Pb = Pb0 + 8 * tb;
+    double* C = C00 + 8 * ta + tb * ld8;
+    double c0v = C[0], c1v = C[ld4];
+    c.mma(c0v, c1v, -Pa[0], Pb[0]);
+    c.mma(c0v, c1v, -Pa[ld4], Pb[ld4]);
+    // the strict upper triangle of a diagonal tile belongs to K: store the lower part only
+    const bool diag = (ta == tb);
+    if (!diag || g >= t) C[0] = c0v;
+    if (!diag || g >= 4 + t) C[ld4] = c1v;
+    tb += stride;
+    while (tb > ta) { tb -= ta + 1; ++ta; }
+  }
 }
 
 // Blocked right-looking Cholesky with one-step lookahead.  Sets flag on breakdown.  On exit the lower triangle holds L,
@@ -267,25 +272,17 @@ GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s) {
     const int T = nblk - kb - 1, ntile = T * (T + 1) / 2 + T;
     if (c.warp == 0) {
       // critical path first: the next diagonal tile, then its factorisation by one thread
-      gp_chol_update_tile(c, s, j0, 0, 0);
+      gp_chol_update_tiles(c, s, j0, 0, ntile, ntile);   // tile (0, 0) only
       c.warp_sync();
       if (c.lane == 0) {
         if (!gp_chol8(s.A, s.ld, j0 + GP_NB, s.rdiag)) s.flag[0] = 1;
       }
       if (c.nwarp == 1) {
         c.warp_sync();
-        for (int q = 1; q < ntile; ++q) {
-          int ta, tb;
-          gp_tile_index(q, ta, tb);
-          gp_chol_update_tile(c, s, j0, ta, tb);
-        }
+        gp_chol_update_tiles(c, s, j0, 1, 1, ntile);
       }
     } else {
-      for (int q = c.warp; q < ntile; q += c.nwarp - 1) {
-        int ta, tb;
-        gp_tile_index(q, ta, tb);
-        gp_chol_update_tile(c, s, j0, ta, tb);
-      }
+      gp_chol_update_tiles(c, s, j0, c.warp, c.nwarp - 1, ntile);
     }
     c.sync();
     gp_panel_solve(c, s, j0 + GP_NB);
@@ -300,10 +297,10 @@ GP_DEV void gp_collect_z(Ctx& c, const GpSmem& s, double& quad, double& logdet) 
   quad = 0.0;
   logdet = 0.0;
   for (int i = c.tid; i < np; i += c.nthr) {
-    const double zi = s.A[np + (size_t)i * ld];
+    const double zi = s.A[np + i * ld];
     s.z[i] = zi;
     quad += zi * zi;
-    logdet += log(s.A[i + (size_t)i * ld]);
+    logdet += log(s.A[i + i * ld]);
   }
   c.sync();
 }
@@ -320,7 +317,7 @@ GP_DEV void gp_invert_diag_blocks(Ctx& c, const GpSmem& s) {
     for (int cc = 0; cc < 8; ++cc) {
       r[cc] = s.rdiag[j0 + cc];
 #pragma unroll
-      for (int i = cc + 1; i < 8; ++i) l[i][cc] = s.A[(j0 + i) + (size_t)(j0 + cc) * ld];
+      for (int i = cc + 1; i < 8; ++i) l[i][cc] = s.A[(j0 + i) + (j0 + cc) * ld];
     }
     // column by column; L stays in registers, so X can overwrite it in memory as soon as a column is done
 #pragma unroll
@@ -335,7 +332,7 @@ GP_DEV void gp_invert_diag_blocks(Ctx& c, const GpSmem& s) {
         x[i] = acc * r[i];
       }
 #pragma unroll
-      for (int i = j; i < 8; ++i) s.A[(j0 + i) + (size_t)(j0 + j) * ld] = x[i];
+      for (int i = j; i < 8; ++i) s.A[(j0 + i) + (j0 + j) * ld] = x[i];
     }
   }
 }
@@ -355,33 +352,37 @@ GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
       double w0 = 0.0, w1 = 0.0;
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        const double a = A[(r0 + g) + (size_t)(j0 + 4 * kc + t) * ld];
+        const double a = A[(r0 + g) + (j0 + 4 * kc + t) * ld];
         const int n = gp_perm(g);   // tile column supplied by this lane
-        const double b = (4 * kc + t >= n) ? A[(j0 + 4 * kc + t) + (size_t)(j0 + n) * ld] : 0.0;   // X11 is lower triangular
+        const double b = (4 * kc + t >= n) ? A[(j0 + 4 * kc + t) + (j0 + n) * ld] : 0.0;   // X11 is lower triangular
         c.mma(w0, w1, -a, b);
       }
-      A[(np + t) + (size_t)(r0 + g) * ld] = w0;
-      A[(np + 4 + t) + (size_t)(r0 + g) * ld] = w1;
+      A[(np + t) + (r0 + g) * ld] = w0;
+      A[(np + 4 + t) + (r0 + g) * ld] = w1;
     }
     c.sync();
     // (2) X21[I] = sum_{K <= I} X22[I][K] W[K]   (two accumulator chains to hide the DMMA latency)
-    for (int I = T - 1 - c.warp; I >= 0; I -= c.nwarp) {
-      const int r0 = j0 + GP_NB + 8 * I;
-      double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-      for (int K = 0; K <= I; ++K) {
-        const int k0 = j0 + GP_NB + 8 * K;
-        const double* Xa = A + (r0 + g) + (size_t)(k0 + t) * ld;
-        const double* Wb = A + (np + gp_perm(g)) + (size_t)(k0 + t) * ld;
-        double a0 = Xa[0], a1 = Xa[(size_t)4 * ld];
-        if (K == I) {   // diagonal block of X22: lower triangular
-          if (g < t) a0 = 0.0;
-          if (g < 4 + t) a1 = 0.0;
+    {
+      const int base = j0 + GP_NB, ld4 = 4 * ld, ld8 = 8 * ld;
+      const double* Xa0 = A + base + g + (base + t) * ld;              // + 8 I + K ld8
+      const double* Wb0 = A + np + gp_perm(g) + (base + t) * ld;       // + K ld8
+      for (int I = T - 1 - c.warp; I >= 0; I -= c.nwarp) {
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+        const double* Xa = Xa0 + 8 * I;
+        const double* Wb = Wb0;
+        for (int K = 0; K < I; ++K) {
+          c.mma(p0, p1, Xa[0], Wb[0]);
+          c.mma(q0, q1, Xa[ld4], Wb[ld4]);
+          Xa += ld8;
+          Wb += ld8;
         }
-        c.mma(p0, p1, a0, Wb[0]);
-        c.mma(q0, q1, a1, Wb[(size_t)4 * ld]);
+        // K == I: diagonal block of X22, lower triangular
+        c.mma(p0, p1, (g < t) ? 0.0 : Xa[0], Wb[0]);
+        c.mma(q0, q1, (g < 4 + t) ? 0.0 : Xa[ld4], Wb[ld4]);
+        double* O = A + base + 8 * I + g + (j0 + t) * ld;
+        O[0] = p0 + q0;
+        O[ld4] = p1 + q1;
       }
-      A[(r0 + g) + (size_t)(j0 + t) * ld] = p0 + q0;
-      A[(r0 + g) + (size_t)(j0 + 4 + t) * ld] = p1 + q1;
     }
     c.sync();
   }
@@ -392,7 +393,7 @@ template <class Ctx>
 GP_DEV void gp_alpha_from_inverse(Ctx& c, const GpSmem& s) {
   const int np = s.np, ld = s.ld;
   for (int j = c.warp; j < np; j += c.nwarp) {
-    const double* col = s.A + (size_t)j * ld;
+    const double* col = s.A + j * ld;
     double acc = 0.0;
     for (int i = j + c.lane; i < np; i += 32) acc += col[i] * s.z[i];
     for (int o = 16; o > 0; o >>= 1) acc += c.shfl_xor(acc, o);
@@ -408,14 +409,14 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double tr[4]) {
   const int np = s.np, ld = s.ld, T = np / GP_NB, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const double* A = s.A;
   tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
+  int I = 0, J = c.warp;
+  while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
-    int I, J;
-    gp_tile_index(q, I, J);
     const int i0 = 8 * I, j0 = 8 * J;
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
     // K^-1[i][j] = sum_{k >= i} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X[k0 + t][i0 + g], B (k = t, n = g) = X[k0 + t][j0 + g]
-    const double* Xi = A + t + (size_t)(i0 + g) * ld;
-    const double* Xj = A + t + (size_t)(j0 + g) * ld;
+    const double* Xi = A + t + (i0 + g) * ld;
+    const double* Xj = A + t + (j0 + g) * ld;
     {
       // k-block K = I: X[k][i] is lower triangular there (k >= i), and so is X[k][j] when J == I
       const int k0 = i0;
@@ -439,7 +440,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double tr[4]) {
       const double kinv = e ? (p1 + q1) : (p0 + q0);
       const double w = ai * s.alpha[j] - kinv;
       if (i > j) {
-        const double kij = A[j + (size_t)i * ld];   // K kept in the strict upper triangle
+        const double kij = A[j + i * ld];   // K kept in the strict upper triangle
         const double du = ui - s.u[j], dv = vi - s.v[j];
         const double wk = w * kij;
         tr[0] += wk;
@@ -449,6 +450,8 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double tr[4]) {
         tr[3] += w;
       }
     }
+    J += c.nwarp;
+    while (J > I) { J -= I + 1; ++I; }
   }
 }
 
@@ -528,8 +531,8 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
       acc[r] = k;
     }
     for (int j = 0; j < i0; ++j) {
-      const double vj = V[(size_t)j * ldv];
-      const double* col = A + i0 + (size_t)j * ld;
+      const double vj = V[j * ldv];
+      const double* col = A + i0 + j * ld;
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r] -= col[r] * vj;
     }
@@ -539,10 +542,10 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
       const int i = i0 + r;
       double a = acc[r];
 #pragma unroll
-      for (int k = 0; k < r; ++k) a -= A[i + (size_t)(i0 + k) * ld] * acc[k];
+      for (int k = 0; k < r; ++k) a -= A[i + (i0 + k) * ld] * acc[k];
       a = a * s.rdiag[i];
       acc[r] = a;
-      V[(size_t)i * ldv] = a;
+      V[i * ldv] = a;
       m += a * s.z[i];
       q2 += a * a;
     }

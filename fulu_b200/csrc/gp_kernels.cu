@@ -15,6 +15,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/fulu_gp.h"
 #include "gp_block.cuh"
 #include "lbfgsb.cuh"
@@ -591,42 +593,40 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   const unsigned step_grid = (unsigned)((w.window + 127) / 128);
   constexpr int kMaxGroup = 16;
   const bool prof = opt->profile != nullptr;
-  cudaEvent_t ev[3 * kMaxGroup];
-  if (prof)
-    for (int i = 0; i < 3 * kMaxGroup; ++i) CU_TRY(cudaEventCreate(&ev[i]));
-  double eval_ms = 0.0, step_ms = 0.0;
+  std::vector<cudaEvent_t> ev;   // 3 per round when profiling; read back only after the loop so timing does not perturb it
   int round = 0, group = 4;
   bool finished = false;
   while (round < w.max_rounds) {
     int upto = round + group;
     if (upto > w.max_rounds) upto = w.max_rounds;
-    const int first = round;
     for (; round < upto; ++round) {
-      const int e = 3 * (round - first);
-      if (prof) cudaEventRecord(ev[e], st);
+      if (prof) {
+        for (int i = 0; i < 3; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); ev.push_back(e); }
+        cudaEventRecord(ev[3 * round], st);
+      }
       if (w.globalA) fit_eval_kernel<true><<<w.grid_eval, kEvalThreads, w.smem_eval, st>>>(d, round);
       else fit_eval_kernel<false><<<w.grid_eval, kEvalThreads, w.smem_eval, st>>>(d, round);
-      if (prof) cudaEventRecord(ev[e + 1], st);
+      if (prof) cudaEventRecord(ev[3 * round + 1], st);
       fit_step_kernel<<<step_grid, 128, 0, st>>>(d, round);
-      if (prof) cudaEventRecord(ev[e + 2], st);
+      if (prof) cudaEventRecord(ev[3 * round + 2], st);
     }
     CU_TRY(cudaGetLastError());
     int32_t remaining = 0;
     CU_TRY(cudaMemcpyAsync(&remaining, d.counts + round, 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    if (prof)
-      for (int r = first; r < round; ++r) {
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, ev[3 * (r - first)], ev[3 * (r - first) + 1]);
-        cudaEventElapsedTime(&b, ev[3 * (r - first) + 1], ev[3 * (r - first) + 2]);
-        eval_ms += a;
-        step_ms += b;
-      }
     if (remaining == 0) { finished = true; break; }
     if (group < kMaxGroup) group *= 2;
   }
   if (prof) {
-    for (int i = 0; i < 3 * kMaxGroup; ++i) cudaEventDestroy(ev[i]);
+    double eval_ms = 0.0, step_ms = 0.0;
+    for (int r = 0; r < round; ++r) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ev[3 * r], ev[3 * r + 1]);
+      cudaEventElapsedTime(&b, ev[3 * r + 1], ev[3 * r + 2]);
+      eval_ms += a;
+      step_ms += b;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     double* pr = opt->profile;
     pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = 2.0 * round + 4.0; pr[4] = w.window; pr[5] = w.grid_eval;
     pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0;

@@ -1,0 +1,60 @@
+"""The CUDA block algorithm (fulu_b200/csrc/gp_block.cuh) executed on host threads (tests/_host/host_gp_block.cpp: barriers for
+__syncthreads/__syncwarp, emulated DMMA and shuffles) against the golden vectors of the real reference.  Same tolerances as the
+GPU parity tests; lets the device code be checked where there is no GPU."""
+import numpy as np
+import pytest
+
+import hostblock as H
+from conftest import load_golden, relerr
+from oracle import gp_oracle as O
+
+CASES = ["readme", "readme_err", "testfixture", "csv34299", "csv34299_err", "csv34299_band2", "plasticc_0", "plasticc_1", "ztf_2", "ztf_5"]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("nthr", [64, 256])
+def test_block_lml_grad_predict(name, nthr):
+    if nthr == 256 and name not in ("csv34299", "ztf_2", "readme"):
+        pytest.skip("8-warp emulation only on a few cases (slow)")
+    g = load_golden(name)
+    p = H.prepare(g["t"], g["flux"], g["flux_err"], g["band"], g["loglam"], bool(g["use_err"]), nthr=nthr)
+    assert p.status == 0
+    np.testing.assert_allclose([p.stats[0], p.stats[2]], g["x_mean"], rtol=1e-14)
+    np.testing.assert_allclose([p.stats[1], p.stats[3]], g["x_scale"], rtol=1e-12)
+    np.testing.assert_allclose(p.stats[4:6], [g["y_mean"], g["y_std"]], rtol=1e-13)
+    p2l = {i: float(v) for i, v in enumerate(g["loglam"])}
+    gp = O.ClosedFormGP(p2l, use_err=bool(g["use_err"])).prepare(g["t"], g["flux"], g["flux_err"], g["band"])
+    for k in (0, 2, 4, 6):
+        th = g["thetas"][k]
+        lml, grad, ok = H.lml_grad(p, th, nthr=nthr)
+        assert ok
+        assert abs(lml - g["lml"][k]) <= 1e-9 * max(1.0, abs(g["lml"][k]))
+        _, _, gs = O.lml_and_grad(gp.X, gp.y, gp.alpha, th, return_scale=True)
+        den = np.maximum(np.maximum(np.abs(g["grad"][k]), 1e-2 * gs), 1e-30)
+        assert np.max(np.abs(grad - g["grad"][k]) / den) < 1e-9
+    nb, n_obs = len(g["loglam"]), int(g["n_obs"])
+    m, s, lml, st = H.predict_grid(p, g["theta_star"], nb, n_obs, float(g["t_min"]), float(g["t_max"]), nthr=nthr)
+    assert st == 0
+    assert relerr(m, g["flux_aug"], floor=1e-3 * float(g["y_std"])) < 1e-9
+    assert relerr(s, g["flux_err_aug"]) < 1e-9
+    assert abs(lml - float(g["lml_star"])) <= 1e-9 * max(1.0, abs(float(g["lml_star"])))
+
+
+def test_block_not_positive_definite_is_reported():
+    # duplicate observations with (almost) no noise: K is numerically singular
+    t = np.array([0.0, 0.0, 1.0, 1.0, 2.0, 2.0, 3.0, 3.0])
+    p = H.prepare(t, np.sin(t), np.ones(8), np.zeros(8, np.int32), np.array([3.5]), False, alpha0=0.0, nthr=64)
+    lml, grad, ok = H.lml_grad(p, np.array([0.0, 0.0, 0.0, -800.0]), nthr=64)
+    assert not ok and lml == -np.inf and np.all(grad == 0.0)
+
+
+def test_block_predict_points_equals_grid():
+    g = load_golden("ztf_0")
+    p = H.prepare(g["t"], g["flux"], g["flux_err"], g["band"], g["loglam"], False, nthr=64)
+    nb, n_obs = len(g["loglam"]), 16
+    m, s, _, _ = H.predict_grid(p, g["theta_star"], nb, n_obs, float(g["t_min"]), float(g["t_max"]), nthr=64)
+    qt = np.tile(np.linspace(float(g["t_min"]), float(g["t_max"]), n_obs), nb)
+    qb = np.repeat(np.arange(nb, dtype=np.int32), n_obs)
+    m2, s2, _, _ = H.predict_points(p, g["theta_star"], qt, qb, nthr=64)
+    np.testing.assert_array_equal(m, m2)
+    np.testing.assert_array_equal(s, s2)
