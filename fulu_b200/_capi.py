@@ -31,7 +31,7 @@ class FitOptions(ctypes.Structure):
 
 EXPORTS = (
     "fulu_gp_abi_version", "fulu_gp_strerror", "fulu_gp_workspace_bytes", "fulu_gp_lml_batch", "fulu_gp_fit_batch",
-    "fulu_gp_predict_grid_batch", "fulu_gp_predict_points_batch", "fulu_gp_fp64_peak",
+    "fulu_gp_predict_grid_batch", "fulu_gp_predict_points_batch", "fulu_gp_fp64_peak", "fulu_gp_debug_phase_cycles",
 )
 
 _lib = None
@@ -63,6 +63,7 @@ def load():
     lib.fulu_gp_predict_grid_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_predict_points_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_fp64_peak.argtypes = [i32, i32, c_double_p, vp]
+    lib.fulu_gp_debug_phase_cycles.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     for name in EXPORTS:
         if name not in ("fulu_gp_strerror",):
             getattr(lib, name).restype = ctypes.c_int

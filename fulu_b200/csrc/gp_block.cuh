@@ -460,11 +460,15 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double tr[4]) {
 template <class Ctx>
 GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta, const GpSmem& s, double& lml, double grad[4], bool& ok) {
   const double cst = exp(theta[0]), lt = exp(theta[1]), ll = exp(theta[2]), s2 = exp(theta[3]);
+  c.mark(0);
   gp_load_curve(c, cv, s, lt, ll);
   c.sync();
+  c.mark(1);
   gp_assemble(c, s, cv.n, cst, s2, true);
   c.sync();
+  c.mark(2);
   gp_cholesky(c, s);
+  c.mark(3);
   ok = (s.flag[0] == 0);
   if (!ok) {
     lml = -INFINITY;
@@ -474,10 +478,15 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
   }
   double v[6];
   gp_collect_z(c, s, v[4], v[5]);
+  c.mark(4);
   gp_trtri(c, s);
+  c.mark(5);
   gp_alpha_from_inverse(c, s);
+  c.mark(6);
   gp_inverse_traces(c, s, cv.n, v);
+  c.mark(7);
   gp_block_sum(c, v, s.red);
+  c.mark(8);
   lml = -0.5 * v[4] - v[5] - 0.5 * (double)cv.n * GP_LOG_2PI;
   grad[0] = v[0] + 0.5 * cst * v[3];
   grad[1] = v[1];

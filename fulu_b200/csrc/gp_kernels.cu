@@ -25,8 +25,12 @@ namespace {
 
 struct DevCtx {
   int tid, nthr, lane, warp, nwarp;
+  long long* marks;   // optional phase timestamps (fulu_gp_debug_phase_cycles); null in production launches
   __device__ __forceinline__ DevCtx() : tid((int)threadIdx.x), nthr((int)blockDim.x), lane((int)threadIdx.x & 31),
-                                        warp((int)threadIdx.x >> 5), nwarp(((int)blockDim.x + 31) >> 5) {}
+                                        warp((int)threadIdx.x >> 5), nwarp(((int)blockDim.x + 31) >> 5), marks(nullptr) {}
+  __device__ __forceinline__ void mark(int id) {
+    if (marks != nullptr && tid == 0) marks[id] = clock64();
+  }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void warp_sync() { __syncwarp(); }
   // FP64 tensor-core tile: C(8x8) += A(8x4, row) * B(4x8, col); lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
@@ -174,9 +178,10 @@ __device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stri
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
 template <bool kGlobalA>
 __global__ void __launch_bounds__(kEvalThreads, 2) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
-                                                            double* gA, size_t gA_stride) {
+                                                            double* gA, size_t gA_stride, long long* marks) {
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
+  if (blockIdx.x == 0) c.marks = marks;
   for (int64_t cu = blockIdx.x; cu < B; cu += gridDim.x) {
     if (tab.pstatus[cu] != 0) {
       if (threadIdx.x == 0) { lml[cu] = NAN; for (int k = 0; k < P; ++k) grad[cu * P + k] = NAN; }
@@ -501,8 +506,21 @@ int fulu_gp_workspace_bytes(const fulu_gp_batch* batch, int32_t n_params, int32_
   return 0;
 }
 
+static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad, double* scaler,
+                    double* ynorm, int32_t* status, void* workspace, size_t workspace_bytes, void* stream, long long* marks);
+
 int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad, double* scaler,
                       double* ynorm, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return lml_impl(batch, n_params, theta, lml, grad, scaler, ynorm, status, workspace, workspace_bytes, stream, nullptr);
+}
+
+int fulu_gp_debug_phase_cycles(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad,
+                               long long* marks, void* workspace, size_t workspace_bytes, void* stream) {
+  return lml_impl(batch, n_params, theta, lml, grad, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream, marks);
+}
+
+static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad, double* scaler,
+                    double* ynorm, int32_t* status, void* workspace, size_t workspace_bytes, void* stream, long long* marks) {
   int rc = check_batch(batch, n_params);
   if (rc) return rc;
   if (batch->n_curves == 0) return 0;
@@ -521,11 +539,11 @@ int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double
   if (w.globalA) {
     rc = set_smem(lml_kernel<true>, w.smem_eval);
     if (rc) return rc;
-    lml_kernel<true><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, at<double>(workspace, w.gA), w.gA_stride);
+    lml_kernel<true><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, at<double>(workspace, w.gA), w.gA_stride, marks);
   } else {
     rc = set_smem(lml_kernel<false>, w.smem_eval);
     if (rc) return rc;
-    lml_kernel<false><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, nullptr, 0);
+    lml_kernel<false><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, nullptr, 0, marks);
   }
   CU_TRY(cudaGetLastError());
   const unsigned g1 = (unsigned)((B + 255) / 256);

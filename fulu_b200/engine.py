@@ -170,6 +170,20 @@ class GPEngine:
                                                    ws.numel(), self._stream()))
             return out
 
+    def phase_cycles(self, batch: DeviceBatch, theta):
+        """Diagnostics: SM-clock cycles CTA 0 spent in each phase of its last LML+gradient evaluation (under a full grid)."""
+        with torch.cuda.device(self.device):
+            B, P = batch.n_curves, theta.shape[1]
+            theta = theta.to(self.device, torch.float64).contiguous()
+            lml, grad = self._new(B), self._new(B, P)
+            marks = torch.zeros(16, dtype=torch.int64, device=self.device)
+            ws = self._workspace(batch, P, 1, 1)
+            _capi.check(self.lib.fulu_gp_debug_phase_cycles(ctypes.byref(batch.c), P, self._p(theta), self._p(lml), self._p(grad),
+                                                            self._p(marks), self._p(ws), ws.numel(), self._stream()))
+            m = marks.cpu().numpy()
+            names = ("load", "assemble", "cholesky", "collect_z", "inverse", "alpha", "traces", "reduce")
+            return {n: int(m[i + 1] - m[i]) for i, n in enumerate(names)}
+
     # ---- a6: optimiser
     def fit(self, batch: DeviceBatch, spec: KernelSpec = None, window=0, max_rounds=0, factr=1e7, pgtol=1e-5, maxiter=15000,
             maxfun=15000, maxls=20, m=10, return_runs=False, profile=False):

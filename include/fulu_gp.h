@@ -123,6 +123,11 @@ int fulu_gp_predict_points_batch(const fulu_gp_batch* batch, int32_t n_params, c
  * MEASURED_PEAKS.json has no FP64 entry. */
 int fulu_gp_fp64_peak(int32_t mode, int32_t iters, double* tflops, void* stream);
 
+/* Diagnostics: same as fulu_gp_lml_batch, and CTA 0 writes clock64() at nine phase boundaries of its first... every evaluation into
+ * marks[0..8] (device pointer to >= 16 int64): load, assemble, cholesky, z, inverse, alpha, traces, reduce.  Used by profiles/. */
+int fulu_gp_debug_phase_cycles(const fulu_gp_batch* batch, int32_t n_params, const double* theta, double* lml, double* grad,
+                               long long* marks, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ struct HostCtx {
   std::barrier<>* block_bar;
   WarpShared* ws;
   void sync() { block_bar->arrive_and_wait(); }
+  void mark(int) {}
   void warp_sync() { ws->bar.arrive_and_wait(); }
   // D = A(8x4, row) * B(4x8, col) + C; lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
   void mma(double& c0, double& c1, double a, double b) {
