@@ -1,4 +1,4 @@
-// Block-level FP64 GP algebra: one CTA owns one light curve's N x N kernel matrix in shared memory.
+// Block-level FP64 GP algebra: one CTA owns one light curve's kernel matrix, packed as 8x8 tiles in shared memory.
 //
 // Functions here are written against a small "block context" (tid/lane/warp, sync(), warp_sync(), mma(), shfl_xor()) so the
 // very same code is executed by a CUDA thread block (DevCtx in gp_kernels.cu: __syncthreads, mma.sync.m8n8k4.f64, shuffles)
@@ -9,21 +9,24 @@
 //   K   = c * exp(-1/2 |x_i/l - x_j/l|^2) + (s2 + alpha_i) I            (a4)
 //   L   = chol(K)                       blocked right-looking, NB = 8    (a5; LAPACK dpotrf in the reference)
 //   X   = L^-1                          blocked in-place triangular inverse (replaces the identity-RHS dpotrs)
-//   a   = X^T z, z = L^-1 y;  LML = -1/2 z.z - sum log L_ii - N/2 log 2pi
+//   z   = L^-1 y, a = X^T z;  LML = -1/2 z.z - sum log L_ii - N/2 log 2pi
 //   K^-1 = X^T X is never stored: each 8x8 tile is reduced straight into the gradient traces
 //   g_k = 1/2 sum_ij (a_i a_j - K^-1_ij) dK_ij/dtheta_k                  (Eq. 5.9)
 //
 // Every O(N^3) piece runs on 8x8 tiles through the FP64 tensor-core instruction (DMMA m8n8k4; on B200 it sustains the full
-// FP64 rate with an eighth of the issue slots of a DFMA loop, measured 37.2 vs 33.9 TFLOP/s).  The inherently serial part of
-// the Cholesky - the chain of N reciprocal square roots down the diagonal - is done by one thread on an 8x8 block *while* the
-// other warps apply the previous panel to the rest of the trailing matrix (lookahead), so a step costs two barriers.
+// FP64 rate with an eighth of the issue slots of a DFMA loop, measured 37.2 vs 33.9 TFLOP/s).
 //
-// Storage: A is column-major, np = N padded to a multiple of 8 (identity padding), np columns of ld rows with
-// ld = np + 12 (= 4 mod 8): lane (g, t) of a fragment load touches row g/column t (or row t/column g), i.e. 64-bit bank
-// (g + 4t) mod 16 - conflict free for both orientations.  The strict upper triangle keeps K for the gradient pass while the lower
-// triangle is overwritten by L and then L^-1.  Rows np..np+7 are a border tile-row: row np carries y^T, so the panel solves and
-// trailing updates of the Cholesky turn it into z^T = (L^-1 y)^T for free (bordered factorisation); after that the border
-// rows are reused as the 8-wide panel scratch of the triangular inverse.
+// Storage (v3).  Only the lower triangle exists: tile (I, J), J <= I < T (T = np / 8, np = N padded to a multiple of 8 with an
+// identity block) lives at 64 (I (I + 1) / 2 + J) doubles, followed by one border tile-row I = T (tiles (T, 0..T-1)) whose row 0
+// carries y^T.  The bordered matrix M = [[L, 0], [z^T, 1]] is what the algorithms act on:
+//   * the panel solves and trailing updates of the Cholesky turn the border row into z^T = (L^-1 y)^T for free,
+//   * the triangular inverse of M has -a^T = -(X^T z)^T in its border row, so alpha = K^-1 y costs nothing extra either.
+// K itself is not kept: the gradient pass recomputes K_ij (one exp) where it meets K^-1_ij.  That halves the footprint
+// (N = 100: 55 KB instead of 100 KB), which is what lets four curves be resident per SM instead of two - the evaluation is
+// latency bound (serial 8x8 diagonal factorisations, barriers), so residency is throughput.
+// Inside a tile element (r, c) sits at 8 c + (r ^ swz(c)), swz(c) = (c & 2 ? 6 : 0) ^ (c & 4): every fragment access pattern used
+// below - (g, t), (g, 4+t), (perm g, t), (t, g), (t, perm g) and their +4 variants, lane = 4 g + t - touches 16 distinct
+// 64-bit banks per half-warp (checked exhaustively in tests/test_block_host.py::test_tile_swizzle_is_conflict_free).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -38,6 +41,11 @@
 
 #define GP_NB 8
 #define GP_LOG_2PI 1.8378770664093453
+#define GP_RED 96
+// Cholesky step: tiles of the trailing update handed to each of the other warps while warp 0 factors the next diagonal block
+#ifndef GP_CHOL8_TILES
+#define GP_CHOL8_TILES 10
+#endif
 
 struct GpCurveView {
   int n;               // observations
@@ -49,51 +57,65 @@ struct GpCurveView {
 };
 
 struct GpSmem {
-  double* A;      // np columns of ld rows
+  double* A;      // packed tiles: T (T + 1) / 2 lower tiles, then T border tiles
   double* u;      // np   x_i0 / l_t
   double* v;      // np   x_i1 / l_lambda
-  double* y;      // np
-  double* al;     // np
-  double* alpha;  // np   K^-1 y
-  double* z;      // np   L^-1 y
   double* rdiag;  // np   1 / L_ii
-  double* red;    // reduction scratch, 64 doubles
+  double* red;    // reduction scratch, GP_RED doubles (16 warps x 6 values)
   int* flag;      // [0] = Cholesky breakdown
-  int np, ld;
+  int np, T;
 };
 
 GP_HD int gp_pad(int n) { return (n + GP_NB - 1) / GP_NB * GP_NB; }
-GP_HD int gp_ld(int np) { return np + GP_NB + 4; }
-GP_HD size_t gp_vec_doubles(int np) { return 7 * (size_t)np + 64 + 2; }
+GP_HD size_t gp_mat_doubles(int np) { const size_t T = (size_t)np / GP_NB; return 64 * (T * (T + 1) / 2 + T); }
+GP_HD size_t gp_vec_doubles(int np) { return 3 * (size_t)np + GP_RED + 2; }
 // doubles of shared memory needed for a curve of n observations (matrix + vectors)
 GP_HD size_t gp_smem_doubles(int n) {
-  const size_t np = (size_t)gp_pad(n);
-  return np * (size_t)gp_ld((int)np) + gp_vec_doubles((int)np);
+  const int np = gp_pad(n);
+  return gp_mat_doubles(np) + gp_vec_doubles(np);
 }
 
 // vectors at `vec`, matrix at `mat` (shared memory, or a per-CTA global slab for long curves)
 GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
   GpSmem s;
   s.np = gp_pad(n);
-  s.ld = gp_ld(s.np);
+  s.T = s.np / GP_NB;
   s.A = mat;
   double* p = vec;
   s.u = p; p += s.np;
   s.v = p; p += s.np;
-  s.y = p; p += s.np;
-  s.al = p; p += s.np;
-  s.alpha = p; p += s.np;
-  s.z = p; p += s.np;
   s.rdiag = p; p += s.np;
-  s.red = p; p += 64;
+  s.red = p; p += GP_RED;
   s.flag = (int*)p;
   return s;
 }
 
+// ---------------------------------------------------------------------------------------------- tile addressing
+GP_HD int gp_swz(int c) { return ((c & 2) ? 6 : 0) ^ (c & 4); }
+GP_HD int gp_el(int r, int c) { return c * 8 + (r ^ gp_swz(c)); }           // element (r, c) inside a tile
+GP_HD int gp_tile(int I, int J) { return 64 * (I * (I + 1) / 2 + J); }      // tile (I, J), J <= I; border row: I = T
+GP_HD int gp_at(int i, int j) { return gp_tile(i >> 3, j >> 3) + gp_el(i & 7, j & 7); }   // matrix element (i, j), j <= i
 // column permutation of the accumulator fragment: register c0 of lane (g, t) holds tile column t, c1 holds column 4 + t
-// (instead of 2t, 2t+1), so that accumulator loads/stores hit banks (g + 4t) as well.  B-fragment lane g must then supply
+// (instead of 2t, 2t+1), so that accumulator loads/stores are conflict free too.  B-fragment lane g must then supply
 // tile column gp_perm(g).
 GP_HD int gp_perm(int g) { return (g & 1) ? 4 + (g >> 1) : (g >> 1); }
+
+// per-lane fragment offsets inside a tile (lane = 4 g + t)
+struct GpFrag {
+  int a0, a1;   // (g, t), (g, 4 + t)          A operand [m = g][k]; also the permuted accumulator
+  int b0, b1;   // (perm g, t), (perm g, 4 + t)  B operand = rows of a tile (B[k][n] = tile[n][k])
+  int t0, t1;   // (t, g), (4 + t, g)          transposed A / native B = columns of a tile
+  int p0, p1;   // (t, perm g), (4 + t, perm g)  B operand = a tile as is, permuted output
+};
+GP_HD GpFrag gp_frag(int lane) {
+  const int g = lane >> 2, t = lane & 3, pg = gp_perm(g);
+  GpFrag f;
+  f.a0 = gp_el(g, t); f.a1 = gp_el(g, 4 + t);
+  f.b0 = gp_el(pg, t); f.b1 = gp_el(pg, 4 + t);
+  f.t0 = gp_el(t, g); f.t1 = gp_el(4 + t, g);
+  f.p0 = gp_el(t, pg); f.p1 = gp_el(4 + t, pg);
+  return f;
+}
 
 // ---------------------------------------------------------------------------------------------- reductions
 // Sum of v[k] over the block (result in every thread).  Warp shuffles for the column reduction, one smem hop across warps.
@@ -125,51 +147,58 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, double
     if (i < cv.n) {
       s.u[i] = cv.xs[i] / lt;              // X / length_scale  (kernels.py:1561)
       s.v[i] = cv.lam[cv.band[i]] / ll;
-      s.y[i] = cv.y[i];
-      s.al[i] = cv.al[i];
     } else {
-      s.u[i] = 0.0; s.v[i] = 0.0; s.y[i] = 0.0; s.al[i] = 0.0;
+      s.u[i] = 0.0; s.v[i] = 0.0;
     }
   }
   if (c.tid == 0) s.flag[0] = 0;
 }
 
-// K into the lower triangle (to be factored), a copy into the strict upper triangle if keep_upper, and the border rows.
-// One warp per column, lanes down the rows: conflict-free stores for the lower triangle.
+// c * exp(-1/2 |x_i/l - x_j/l|^2) for i != j  (kernels.py:1561-1565)
+GP_DEV double gp_kernel_value(double cst, double ui, double vi, double uj, double vj) {
+  const double du = ui - uj, dv = vi - vj;
+  return cst * exp(-0.5 * (du * du + dv * dv));
+}
+
+// K into the lower tiles, y^T into row 0 of the border tile-row.  One warp per tile; lane (g, t) writes (g, t) and (g, 4 + t).
 template <class Ctx>
-GP_DEV void gp_assemble(Ctx& c, const GpSmem& s, int n, double cst, double s2, bool keep_upper) {
-  const int np = s.np, ld = s.ld;
-  for (int j = c.warp; j < np; j += c.nwarp) {
-    const double uj = s.u[j], vj = s.v[j];
-    double* col = s.A + j * ld;
-    for (int i = j + c.lane; i < np + GP_NB; i += 32) {
-      double val;
-      if (i == j) {
-        val = (j < n) ? (cst + s2) + s.al[j] : 1.0;    // White on the diagonal, then K[diag] += alpha (_gpr.py:589)
-      } else if (i < np) {
-        val = 0.0;
-        if (i < n) {   // j < i < n
-          const double du = s.u[i] - uj, dv = s.v[i] - vj;
-          val = cst * exp(-0.5 * (du * du + dv * dv));
-        }
-        if (keep_upper) s.A[j + i * ld] = val;
-      } else {
-        val = (i == np) ? s.y[j] : 0.0;                // border: y^T then seven zero rows
-      }
-      col[i] = val;
+GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, double cst, double s2) {
+  const int T = s.T, n = cv.n, ntile = T * (T + 1) / 2 + T, g = c.lane >> 2, t = c.lane & 3;
+  const GpFrag f = gp_frag(c.lane);
+  int I = 0, J = c.warp;
+  while (J > I) { J -= I + 1; ++I; }
+  for (int q = c.warp; q < ntile; q += c.nwarp) {
+    double* tp = s.A + 64 * q;
+    const int j0 = 8 * J + t, j1 = j0 + 4;
+    double v0, v1;
+    if (I == T) {            // border: y^T then seven zero rows
+      v0 = (g == 0 && j0 < n) ? cv.y[j0] : 0.0;
+      v1 = (g == 0 && j1 < n) ? cv.y[j1] : 0.0;
+    } else {
+      const int i = 8 * I + g;
+      const double ui = s.u[i], vi = s.v[i];
+      v0 = (i > j0 && i < n) ? gp_kernel_value(cst, ui, vi, s.u[j0], s.v[j0]) : 0.0;
+      v1 = (i > j1 && i < n) ? gp_kernel_value(cst, ui, vi, s.u[j1], s.v[j1]) : 0.0;
+      // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding
+      if (i == j0) v0 = (i < n) ? (cst + s2) + cv.al[i] : 1.0;
+      if (i == j1) v1 = (i < n) ? (cst + s2) + cv.al[i] : 1.0;
     }
+    tp[f.a0] = v0;
+    tp[f.a1] = v1;
+    J += c.nwarp;
+    while (J > I) { J -= I + 1; ++I; }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- Cholesky
-// 8x8 diagonal block at A[j0.., j0..] (lower) -> L in place, rdiag[j0..] = 1/L_jj.  Division-free: r = rsqrt(d), L_jj = d r.
+// 8x8 diagonal tile (lower part) -> L in place, rdiag[0..7] = 1/L_jj.  Division-free: r = rsqrt(d), L_jj = d r.
 // Executed by ONE thread; everything is unrolled into registers so the scheduler starts column j+1's rsqrt as early as possible.
-GP_DEV bool gp_chol8(double* A, int ld, int j0, double* rdiag) {
+GP_DEV bool gp_chol8(double* tp, double* rdiag) {
   double a[8][8];
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
-    for (int r = cc; r < 8; ++r) a[r][cc] = A[(j0 + r) + (j0 + cc) * ld];
+    for (int r = cc; r < 8; ++r) a[r][cc] = tp[gp_el(r, cc)];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -181,7 +210,7 @@ GP_DEV bool gp_chol8(double* A, int ld, int j0, double* rdiag) {
     const double r = 1.0 / sqrt(d);
 #endif
     a[j][j] = d * r;
-    rdiag[j0 + j] = r;
+    rdiag[j] = r;
 #pragma unroll
     for (int i = j + 1; i < 8; ++i) a[i][j] *= r;
 #pragma unroll
@@ -192,132 +221,136 @@ GP_DEV bool gp_chol8(double* A, int ld, int j0, double* rdiag) {
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
-    for (int r = cc; r < 8; ++r) A[(j0 + r) + (j0 + cc) * ld] = a[r][cc];
+    for (int r = cc; r < 8; ++r) tp[gp_el(r, cc)] = a[r][cc];
   return ok;
 }
 
-// rows below the diagonal block j0 (border included): solve x L_D^T = p by forward substitution, one row per thread
+// rows below the diagonal tile kb (border row included): solve x L_D^T = p by forward substitution, one row per thread
 template <class Ctx>
-GP_DEV void gp_panel_solve(Ctx& c, const GpSmem& s, int j0) {
-  const int ld = s.ld, rem = s.np - j0;   // rows j0+8 .. np+7
-  if (c.tid >= rem) return;
-  double* A = s.A;
+GP_DEV void gp_panel_solve(Ctx& c, const GpSmem& s, int kb) {
+  const int T = s.T, rows = (T - kb - 1) * 8 + 1;   // + 1: row 0 of the border tile
+  if (c.tid >= rows) return;
+  const double* D = s.A + gp_tile(kb, kb);
   double l[8][8], r[8];
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
-    r[cc] = s.rdiag[j0 + cc];
+    r[cc] = s.rdiag[8 * kb + cc];
 #pragma unroll
-    for (int k = 0; k < cc; ++k) l[cc][k] = A[(j0 + cc) + (j0 + k) * ld];
+    for (int k = 0; k < cc; ++k) l[cc][k] = D[gp_el(cc, k)];
   }
-  for (int i = c.tid; i < rem; i += c.nthr) {
-    double* row = A + (j0 + GP_NB + i) + j0 * ld;
+  for (int i = c.tid; i < rows; i += c.nthr) {
+    const int I = kb + 1 + (i >> 3), rr = i & 7;
+    double* tp = s.A + gp_tile(I, kb);
     double x[8];
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
-      double acc = row[cc * ld];
+      double acc = tp[gp_el(rr, cc)];
 #pragma unroll
       for (int k = 0; k < cc; ++k) acc -= x[k] * l[cc][k];
       x[cc] = acc * r[cc];
     }
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) row[cc * ld] = x[cc];
+    for (int cc = 0; cc < 8; ++cc) tp[gp_el(rr, cc)] = x[cc];
   }
 }
 
-// Trailing update of step j0 for the tiles q0, q0 + stride, ... of the linear lower-triangular enumeration
-// (q = ta (ta + 1) / 2 + tb):  C(ta, tb) -= P_ta P_tb^T  with P = the solved panel (8 columns at j0).  Warp-wide.
-// Lane (g, t): A-fragment = P[row g][col t], B-fragment = P[row perm(g)][col t], accumulator c0/c1 = C[g][t], C[g][4 + t].
+// Trailing update of step kb for the tiles q0, q0 + stride, ... < qend of the linear enumeration q = ta (ta + 1) / 2 + tb
+// (ta = 0..Tr, row Tr = the border):  C(ta, tb) -= P_ta P_tb^T  with P = the solved panel (block column kb).  Warp-wide.
 template <class Ctx>
-GP_DEV void gp_chol_update_tiles(Ctx& c, const GpSmem& s, int j0, int q0, int stride, int ntile) {
-  const int ld = s.ld, g = c.lane >> 2, t = c.lane & 3;
+GP_DEV void gp_chol_update_tiles(Ctx& c, const GpSmem& s, const GpFrag& f, int kb, int q0, int stride, int qend) {
+  if (q0 >= qend) return;
   double* A = s.A;
-  const int base = j0 + GP_NB;
-  const double* Pa0 = A + base + g + (j0 + t) * ld;            // + 8 ta
-  const double* Pb0 = A + base + gp_perm(g) + (j0 + t) * ld;   // + 8 tb
-  double* C00 = A + base + g + (base + t) * ld;                // + 8 ta + 8 tb ld
-  const int ld4 = 4 * ld, ld8 = 8 * ld;
-  // locate the first tile: ta (ta + 1) / 2 <= q0
+  const int base = kb + 1;
   int ta = 0, tb = q0;
   while (tb > ta) { tb -= ta + 1; ++ta; }
-  for (int q = q0; q < ntile; q += stride) {
-    const double* Pa = Pa0 + 8 * ta;
-    const double* Pb = Pb0 + 8 * tb;
-    double* C = C00 + 8 * ta + tb * ld8;
-    double c0v = C[0], c1v = C[ld4];
-    c.mma(c0v, c1v, -Pa[0], Pb[0]);
-    c.mma(c0v, c1v, -Pa[ld4], Pb[ld4]);
-    // the strict upper triangle of a diagonal tile belongs to K: store the lower part only
-    const bool diag = (ta == tb);
-    if (!diag || g >= t) C[0] = c0v;
-    if (!diag || g >= 4 + t) C[ld4] = c1v;
+  for (int q = q0; q < qend; q += stride) {
+    const double* Pa = A + gp_tile(base + ta, kb);
+    const double* Pb = A + gp_tile(base + tb, kb);
+    double* C = A + gp_tile(base + ta, base + tb);
+    double c0v = C[f.a0], c1v = C[f.a1];
+    c.mma(c0v, c1v, -Pa[f.a0], Pb[f.b0]);
+    c.mma(c0v, c1v, -Pa[f.a1], Pb[f.b1]);
+    C[f.a0] = c0v;
+    C[f.a1] = c1v;
     tb += stride;
     while (tb > ta) { tb -= ta + 1; ++ta; }
   }
 }
 
-// Blocked right-looking Cholesky with one-step lookahead.  Sets flag on breakdown.  On exit the lower triangle holds L,
-// rdiag holds 1/L_ii and border row np holds z^T = (L^-1 y)^T.
+// Blocked right-looking Cholesky of the bordered matrix with one-step lookahead: warp 0 brings the next diagonal tile up to
+// date and one of its threads factors it (the chain of 8 reciprocal square roots) while the other warps apply the panel to
+// the rest of the trailing matrix.  Sets flag on breakdown.  On exit the lower tiles hold L, rdiag holds 1/L_ii and row 0 of
+// the border tile-row holds z^T = (L^-1 y)^T.
 template <class Ctx>
 GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s) {
-  const int np = s.np, nblk = np / GP_NB;
+  const int T = s.T;
+  const GpFrag f = gp_frag(c.lane);
   if (c.tid == 0) {
-    if (!gp_chol8(s.A, s.ld, 0, s.rdiag)) s.flag[0] = 1;
+    if (!gp_chol8(s.A + gp_tile(0, 0), s.rdiag)) s.flag[0] = 1;
   }
   c.sync();
   gp_panel_solve(c, s, 0);
   c.sync();
-  for (int kb = 0; kb + 1 < nblk; ++kb) {
-    const int j0 = kb * GP_NB;
-    // trailing matrix: T x T lower tiles plus the border tile-row (ta = T) over the T tile-columns
-    const int T = nblk - kb - 1, ntile = T * (T + 1) / 2 + T;
-    if (c.warp == 0) {
-      // critical path first: the next diagonal tile, then its factorisation by one thread
-      gp_chol_update_tiles(c, s, j0, 0, ntile, ntile);   // tile (0, 0) only
+  for (int kb = 0; kb + 1 < T; ++kb) {
+    // trailing matrix: Tr x Tr lower tiles plus the border tile-row (ta = Tr) over the Tr tile-columns
+    const int Tr = T - kb - 1, ntile = Tr * (Tr + 1) / 2 + Tr;
+    if (c.nwarp == 1) {
+      gp_chol_update_tiles(c, s, f, kb, 0, 1, 1);
       c.warp_sync();
       if (c.lane == 0) {
-        if (!gp_chol8(s.A, s.ld, j0 + GP_NB, s.rdiag)) s.flag[0] = 1;
+        if (!gp_chol8(s.A + gp_tile(kb + 1, kb + 1), s.rdiag + 8 * (kb + 1))) s.flag[0] = 1;
       }
-      if (c.nwarp == 1) {
-        c.warp_sync();
-        gp_chol_update_tiles(c, s, j0, 1, 1, ntile);
-      }
+      c.warp_sync();
+      gp_chol_update_tiles(c, s, f, kb, 1, 1, ntile);
     } else {
-      gp_chol_update_tiles(c, s, j0, c.warp, c.nwarp - 1, ntile);
+      // segment A (tiles 1 .. nA) is shared by warps 1.., segment B (the rest) by all warps once warp 0 is back
+      int nA = GP_CHOL8_TILES * (c.nwarp - 1);
+      if (nA > ntile - 1) nA = ntile - 1;
+      if (c.warp == 0) {
+        gp_chol_update_tiles(c, s, f, kb, 0, 1, 1);   // critical path first: the next diagonal tile
+        c.warp_sync();
+        if (c.lane == 0) {
+          if (!gp_chol8(s.A + gp_tile(kb + 1, kb + 1), s.rdiag + 8 * (kb + 1))) s.flag[0] = 1;
+        }
+        c.warp_sync();
+      } else {
+        gp_chol_update_tiles(c, s, f, kb, c.warp, c.nwarp - 1, 1 + nA);
+      }
+      gp_chol_update_tiles(c, s, f, kb, 1 + nA + c.warp, c.nwarp, ntile);
     }
     c.sync();
-    gp_panel_solve(c, s, j0 + GP_NB);
+    gp_panel_solve(c, s, kb + 1);
     c.sync();
   }
 }
 
-// After gp_cholesky: copies z (border row np) to s.z and returns this thread's share of z.z (= y^T K^-1 y) and of sum log L_ii.
+// After gp_cholesky: this thread's share of z.z (= y^T K^-1 y) and of sum log L_ii.
 template <class Ctx>
-GP_DEV void gp_collect_z(Ctx& c, const GpSmem& s, double& quad, double& logdet) {
-  const int np = s.np, ld = s.ld;
+GP_DEV void gp_collect(Ctx& c, const GpSmem& s, double& quad, double& logdet) {
+  const int np = s.np, T = s.T;
   quad = 0.0;
   logdet = 0.0;
   for (int i = c.tid; i < np; i += c.nthr) {
-    const double zi = s.A[np + i * ld];
-    s.z[i] = zi;
+    const double zi = s.A[gp_tile(T, i >> 3) + gp_el(0, i & 7)];
     quad += zi * zi;
-    logdet += log(s.A[i + i * ld]);
+    logdet -= log(s.rdiag[i]);   // log L_ii = -log(1 / L_ii); rdiag and the border row survive until the inverse's first barrier
   }
-  c.sync();
 }
 
 // ---------------------------------------------------------------------------------------------- triangular inverse
-// inverse of every 8x8 diagonal block in place (one thread per block, division-free thanks to rdiag)
+// inverse of every 8x8 diagonal tile in place (one thread per tile, division-free thanks to rdiag); the strict upper part of
+// the tile is zeroed so that later tile products need no masks
 template <class Ctx>
 GP_DEV void gp_invert_diag_blocks(Ctx& c, const GpSmem& s) {
-  const int ld = s.ld, nblk = s.np / GP_NB;
-  for (int kb = c.tid; kb < nblk; kb += c.nthr) {
-    const int j0 = kb * GP_NB;
+  const int T = s.T;
+  for (int kb = c.tid; kb < T; kb += c.nthr) {
+    double* tp = s.A + gp_tile(kb, kb);
     double l[8][8], r[8];
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc) {
-      r[cc] = s.rdiag[j0 + cc];
+      r[cc] = s.rdiag[8 * kb + cc];
 #pragma unroll
-      for (int i = cc + 1; i < 8; ++i) l[i][cc] = s.A[(j0 + i) + (j0 + cc) * ld];
+      for (int i = cc + 1; i < 8; ++i) l[i][cc] = tp[gp_el(i, cc)];
     }
     // column by column; L stays in registers, so X can overwrite it in memory as soon as a column is done
 #pragma unroll
@@ -332,120 +365,104 @@ GP_DEV void gp_invert_diag_blocks(Ctx& c, const GpSmem& s) {
         x[i] = acc * r[i];
       }
 #pragma unroll
-      for (int i = j; i < 8; ++i) s.A[(j0 + i) + (j0 + j) * ld] = x[i];
+      for (int i = 0; i < 8; ++i) tp[gp_el(i, j)] = (i >= j) ? x[i] : 0.0;
     }
   }
 }
 
-// In place: lower triangle L -> X = L^-1, block columns from the last to the first:  X21 = -X22 (L21 X11).
+// In place: M = [[L, 0], [z^T, 1]] -> M^-1 = [[X, 0], [-a^T, 1]], block columns from the last to the first.  For block column
+// kb with rows I in (kb, T]:   W_I = -M_I,kb X_kb,kb (in place), then X_I,kb = sum_{kb < K <= I} X_I,K W_K, written over W_I.
+// Row I only reads W_K with K <= I, so rows are finished from the bottom up in waves of one row per warp, with one barrier
+// between a wave's reads and its stores; no scratch is needed.
 template <class Ctx>
 GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
-  const int np = s.np, ld = s.ld, nblk = np / GP_NB, g = c.lane >> 2, t = c.lane & 3;
+  const int T = s.T;
   double* A = s.A;
+  const GpFrag f = gp_frag(c.lane);
   gp_invert_diag_blocks(c, s);
   c.sync();
-  for (int kb = nblk - 2; kb >= 0; --kb) {
-    const int j0 = kb * GP_NB, T = nblk - kb - 1;   // T row-tiles below the diagonal block
-    // (1) W = -(L21 X11), stored transposed in the border rows: W[i][cc] at A[(np + cc) + (j0 + 8 + i) * ld]
-    for (int I = c.warp; I < T; I += c.nwarp) {
-      const int r0 = j0 + GP_NB + 8 * I;
-      double w0 = 0.0, w1 = 0.0;
-#pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        const double a = A[(r0 + g) + (j0 + 4 * kc + t) * ld];
-        const int n = gp_perm(g);   // tile column supplied by this lane
-        const double b = (4 * kc + t >= n) ? A[(j0 + 4 * kc + t) + (j0 + n) * ld] : 0.0;   // X11 is lower triangular
-        c.mma(w0, w1, -a, b);
-      }
-      A[(np + t) + (r0 + g) * ld] = w0;
-      A[(np + 4 + t) + (r0 + g) * ld] = w1;
-    }
-    c.sync();
-    // (2) X21[I] = sum_{K <= I} X22[I][K] W[K]   (two accumulator chains to hide the DMMA latency)
+  for (int kb = T - 1; kb >= 0; --kb) {
+    // (1) W_I = -(M_I,kb X11)
     {
-      const int base = j0 + GP_NB, ld4 = 4 * ld, ld8 = 8 * ld;
-      const double* Xa0 = A + base + g + (base + t) * ld;              // + 8 I + K ld8
-      const double* Wb0 = A + np + gp_perm(g) + (base + t) * ld;       // + K ld8
-      for (int I = T - 1 - c.warp; I >= 0; I -= c.nwarp) {
-        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-        const double* Xa = Xa0 + 8 * I;
-        const double* Wb = Wb0;
-        for (int K = 0; K < I; ++K) {
-          c.mma(p0, p1, Xa[0], Wb[0]);
-          c.mma(q0, q1, Xa[ld4], Wb[ld4]);
-          Xa += ld8;
-          Wb += ld8;
-        }
-        // K == I: diagonal block of X22, lower triangular
-        c.mma(p0, p1, (g < t) ? 0.0 : Xa[0], Wb[0]);
-        c.mma(q0, q1, (g < 4 + t) ? 0.0 : Xa[ld4], Wb[ld4]);
-        double* O = A + base + 8 * I + g + (j0 + t) * ld;
-        O[0] = p0 + q0;
-        O[ld4] = p1 + q1;
+      const double* X11 = A + gp_tile(kb, kb);
+      const double b0 = X11[f.p0], b1 = X11[f.p1];
+      for (int I = kb + 1 + c.warp; I <= T; I += c.nwarp) {
+        double* tp = A + gp_tile(I, kb);
+        double w0 = 0.0, w1 = 0.0;
+        c.mma(w0, w1, -tp[f.a0], b0);
+        c.mma(w0, w1, -tp[f.a1], b1);
+        tp[f.a0] = w0;
+        tp[f.a1] = w1;
       }
     }
     c.sync();
-  }
-}
-
-// alpha = X^T z  (X = L^-1 in the lower triangle): one warp per column, lanes down the rows, shuffle reduction
-template <class Ctx>
-GP_DEV void gp_alpha_from_inverse(Ctx& c, const GpSmem& s) {
-  const int np = s.np, ld = s.ld;
-  for (int j = c.warp; j < np; j += c.nwarp) {
-    const double* col = s.A + j * ld;
-    double acc = 0.0;
-    for (int i = j + c.lane; i < np; i += 32) acc += col[i] * s.z[i];
-    for (int o = 16; o > 0; o >>= 1) acc += c.shfl_xor(acc, o);
-    if (c.lane == 0) s.alpha[j] = acc;
+    // (2) waves of rows, bottom up
+    for (int Itop = T; Itop > kb; Itop -= c.nwarp) {
+      const int I = Itop - c.warp;
+      double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+      if (I > kb) {
+        const double* Xr = A + gp_tile(I, kb + 1);   // X_I,K for K = kb + 1 ..
+        const double* Wk = A + gp_tile(kb + 1, kb);  // W_K: next K is (K + 1) tiles further
+        int K = kb + 1;
+        const int Kend = (I == T) ? T : I + 1;       // the border's own diagonal tile is the identity
+        for (; K < Kend; ++K) {
+          c.mma(p0, p1, Xr[f.a0], Wk[f.p0]);
+          c.mma(q0, q1, Xr[f.a1], Wk[f.p1]);
+          Xr += 64;
+          Wk += 64 * (K + 1);
+        }
+        if (I == T) { p0 += Wk[f.a0]; p1 += Wk[f.a1]; }   // Wk now points at W_T
+      }
+      c.sync();
+      if (I > kb) {
+        double* O = A + gp_tile(I, kb);
+        O[f.a0] = p0 + q0;
+        O[f.a1] = p1 + q1;
+      }
+    }
   }
   c.sync();
 }
 
-// Fused K^-1 = X^T X (8x8 DMMA tiles) and gradient traces.  tr[0] = sum_{i>j} W_ij K_ij, tr[1]/tr[2] the same weighted by the
-// squared scaled time / wavelength differences, tr[3] = sum_i W_ii  (W = alpha alpha^T - K^-1).
+// Fused K^-1 = X^T X (8x8 DMMA tiles), recomputed K and gradient traces.  tr[0] = sum_{i>j} W_ij K_ij, tr[1]/tr[2] the same
+// weighted by the squared scaled time / wavelength differences, tr[3] = sum_i W_ii  (W = alpha alpha^T - K^-1).
 template <class Ctx>
-GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double tr[4]) {
-  const int np = s.np, ld = s.ld, T = np / GP_NB, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
+GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double cst, double tr[4]) {
+  const int T = s.T, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const double* A = s.A;
+  const GpFrag f = gp_frag(c.lane);
+  const double* bord = A + gp_tile(T, 0);
   tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
-    const int i0 = 8 * I, j0 = 8 * J;
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-    // K^-1[i][j] = sum_{k >= i} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X[k0 + t][i0 + g], B (k = t, n = g) = X[k0 + t][j0 + g]
-    const double* Xi = A + t + (i0 + g) * ld;
-    const double* Xj = A + t + (j0 + g) * ld;
-    {
-      // k-block K = I: X[k][i] is lower triangular there (k >= i), and so is X[k][j] when J == I
-      const int k0 = i0;
-      double a0 = Xi[k0], a1 = Xi[k0 + 4], b0 = Xj[k0], b1 = Xj[k0 + 4];
-      if (t < g) a0 = 0.0;
-      if (4 + t < g) a1 = 0.0;
-      if (I == J) { b0 = a0; b1 = a1; }
-      c.mma(p0, p1, a0, b0);
-      c.mma(q0, q1, a1, b1);
-    }
-    for (int k0 = i0 + 8; k0 < np; k0 += 8) {
-      c.mma(p0, p1, Xi[k0], Xj[k0]);
-      c.mma(q0, q1, Xi[k0 + 4], Xj[k0 + 4]);
+    // K^-1[i][j] = sum_{k >= i} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
+    // the diagonal tiles of X carry explicit zeros above the diagonal
+    const double* Xi = A + gp_tile(I, I);
+    const double* Xj = A + gp_tile(I, J);
+    for (int K = I; K < T; ++K) {
+      c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
+      c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
+      Xi += 64 * (K + 1);
+      Xj += 64 * (K + 1);
     }
     // epilogue: lane (g, t) owns (i, j) = (i0 + g, j0 + 2t) and (i0 + g, j0 + 2t + 1)
-    const int i = i0 + g;
-    const double ai = s.alpha[i], ui = s.u[i], vi = s.v[i];
+    const int i = 8 * I + g;
+    const double ai = -bord[64 * I + gp_el(0, g)], ui = s.u[i], vi = s.v[i];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int j = j0 + 2 * t + e;
+      const int jc = 2 * t + e, j = 8 * J + jc;
       const double kinv = e ? (p1 + q1) : (p0 + q0);
-      const double w = ai * s.alpha[j] - kinv;
+      const double w = ai * -bord[64 * J + gp_el(0, jc)] - kinv;
       if (i > j) {
-        const double kij = A[j + i * ld];   // K kept in the strict upper triangle
-        const double du = ui - s.u[j], dv = vi - s.v[j];
-        const double wk = w * kij;
-        tr[0] += wk;
-        tr[1] += wk * (du * du);
-        tr[2] += wk * (dv * dv);
+        if (i < n) {
+          const double du = ui - s.u[j], dv = vi - s.v[j];
+          const double wk = w * (cst * exp(-0.5 * (du * du + dv * dv)));   // K_ij again (not stored)
+          tr[0] += wk;
+          tr[1] += wk * (du * du);
+          tr[2] += wk * (dv * dv);
+        }
       } else if (i == j && i < n) {
         tr[3] += w;
       }
@@ -464,7 +481,7 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
   gp_load_curve(c, cv, s, lt, ll);
   c.sync();
   c.mark(1);
-  gp_assemble(c, s, cv.n, cst, s2, true);
+  gp_assemble(c, cv, s, cst, s2);
   c.sync();
   c.mark(2);
   gp_cholesky(c, s);
@@ -477,13 +494,12 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
     return;
   }
   double v[6];
-  gp_collect_z(c, s, v[4], v[5]);
+  gp_collect(c, s, v[4], v[5]);
   c.mark(4);
   gp_trtri(c, s);
   c.mark(5);
-  gp_alpha_from_inverse(c, s);
   c.mark(6);
-  gp_inverse_traces(c, s, cv.n, v);
+  gp_inverse_traces(c, s, cv.n, cst, v);
   c.mark(7);
   gp_block_sum(c, v, s.red);
   c.mark(8);
@@ -502,19 +518,19 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const double* theta, const 
   const double cst = exp(theta[0]), lt = exp(theta[1]), ll = exp(theta[2]), s2 = exp(theta[3]);
   gp_load_curve(c, cv, s, lt, ll);
   c.sync();
-  gp_assemble(c, s, cv.n, cst, s2, false);
+  gp_assemble(c, cv, s, cst, s2);
   c.sync();
   gp_cholesky(c, s);
   ok = (s.flag[0] == 0);
   if (!ok) { lml = -INFINITY; c.sync(); return; }
   double v[2];
-  gp_collect_z(c, s, v[0], v[1]);
+  gp_collect(c, s, v[0], v[1]);
   gp_block_sum(c, v, s.red);
   lml = -0.5 * v[0] - v[1] - 0.5 * (double)cv.n * GP_LOG_2PI;
 }
 
 // ---------------------------------------------------------------------------------------------- prediction
-// Query points against a factored curve (s.A lower = L, s.z = L^-1 y), one query point per thread:
+// Query points against a factored curve (lower tiles = L, border row = z^T), one query point per thread:
 //   k*_i = c exp(-1/2 |x*/l - x_i/l|^2)          (kernels.py:1569-1570; White contributes 0 off the training set)
 //   v    = L^-1 k*  by forward substitution       (_gpr.py:460-462: solve_triangular, NOT an explicit inverse - at noise
 //                                                  levels of 1e-5 the explicit-inverse product loses ~40x in the variance)
@@ -524,26 +540,41 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const double* theta, const 
 #define GP_QC 128   // query columns per pass (= threads that own a column)
 
 GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, double vq, double* V, int ldv, double& mean, double& v2) {
-  const int ld = s.ld;
   const double* A = s.A;
+  const double* bord = A + gp_tile(s.T, 0);
   double m = 0.0, q2 = 0.0;
   for (int i0 = 0; i0 < n; i0 += 4) {
+    const int I = i0 >> 3, rho = i0 & 4;
     double acc[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = i0 + r;
       double k = 0.0;
-      if (i < n) {
-        const double du = uq - s.u[i], dv = vq - s.v[i];
-        k = cst * exp(-0.5 * (du * du + dv * dv));
-      }
+      if (i < n) k = gp_kernel_value(cst, uq, vq, s.u[i], s.v[i]);
       acc[r] = k;
     }
-    for (int j = 0; j < i0; ++j) {
-      const double vj = V[j * ldv];
-      const double* col = A + i0 + j * ld;
+    const double* row = A + gp_tile(I, 0);
+    const double* vp = V;
+    for (int J = 0; J < I; ++J) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] -= col[r] * vj;
+      for (int cc = 0; cc < 8; ++cc) {
+        const double vj = vp[cc * ldv];
+        const double* e = row + 8 * cc;
+        const int sw = gp_swz(cc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] -= e[(rho + r) ^ sw] * vj;
+      }
+      row += 64;
+      vp += 8 * ldv;
+    }
+    // `row` is the diagonal tile now: its first four columns when this is the tile's second half
+    if (rho) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const double vj = vp[cc * ldv];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] -= row[gp_el(4 + r, cc)] * vj;
+      }
     }
     // 4x4 diagonal block by substitution (rows >= n are identity padding)
 #pragma unroll
@@ -551,11 +582,11 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
       const int i = i0 + r;
       double a = acc[r];
 #pragma unroll
-      for (int k = 0; k < r; ++k) a -= A[i + (i0 + k) * ld] * acc[k];
+      for (int k = 0; k < r; ++k) a -= row[gp_el(rho + r, rho + k)] * acc[k];
       a = a * s.rdiag[i];
       acc[r] = a;
       V[i * ldv] = a;
-      m += a * s.z[i];
+      m += a * bord[64 * I + gp_el(0, rho + r)];
       q2 += a * a;
     }
   }

@@ -40,7 +40,8 @@ struct DevCtx {
   __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 };
 
-constexpr int kEvalThreads = 256;
+constexpr int kEvalMaxThreads = 512;   // 128 registers per thread fill the register file at 512 threads per SM:
+                                       // an evaluation CTA gets 512 / (CTAs per SM) threads
 constexpr int kPredictThreads = 128;
 constexpr int kPrepThreads = 128;
 constexpr size_t kMaxSmem = 227 * 1024;
@@ -54,7 +55,7 @@ struct WsLayout {
   size_t run_f, run_x, run_nev, run_end, starts;                              // per (curve, start) results
   size_t gA, gV;                                                              // per-CTA global scratch
   size_t total;
-  int window, max_rounds, grid_eval, grid_predict;
+  int window, max_rounds, grid_eval, grid_predict, threads_eval, occ_eval;
   size_t gA_stride, gV_stride;   // doubles per CTA
   bool globalA;
   size_t smem_eval, smem_predict;
@@ -79,17 +80,24 @@ constexpr int kDefaultMaxRounds = 200000;
 void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int sms, WsLayout& w) {
   const size_t B = (size_t)b.n_curves, NT = (size_t)b.n_obs_total;
   const int nmax = b.n_max < 1 ? 1 : b.n_max;
-  const size_t np = (size_t)gp_pad(nmax), ld = (size_t)gp_ld((int)np);
-  size_t full = gp_smem_doubles(nmax) * sizeof(double) + 16;
+  const size_t np = (size_t)gp_pad(nmax);
+  const size_t vec = gp_vec_doubles((int)np) * sizeof(double) + 16;
+  const size_t full = gp_mat_doubles((int)np) * sizeof(double) + vec;
   w.globalA = full > kMaxSmem;
-  size_t vec = gp_vec_doubles((int)np) * sizeof(double) + 16;
   w.smem_eval = w.globalA ? vec : full;
   w.smem_predict = w.smem_eval;
-  int occ = w.globalA ? (np <= 512 ? 2 : 1) : (int)(kMaxSmem / (w.smem_eval + 1024));
+  // residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation is latency bound, so as many curves per
+  // SM as fit, and the 512 threads the register file allows are split between them
+  int occ = w.globalA ? (np <= 512 ? 2 : 1) : (int)((228 * 1024) / (w.smem_eval + 1024));
   if (occ < 1) occ = 1;
-  if (occ > 8) occ = 8;
+  if (occ > 16) occ = 16;
+  int threads = kEvalMaxThreads / occ / 32 * 32;
+  if (threads < 32) threads = 32;
+  w.occ_eval = occ;
+  w.threads_eval = threads;
   w.grid_eval = sms * occ;
-  w.grid_predict = sms * occ;
+  int occ_p = occ > 4 ? 4 : occ;   // 128-thread prediction CTAs
+  w.grid_predict = sms * occ_p;
   if (window <= 0) window = kDefaultWindow;
   size_t tasks = B * (size_t)(S > 0 ? S : 1);
   if ((size_t)window > tasks) window = (int)(tasks > 0 ? tasks : 1);
@@ -114,7 +122,7 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.run_nev = take(tasks * 4);
   w.run_end = take(tasks * 4);
   w.starts = take((size_t)(S > 0 ? S : 1) * FG_MAXP * 8);
-  w.gA_stride = w.globalA ? np * ld : 0;
+  w.gA_stride = w.globalA ? gp_mat_doubles((int)np) : 0;
   w.gA = take((size_t)w.grid_eval * w.gA_stride * 8);
   w.gV_stride = np * GP_QC;
   w.gV = take((size_t)w.grid_predict * w.gV_stride * 8);
@@ -137,7 +145,7 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
-  __shared__ double red[64];
+  __shared__ double red[GP_RED];
   DevCtx c;
   for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
     const int64_t o = a.offsets[cu];
@@ -168,8 +176,7 @@ __device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t c
 template <bool kGlobalA>
 __device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
   if (!kGlobalA) {
-    const int np = gp_pad(n);
-    return gp_carve(smem, smem + (size_t)np * gp_ld(np), n);
+    return gp_carve(smem, smem + gp_mat_doubles(gp_pad(n)), n);
   }
   // vectors in shared memory, the matrix in this CTA's global slab (stays in L2)
   return gp_carve(gA + (size_t)blockIdx.x * gA_stride, smem, n);
@@ -177,7 +184,7 @@ __device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stri
 
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
 template <bool kGlobalA>
-__global__ void __launch_bounds__(kEvalThreads, 2) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
+__global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
                                                             double* gA, size_t gA_stride, long long* marks) {
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
@@ -247,7 +254,7 @@ __global__ void fit_init_kernel(FitDev d) {
 }
 
 template <bool kGlobalA>
-__global__ void __launch_bounds__(kEvalThreads, 2) fit_eval_kernel(FitDev d, int round) {
+__global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
   const int count = d.counts[round];
@@ -360,7 +367,7 @@ struct PredictArgs {
 };
 
 template <bool kGlobalA>
-__global__ void __launch_bounds__(kPredictThreads) predict_kernel(PredictArgs a) {
+__global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double tlim[2];
   DevCtx c;
@@ -539,11 +546,11 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
   if (w.globalA) {
     rc = set_smem(lml_kernel<true>, w.smem_eval);
     if (rc) return rc;
-    lml_kernel<true><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, at<double>(workspace, w.gA), w.gA_stride, marks);
+    lml_kernel<true><<<grid, w.threads_eval, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, at<double>(workspace, w.gA), w.gA_stride, marks);
   } else {
     rc = set_smem(lml_kernel<false>, w.smem_eval);
     if (rc) return rc;
-    lml_kernel<false><<<grid, kEvalThreads, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, nullptr, 0, marks);
+    lml_kernel<false><<<grid, w.threads_eval, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, nullptr, 0, marks);
   }
   CU_TRY(cudaGetLastError());
   const unsigned g1 = (unsigned)((B + 255) / 256);
@@ -622,8 +629,8 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
         for (int i = 0; i < 3; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); ev.push_back(e); }
         cudaEventRecord(ev[3 * round], st);
       }
-      if (w.globalA) fit_eval_kernel<true><<<w.grid_eval, kEvalThreads, w.smem_eval, st>>>(d, round);
-      else fit_eval_kernel<false><<<w.grid_eval, kEvalThreads, w.smem_eval, st>>>(d, round);
+      if (w.globalA) fit_eval_kernel<true><<<w.grid_eval, w.threads_eval, w.smem_eval, st>>>(d, round);
+      else fit_eval_kernel<false><<<w.grid_eval, w.threads_eval, w.smem_eval, st>>>(d, round);
       if (prof) cudaEventRecord(ev[3 * round + 1], st);
       fit_step_kernel<<<step_grid, 128, 0, st>>>(d, round);
       if (prof) cudaEventRecord(ev[3 * round + 2], st);
@@ -647,7 +654,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     double* pr = opt->profile;
     pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = 2.0 * round + 4.0; pr[4] = w.window; pr[5] = w.grid_eval;
-    pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0;
+    pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0; pr[8] = w.threads_eval; pr[9] = w.occ_eval;
   }
   if (!finished) {
     fit_flush_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);

@@ -203,7 +203,7 @@ class GPEngine:
             if return_runs:
                 out["run_lml"] = self._new(B, S)
                 out["run_theta"] = self._new(B, S, P)
-            prof = (ctypes.c_double * 8)() if profile else None
+            prof = (ctypes.c_double * 10)() if profile else None
             if profile:
                 o.profile = ctypes.cast(prof, ctypes.POINTER(ctypes.c_double))
             ws = self._workspace(batch, P, S, window)
@@ -212,7 +212,7 @@ class GPEngine:
                                                    self._p(out.get("run_lml")), self._p(out.get("run_theta")), self._p(ws), ws.numel(),
                                                    self._stream()))
             if profile:
-                keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a")
+                keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a", "threads_eval", "ctas_per_sm")
                 out["profile"] = {k: float(prof[i]) for i, k in enumerate(keys)}
             return out
 

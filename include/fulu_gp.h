@@ -77,10 +77,10 @@ typedef struct fulu_gp_fit_options {
   double pgtol;              /* 1e-5 */
   double lower[FULU_GP_MAX_PARAMS];   /* log-bounds, ln(1e-5) */
   double upper[FULU_GP_MAX_PARAMS];   /* ln(1e5) */
-  double* profile;           /* optional HOST pointer to 8 doubles, filled on return: [0] evaluation rounds, [1] ms spent in the
+  double* profile;           /* optional HOST pointer to 10 doubles, filled on return: [0] evaluation rounds, [1] ms spent in the
                                 evaluation kernel (CUDA events on `stream`), [2] ms in the optimiser-step kernel, [3] kernels launched,
                                 [4] window, [5] evaluation grid (CTAs), [6] dynamic shared memory per CTA (bytes), [7] 1 if K lives in
-                                global memory.  NULL = no per-launch timing. */
+                                global memory, [8] threads per evaluation CTA, [9] evaluation CTAs per SM.  NULL = no per-launch timing. */
 } fulu_gp_fit_options;
 
 int fulu_gp_abi_version(void);

@@ -60,7 +60,7 @@ static void run_block(int nthr, F&& body) {
 extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const double* ferr, const int32_t* band, const double* loglam,
                                int n_bands, int use_err, double alpha0, int nthr, double* xs, double* y, double* al, double* lam,
                                double* stats) {
-  std::vector<double> red(64);
+  std::vector<double> red(GP_RED);
   int status = 0;
   run_block(nthr, [&](HostCtx& c) {
     int st = gp_prepare_curve(c, n, t, flux, ferr, band, loglam, n_bands, use_err, alpha0, xs, y, al, lam, stats, red.data());
@@ -76,7 +76,7 @@ extern "C" int host_gp_lml(int n, const double* xs, const int32_t* band, const d
   int okout = 0;
   const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
-    GpSmem s = gp_carve(smem.data(), smem.data() + (size_t)np * gp_ld(np), n);
+    GpSmem s = gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
     double l, g[4];
     bool ok;
     gp_eval_lml_grad(c, cv, theta, s, l, g, ok);
@@ -95,7 +95,7 @@ extern "C" int host_gp_predict(int n, const double* xs, const int32_t* band, con
   int status = 0;
   const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
-    GpSmem s = gp_carve(smem.data(), smem.data() + (size_t)np * gp_ld(np), n);
+    GpSmem s = gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
     double l;
     int st = gp_predict_curve(c, cv, theta, stats, qd, s, V.data(), mean, stdv, l);
     if (c.tid == 0) { status = st; *lml = l; }
