@@ -14,7 +14,11 @@
 //   g_k = 1/2 sum_ij (a_i a_j - K^-1_ij) dK_ij/dtheta_k                  (Eq. 5.9)
 //
 // Every O(N^3) piece runs on 8x8 tiles through the FP64 tensor-core instruction (DMMA m8n8k4; on B200 it sustains the full
-// FP64 rate with an eighth of the issue slots of a DFMA loop, measured 37.2 vs 33.9 TFLOP/s).
+// FP64 rate with an eighth of the issue slots of a DFMA loop, measured 37.2 vs 33.9 TFLOP/s).  The diagonal 8x8 blocks are
+// factored by one warp holding the block in accumulator layout (two doubles per lane, shuffles for the pivot column), which
+// produces the block's inverse X_D = L_D^-1 in the same sweep; X_D is what gets stored on the diagonal, so the panel solve is a
+// DMMA product P X_D^T, the triangular inverse finds its diagonal blocks done, and nothing in the kernel needs more than a
+// handful of registers per thread (64 registers -> 1024 resident threads per SM).
 //
 // Storage (v3).  Only the lower triangle exists: tile (I, J), J <= I < T (T = np / 8, np = N padded to a multiple of 8 with an
 // identity block) lives at 64 (I (I + 1) / 2 + J) doubles, followed by one border tile-row I = T (tiles (T, 0..T-1)) whose row 0
@@ -30,6 +34,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GP_DEV __device__ __forceinline__
@@ -41,7 +46,7 @@
 
 #define GP_NB 8
 #define GP_LOG_2PI 1.8378770664093453
-#define GP_RED 96
+#define GP_RED 192
 // Cholesky step: tiles of the trailing update handed to each of the other warps while warp 0 factors the next diagonal block
 #ifndef GP_CHOL8_TILES
 #define GP_CHOL8_TILES 10
@@ -60,15 +65,14 @@ struct GpSmem {
   double* A;      // packed tiles: T (T + 1) / 2 lower tiles, then T border tiles
   double* u;      // np   x_i0 / l_t
   double* v;      // np   x_i1 / l_lambda
-  double* rdiag;  // np   1 / L_ii
-  double* red;    // reduction scratch, GP_RED doubles (16 warps x 6 values)
+  double* red;    // reduction scratch, GP_RED doubles (32 warps x 6 values)
   int* flag;      // [0] = Cholesky breakdown
   int np, T;
 };
 
 GP_HD int gp_pad(int n) { return (n + GP_NB - 1) / GP_NB * GP_NB; }
 GP_HD size_t gp_mat_doubles(int np) { const size_t T = (size_t)np / GP_NB; return 64 * (T * (T + 1) / 2 + T); }
-GP_HD size_t gp_vec_doubles(int np) { return 3 * (size_t)np + GP_RED + 2; }
+GP_HD size_t gp_vec_doubles(int np) { return 2 * (size_t)np + GP_RED + 2; }
 // doubles of shared memory needed for a curve of n observations (matrix + vectors)
 GP_HD size_t gp_smem_doubles(int n) {
   const int np = gp_pad(n);
@@ -84,7 +88,6 @@ GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
   double* p = vec;
   s.u = p; p += s.np;
   s.v = p; p += s.np;
-  s.rdiag = p; p += s.np;
   s.red = p; p += GP_RED;
   s.flag = (int*)p;
   return s;
@@ -154,10 +157,45 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, double
   if (c.tid == 0) s.flag[0] = 0;
 }
 
+// exp(x) for x <= 0, branch free so that several evaluations interleave: k = rint(x log2 e), r = x - k ln 2 (two-part
+// constant), degree-13 Taylor polynomial on |r| <= 0.347, 2^k by exponent arithmetic; results below 2^-1021 flush to zero.
+// Maximum error 0.63 ulp over [-708, 0] (tests/test_block_host.py::test_exp_neg_accuracy); the library exp is 0.5 ulp.
+GP_HD double gp_exp_neg(double x) {
+  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);   // low word of t = k
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;
+  p = fma(p, r, 2.08767569878681e-09);
+  p = fma(p, r, 2.505210838544172e-08);
+  p = fma(p, r, 2.755731922398589e-07);
+  p = fma(p, r, 2.7557319223985893e-06);
+  p = fma(p, r, 2.48015873015873e-05);
+  p = fma(p, r, 0.0001984126984126984);
+  p = fma(p, r, 0.001388888888888889);
+  p = fma(p, r, 0.008333333333333333);
+  p = fma(p, r, 0.041666666666666664);
+  p = fma(p, r, 0.16666666666666666);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+#if defined(__CUDA_ARCH__)
+  const double res = __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+#else
+  int64_t tb, pb;
+  memcpy(&tb, &t, 8);
+  memcpy(&pb, &p, 8);
+  pb += (int64_t)(int32_t)(tb & 0xffffffff) << 52;
+  double res;
+  memcpy(&res, &pb, 8);
+#endif
+  return x < -708.0 ? 0.0 : res;
+}
+
 // c * exp(-1/2 |x_i/l - x_j/l|^2) for i != j  (kernels.py:1561-1565)
 GP_DEV double gp_kernel_value(double cst, double ui, double vi, double uj, double vj) {
   const double du = ui - uj, dv = vi - vj;
-  return cst * exp(-0.5 * (du * du + dv * dv));
+  return cst * gp_exp_neg(-0.5 * (du * du + dv * dv));
 }
 
 // K into the lower tiles, y^T into row 0 of the border tile-row.  One warp per tile; lane (g, t) writes (g, t) and (g, 4 + t).
@@ -177,8 +215,11 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, double c
     } else {
       const int i = 8 * I + g;
       const double ui = s.u[i], vi = s.v[i];
-      v0 = (i > j0 && i < n) ? gp_kernel_value(cst, ui, vi, s.u[j0], s.v[j0]) : 0.0;
-      v1 = (i > j1 && i < n) ? gp_kernel_value(cst, ui, vi, s.u[j1], s.v[j1]) : 0.0;
+      // diagonal tiles are assembled in full (both triangles): the warp-level factorisation keeps them symmetric
+      v0 = gp_kernel_value(cst, ui, vi, s.u[j0], s.v[j0]);
+      v1 = gp_kernel_value(cst, ui, vi, s.u[j1], s.v[j1]);
+      if (i >= n || j0 >= n) v0 = 0.0;
+      if (i >= n || j1 >= n) v1 = 0.0;
       // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding
       if (i == j0) v0 = (i < n) ? (cst + s2) + cv.al[i] : 1.0;
       if (i == j1) v1 = (i < n) ? (cst + s2) + cv.al[i] : 1.0;
@@ -191,66 +232,80 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, double c
 }
 
 // ---------------------------------------------------------------------------------------------- Cholesky
-// 8x8 diagonal tile (lower part) -> L in place, rdiag[0..7] = 1/L_jj.  Division-free: r = rsqrt(d), L_jj = d r.
-// Executed by ONE thread; everything is unrolled into registers so the scheduler starts column j+1's rsqrt as early as possible.
-GP_DEV bool gp_chol8(double* tp, double* rdiag) {
-  double a[8][8];
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc)
-#pragma unroll
-    for (int r = cc; r < 8; ++r) a[r][cc] = tp[gp_el(r, cc)];
+// Warp-level Cholesky of one 8x8 diagonal block held in accumulator layout (lane (g, t): a0 = A[g][t], a1 = A[g][4 + t], the
+// block symmetric), together with the inverse of its factor: on exit z0/z1 hold X = L^-1 in the same layout (exact zeros above
+// the diagonal) and logdet has been reduced by sum_j log(1 / L_jj).  Right-looking, one pivot column per step:
+//   r = rsqrt(A_jj);  l_ij = A_ij r;  A_ic -= l_ij l_cj;        X_j: = Z_j: r;  Z_i: -= l_ij X_j:   (Z starts as I)
+// Same arithmetic as a scalar column Cholesky (division free: L_jj = A_jj r is never needed), but every lane carries two
+// matrix entries instead of one thread carrying 36, and the pivot column travels by shuffles.
+// 1 / sqrt(d) for a pivot d in (1e-300, 1e300): hardware seed (MUFU.RSQ64H, ~2^-20) and two Newton steps.  A few instructions
+// on the longest dependent chain of the whole evaluation (N of these in sequence), where the library rsqrt spends twenty.
+GP_DEV double gp_rsqrt(double d) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-(d * y), y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-(d * y), y, 1.0);
+  return fma(0.5 * y, e, y);
+#else
+  return 1.0 / sqrt(d);
+#endif
+}
+
+template <class Ctx>
+GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, double& logdet) {
+  const int g = c.lane >> 2, t = c.lane & 3;
+  z0 = (g == t) ? 1.0 : 0.0;
+  z1 = (g == 4 + t) ? 1.0 : 0.0;
   bool ok = true;
+  double rprod = 1.0;   // running product of 1 / L_jj, folded into the log every four pivots (pivots are within (1e-300, 1e300))
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    double d = a[j][j];
-    if (!(d > 0.0) || !(d < 1.0e300)) { ok = false; d = 1.0; }
-#if defined(__CUDA_ARCH__)
-    const double r = rsqrt(d);
-#else
-    const double r = 1.0 / sqrt(d);
-#endif
-    a[j][j] = d * r;
-    rdiag[j] = r;
-#pragma unroll
-    for (int i = j + 1; i < 8; ++i) a[i][j] *= r;
-#pragma unroll
-    for (int cc = j + 1; cc < 8; ++cc)
-#pragma unroll
-      for (int i = cc; i < 8; ++i) a[i][cc] -= a[i][j] * a[cc][j];
+    const int jt = j & 3;
+    const double aj = (j < 4) ? a0 : a1;           // this lane's entry of block column (j & 3) / (4 + (j & 3))
+    double d = c.shfl(aj, 4 * j + jt);              // A[j][j]
+    const double cg = c.shfl(aj, 4 * g + jt);       // A[g][j]
+    const double c0 = c.shfl(aj, 4 * t + jt);       // A[t][j]
+    const double c1 = c.shfl(aj, 4 * (4 + t) + jt); // A[4 + t][j]
+    const double zj0 = c.shfl(z0, 4 * j + t);       // Z[j][t]
+    const double zj1 = c.shfl(z1, 4 * j + t);       // Z[j][4 + t]
+    if (!(d > 1.0e-300) || !(d < 1.0e300)) { ok = false; d = 1.0; }
+    const double r = gp_rsqrt(d);
+    rprod *= r;
+    const double lg = cg * r, l0 = c0 * r, l1 = c1 * r, x0 = zj0 * r, x1 = zj1 * r;
+    if (g > j) {
+      a0 -= lg * l0;
+      a1 -= lg * l1;
+      z0 -= lg * x0;
+      z1 -= lg * x1;
+    } else if (g == j) {
+      z0 = x0;
+      z1 = x1;
+    }
+    if ((j & 3) == 3) {   // fold into the running log every four pivots: rprod stays far from over/underflow
+      logdet -= log(rprod);
+      rprod = 1.0;
+    }
   }
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc)
-#pragma unroll
-    for (int r = cc; r < 8; ++r) tp[gp_el(r, cc)] = a[r][cc];
   return ok;
 }
 
-// rows below the diagonal tile kb (border row included): solve x L_D^T = p by forward substitution, one row per thread
+// rows below the diagonal tile kb (border tile included): P_I <- P_I X_D^T, the panel solve x L_D^T = p as a DMMA product
+// with the inverted diagonal block.  One tile per warp at a time.
 template <class Ctx>
-GP_DEV void gp_panel_solve(Ctx& c, const GpSmem& s, int kb) {
-  const int T = s.T, rows = (T - kb - 1) * 8 + 1;   // + 1: row 0 of the border tile
-  if (c.tid >= rows) return;
+GP_DEV void gp_panel_mult(Ctx& c, const GpSmem& s, const GpFrag& f, int kb) {
+  const int T = s.T;
+  if (kb + 1 + c.warp > T) return;
   const double* D = s.A + gp_tile(kb, kb);
-  double l[8][8], r[8];
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
-    r[cc] = s.rdiag[8 * kb + cc];
-#pragma unroll
-    for (int k = 0; k < cc; ++k) l[cc][k] = D[gp_el(cc, k)];
-  }
-  for (int i = c.tid; i < rows; i += c.nthr) {
-    const int I = kb + 1 + (i >> 3), rr = i & 7;
+  const double b0 = D[f.b0], b1 = D[f.b1];   // B[k][n] = X_D[n][k]
+  for (int I = kb + 1 + c.warp; I <= T; I += c.nwarp) {
     double* tp = s.A + gp_tile(I, kb);
-    double x[8];
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      double acc = tp[gp_el(rr, cc)];
-#pragma unroll
-      for (int k = 0; k < cc; ++k) acc -= x[k] * l[cc][k];
-      x[cc] = acc * r[cc];
-    }
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) tp[gp_el(rr, cc)] = x[cc];
+    double w0 = 0.0, w1 = 0.0;
+    c.mma(w0, w1, tp[f.a0], b0);
+    c.mma(w0, w1, tp[f.a1], b1);
+    tp[f.a0] = w0;
+    tp[f.a1] = w1;
   }
 }
 
@@ -278,98 +333,64 @@ GP_DEV void gp_chol_update_tiles(Ctx& c, const GpSmem& s, const GpFrag& f, int k
 }
 
 // Blocked right-looking Cholesky of the bordered matrix with one-step lookahead: warp 0 brings the next diagonal tile up to
-// date and one of its threads factors it (the chain of 8 reciprocal square roots) while the other warps apply the panel to
-// the rest of the trailing matrix.  Sets flag on breakdown.  On exit the lower tiles hold L, rdiag holds 1/L_ii and row 0 of
-// the border tile-row holds z^T = (L^-1 y)^T.
+// date and factors it in registers while the other warps apply the panel to the rest of the trailing matrix.  Sets flag on
+// breakdown.  On exit the strictly-lower tiles hold L, the diagonal tiles hold the INVERSES of L's diagonal blocks, row 0 of
+// the border tile-row holds z^T = (L^-1 y)^T, and logdet (valid in lane 0 of warp 0, zero elsewhere) = sum_i log L_ii.
 template <class Ctx>
-GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s) {
+GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, double& logdet) {
   const int T = s.T;
   const GpFrag f = gp_frag(c.lane);
-  if (c.tid == 0) {
-    if (!gp_chol8(s.A + gp_tile(0, 0), s.rdiag)) s.flag[0] = 1;
+  double ld = 0.0;
+  if (c.warp == 0) {
+    double* D = s.A + gp_tile(0, 0);
+    double z0, z1;
+    if (!gp_chol8_warp(c, D[f.a0], D[f.a1], z0, z1, ld) && c.lane == 0) s.flag[0] = 1;
+    D[f.a0] = z0;
+    D[f.a1] = z1;
   }
   c.sync();
-  gp_panel_solve(c, s, 0);
+  gp_panel_mult(c, s, f, 0);
   c.sync();
   for (int kb = 0; kb + 1 < T; ++kb) {
     // trailing matrix: Tr x Tr lower tiles plus the border tile-row (ta = Tr) over the Tr tile-columns
     const int Tr = T - kb - 1, ntile = Tr * (Tr + 1) / 2 + Tr;
-    if (c.nwarp == 1) {
-      gp_chol_update_tiles(c, s, f, kb, 0, 1, 1);
-      c.warp_sync();
-      if (c.lane == 0) {
-        if (!gp_chol8(s.A + gp_tile(kb + 1, kb + 1), s.rdiag + 8 * (kb + 1))) s.flag[0] = 1;
-      }
-      c.warp_sync();
-      gp_chol_update_tiles(c, s, f, kb, 1, 1, ntile);
+    // segment A (tiles 1 .. nA) is shared by warps 1.., segment B (the rest) by all warps once warp 0 is back
+    int nA = GP_CHOL8_TILES * (c.nwarp - 1);
+    if (nA > ntile - 1) nA = ntile - 1;
+    if (c.warp == 0) {
+      // critical path first: the next diagonal tile, updated and factored without leaving the registers
+      const double* P = s.A + gp_tile(kb + 1, kb);
+      double* D = s.A + gp_tile(kb + 1, kb + 1);
+      double a0 = D[f.a0], a1 = D[f.a1], z0, z1;
+      c.mma(a0, a1, -P[f.a0], P[f.b0]);
+      c.mma(a0, a1, -P[f.a1], P[f.b1]);
+      if (!gp_chol8_warp(c, a0, a1, z0, z1, ld) && c.lane == 0) s.flag[0] = 1;
+      D[f.a0] = z0;
+      D[f.a1] = z1;
     } else {
-      // segment A (tiles 1 .. nA) is shared by warps 1.., segment B (the rest) by all warps once warp 0 is back
-      int nA = GP_CHOL8_TILES * (c.nwarp - 1);
-      if (nA > ntile - 1) nA = ntile - 1;
-      if (c.warp == 0) {
-        gp_chol_update_tiles(c, s, f, kb, 0, 1, 1);   // critical path first: the next diagonal tile
-        c.warp_sync();
-        if (c.lane == 0) {
-          if (!gp_chol8(s.A + gp_tile(kb + 1, kb + 1), s.rdiag + 8 * (kb + 1))) s.flag[0] = 1;
-        }
-        c.warp_sync();
-      } else {
-        gp_chol_update_tiles(c, s, f, kb, c.warp, c.nwarp - 1, 1 + nA);
-      }
-      gp_chol_update_tiles(c, s, f, kb, 1 + nA + c.warp, c.nwarp, ntile);
+      gp_chol_update_tiles(c, s, f, kb, c.warp, c.nwarp - 1, 1 + nA);
     }
+    gp_chol_update_tiles(c, s, f, kb, 1 + nA + c.warp, c.nwarp, ntile);
     c.sync();
-    gp_panel_solve(c, s, kb + 1);
+    gp_panel_mult(c, s, f, kb + 1);
     c.sync();
   }
+  logdet = (c.tid == 0) ? ld : 0.0;
 }
 
-// After gp_cholesky: this thread's share of z.z (= y^T K^-1 y) and of sum log L_ii.
+// After gp_cholesky: this thread's share of z.z (= y^T K^-1 y).
 template <class Ctx>
-GP_DEV void gp_collect(Ctx& c, const GpSmem& s, double& quad, double& logdet) {
+GP_DEV double gp_collect(Ctx& c, const GpSmem& s) {
   const int np = s.np, T = s.T;
-  quad = 0.0;
-  logdet = 0.0;
+  double quad = 0.0;
   for (int i = c.tid; i < np; i += c.nthr) {
     const double zi = s.A[gp_tile(T, i >> 3) + gp_el(0, i & 7)];
     quad += zi * zi;
-    logdet -= log(s.rdiag[i]);   // log L_ii = -log(1 / L_ii); rdiag and the border row survive until the inverse's first barrier
   }
+  return quad;
 }
 
 // ---------------------------------------------------------------------------------------------- triangular inverse
-// inverse of every 8x8 diagonal tile in place (one thread per tile, division-free thanks to rdiag); the strict upper part of
-// the tile is zeroed so that later tile products need no masks
-template <class Ctx>
-GP_DEV void gp_invert_diag_blocks(Ctx& c, const GpSmem& s) {
-  const int T = s.T;
-  for (int kb = c.tid; kb < T; kb += c.nthr) {
-    double* tp = s.A + gp_tile(kb, kb);
-    double l[8][8], r[8];
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      r[cc] = s.rdiag[8 * kb + cc];
-#pragma unroll
-      for (int i = cc + 1; i < 8; ++i) l[i][cc] = tp[gp_el(i, cc)];
-    }
-    // column by column; L stays in registers, so X can overwrite it in memory as soon as a column is done
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double x[8];
-      x[j] = r[j];
-#pragma unroll
-      for (int i = j + 1; i < 8; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = j; k < i; ++k) acc -= l[i][k] * x[k];
-        x[i] = acc * r[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tp[gp_el(i, j)] = (i >= j) ? x[i] : 0.0;
-    }
-  }
-}
-
 // In place: M = [[L, 0], [z^T, 1]] -> M^-1 = [[X, 0], [-a^T, 1]], block columns from the last to the first.  For block column
 // kb with rows I in (kb, T]:   W_I = -M_I,kb X_kb,kb (in place), then X_I,kb = sum_{kb < K <= I} X_I,K W_K, written over W_I.
 // Row I only reads W_K with K <= I, so rows are finished from the bottom up in waves of one row per warp, with one barrier
@@ -379,8 +400,7 @@ GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
   const int T = s.T;
   double* A = s.A;
   const GpFrag f = gp_frag(c.lane);
-  gp_invert_diag_blocks(c, s);
-  c.sync();
+  // (the diagonal tiles already hold the inverted diagonal blocks: gp_cholesky)
   for (int kb = T - 1; kb >= 0; --kb) {
     // (1) W_I = -(M_I,kb X11)
     {
@@ -458,7 +478,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double cst, double
       if (i > j) {
         if (i < n) {
           const double du = ui - s.u[j], dv = vi - s.v[j];
-          const double wk = w * (cst * exp(-0.5 * (du * du + dv * dv)));   // K_ij again (not stored)
+          const double wk = w * (cst * gp_exp_neg(-0.5 * (du * du + dv * dv)));   // K_ij again (not stored)
           tr[0] += wk;
           tr[1] += wk * (du * du);
           tr[2] += wk * (dv * dv);
@@ -484,7 +504,8 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
   gp_assemble(c, cv, s, cst, s2);
   c.sync();
   c.mark(2);
-  gp_cholesky(c, s);
+  double v[6];
+  gp_cholesky(c, s, v[5]);
   c.mark(3);
   ok = (s.flag[0] == 0);
   if (!ok) {
@@ -493,8 +514,7 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
     c.sync();
     return;
   }
-  double v[6];
-  gp_collect(c, s, v[4], v[5]);
+  v[4] = gp_collect(c, s);   // the border row is next written after the inverse's first barrier
   c.mark(4);
   gp_trtri(c, s);
   c.mark(5);
@@ -520,11 +540,11 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const double* theta, const 
   c.sync();
   gp_assemble(c, cv, s, cst, s2);
   c.sync();
-  gp_cholesky(c, s);
+  double v[2];
+  gp_cholesky(c, s, v[1]);
   ok = (s.flag[0] == 0);
   if (!ok) { lml = -INFINITY; c.sync(); return; }
-  double v[2];
-  gp_collect(c, s, v[0], v[1]);
+  v[0] = gp_collect(c, s);
   gp_block_sum(c, v, s.red);
   lml = -0.5 * v[0] - v[1] - 0.5 * (double)cv.n * GP_LOG_2PI;
 }
@@ -536,57 +556,41 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const double* theta, const 
 //                                                  levels of 1e-5 the explicit-inverse product loses ~40x in the variance)
 //   mean* = k*.alpha = v.z                        (_gpr.py:446-447)
 //   |v|^2 -> var = (c + s2) - |v|^2               (_gpr.py:480-481)
-// Each thread owns column q of V (V[i * ldv + q]); rows are processed four at a time so each v_j load feeds four FMAs.
+// Each thread owns column q of V (V[i * ldv + q]).  Block substitution over the 8x8 tiles: v_I = X_II (k*_I - sum_{J<I} L_IJ v_J)
+// with X_II = L_II^-1 from gp_cholesky (explicit inverses only of the 8x8 diagonal blocks; between blocks it is substitution).
 #define GP_QC 128   // query columns per pass (= threads that own a column)
 
 GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, double vq, double* V, int ldv, double& mean, double& v2) {
   const double* A = s.A;
   const double* bord = A + gp_tile(s.T, 0);
   double m = 0.0, q2 = 0.0;
-  for (int i0 = 0; i0 < n; i0 += 4) {
-    const int I = i0 >> 3, rho = i0 & 4;
-    double acc[4];
+  for (int I = 0; 8 * I < n; ++I) {
+    double acc[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = i0 + r;
-      double k = 0.0;
-      if (i < n) k = gp_kernel_value(cst, uq, vq, s.u[i], s.v[i]);
-      acc[r] = k;
+    for (int r = 0; r < 8; ++r) {
+      const int i = 8 * I + r;
+      acc[r] = (i < n) ? gp_kernel_value(cst, uq, vq, s.u[i], s.v[i]) : 0.0;
     }
     const double* row = A + gp_tile(I, 0);
-    const double* vp = V;
+    double* vp = V;
     for (int J = 0; J < I; ++J) {
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
         const double vj = vp[cc * ldv];
-        const double* e = row + 8 * cc;
-        const int sw = gp_swz(cc);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] -= e[(rho + r) ^ sw] * vj;
+        for (int r = 0; r < 8; ++r) acc[r] -= row[gp_el(r, cc)] * vj;
       }
       row += 64;
       vp += 8 * ldv;
     }
-    // `row` is the diagonal tile now: its first four columns when this is the tile's second half
-    if (rho) {
+    // `row` is the diagonal tile now: X_II, lower triangular
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const double vj = vp[cc * ldv];
+    for (int r = 0; r < 8; ++r) {
+      double a = 0.0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] -= row[gp_el(4 + r, cc)] * vj;
-      }
-    }
-    // 4x4 diagonal block by substitution (rows >= n are identity padding)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = i0 + r;
-      double a = acc[r];
-#pragma unroll
-      for (int k = 0; k < r; ++k) a -= row[gp_el(rho + r, rho + k)] * acc[k];
-      a = a * s.rdiag[i];
-      acc[r] = a;
-      V[i * ldv] = a;
-      m += a * bord[64 * I + gp_el(0, rho + r)];
+      for (int k = 0; k <= r; ++k) a += row[gp_el(r, k)] * acc[k];
+      vp[r * ldv] = a;
+      m += a * bord[64 * I + gp_el(0, r)];
       q2 += a * a;
     }
   }

@@ -38,10 +38,11 @@ struct DevCtx {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
   }
   __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 };
 
-constexpr int kEvalMaxThreads = 512;   // 128 registers per thread fill the register file at 512 threads per SM:
-                                       // an evaluation CTA gets 512 / (CTAs per SM) threads
+constexpr int kEvalMaxThreads = 1024;  // 64 registers per thread fill the register file at 1024 threads per SM:
+                                       // an evaluation CTA gets 1024 / (CTAs per SM) threads
 constexpr int kPredictThreads = 128;
 constexpr int kPrepThreads = 128;
 constexpr size_t kMaxSmem = 227 * 1024;

@@ -102,10 +102,12 @@ class DeviceBatch:
         self.c = c
 
     @staticmethod
-    def from_host(b: CurveBatch, device=None, use_err=False, pinned=None):
-        """H2D copy of a host batch.  `pinned`: optional dict of pinned staging tensors (see HostStaging)."""
+    def from_host(b: CurveBatch, device=None, use_err=False, pinned=None, n_max=None):
+        """H2D copy of a host batch.  `pinned`: optional dict of pinned staging tensors (see HostStaging).  `n_max`: an upper
+        bound on the curve length (default: the batch's own maximum); it fixes the launch geometry."""
         device = _require_cuda(device)
-        n_max = int(b.lengths().max()) if b.n_curves else 0
+        own = int(b.lengths().max()) if b.n_curves else 0
+        n_max = own if n_max is None else max(int(n_max), own)
         if pinned is None:
             src = dict(offsets=torch.from_numpy(b.offsets), t=torch.from_numpy(b.t), flux=torch.from_numpy(b.flux),
                        flux_err=torch.from_numpy(b.flux_err), band=torch.from_numpy(b.band), loglam=torch.from_numpy(b.loglam))
@@ -260,7 +262,9 @@ class GPEngine:
 
 
 # ------------------------------------------------------------------------------------------------ batched entry point
-N_BUCKETS = (32, 64, 100, 128, 156, 256, 512, 1024, 2048, 4096)
+# upper bounds of the length classes one launch covers: the class bound (not the batch's own maximum) fixes the launch geometry
+# (shared memory, CTAs per SM, threads per CTA), so a curve's result does not depend on what else is in the batch
+N_BUCKETS = (32, 64, 104, 128, 160, 216, 304, 512, 1024, 2048, 4096)
 
 
 @dataclass
@@ -296,9 +300,9 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     lengths = curves.lengths()
     groups = bucket_curves(lengths) if B else []
     single = len(groups) == 1 and len(groups[0][1]) == B
-    for _, idx in groups:
+    for bound, idx in groups:
         sub = curves if single else curves.take(idx)
-        db = DeviceBatch.from_host(sub, engine.device, use_err=use_err, pinned=pinned if single else None)
+        db = DeviceBatch.from_host(sub, engine.device, use_err=use_err, pinned=pinned if single else None, n_max=bound)
         fit = engine.fit(db, spec, window=window)
         tmn = None if t_min is None else np.asarray(t_min, np.float64)[idx]
         tmx = None if t_max is None else np.asarray(t_max, np.float64)[idx]

@@ -33,6 +33,13 @@ struct HostCtx {
     }
     ws->bar.arrive_and_wait();
   }
+  double shfl(double v, int src) {
+    ws->x[lane] = v;
+    ws->bar.arrive_and_wait();
+    double r = ws->x[src & 31];
+    ws->bar.arrive_and_wait();
+    return r;
+  }
   double shfl_xor(double v, int m) {
     ws->x[lane] = v;
     ws->bar.arrive_and_wait();
@@ -101,4 +108,8 @@ extern "C" int host_gp_predict(int n, const double* xs, const int32_t* band, con
     if (c.tid == 0) { status = st; *lml = l; }
   });
   return status;
+}
+
+extern "C" void host_gp_exp_neg(int n, const double* x, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = gp_exp_neg(x[i]);
 }

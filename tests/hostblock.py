@@ -70,3 +70,11 @@ def predict_points(p, theta, qt, qband, nthr=32):
     st = lib.host_gp_predict(p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), _dp(p.stats), m, 0,
                              ctypes.c_double(0), ctypes.c_double(0), _dp(qt), _ip(qband), nthr, _dp(mean), _dp(std), ctypes.byref(lml))
     return mean, std, lml.value, st
+
+
+def exp_neg(x):
+    lib = _lib()
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.empty_like(x)
+    lib.host_gp_exp_neg(len(x), _dp(x), _dp(out))
+    return out

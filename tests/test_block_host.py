@@ -77,3 +77,14 @@ def test_tile_swizzle_is_conflict_free():
                 a = f(lane >> 2, lane & 3)
                 banks.setdefault(a % 16, set()).add(a)
             assert max(len(v) for v in banks.values()) == 1
+
+
+def test_exp_neg_accuracy():
+    """gp_exp_neg (the kernel-matrix exponential) against a long-double reference: <= 0.7 ulp on [-708, 0], exact at 0, 0 below."""
+    rng = np.random.default_rng(0)
+    x = -(10.0 ** rng.uniform(-8, np.log10(708.0), 400000))
+    got = H.exp_neg(x)
+    ref = np.exp(x.astype(np.longdouble))
+    err = np.abs((got - ref) / ref).astype(np.float64) / 2.0 ** -52
+    assert err.max() < 0.7
+    np.testing.assert_array_equal(H.exp_neg(np.array([0.0, -0.0, -1e-300, -709.0, -1e6, -np.inf])), [1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
