@@ -7,7 +7,7 @@
 //
 // What is computed (reference lines: sklearn/gaussian_process/_gpr.py:583-651, kernels.py:1558-1585):
 //   K   = c * exp(-1/2 |x_i/l - x_j/l|^2) + (s2 + alpha_i) I            (a4)
-//   L   = chol(K)                       blocked right-looking, NB = 8    (a5; LAPACK dpotrf in the reference)
+//   L   = chol(K)                       blocked left-looking, NB = 8     (a5; LAPACK dpotrf in the reference)
 //   X   = L^-1                          blocked in-place triangular inverse (replaces the identity-RHS dpotrs)
 //   z   = L^-1 y, a = X^T z;  LML = -1/2 z.z - sum log L_ii - N/2 log 2pi
 //   K^-1 = X^T X is never stored: each 8x8 tile is reduced straight into the gradient traces
@@ -47,10 +47,6 @@
 #define GP_NB 8
 #define GP_LOG_2PI 1.8378770664093453
 #define GP_RED 192
-// Cholesky step: tiles of the trailing update handed to each of the other warps while warp 0 factors the next diagonal block
-#ifndef GP_CHOL8_TILES
-#define GP_CHOL8_TILES 10
-#endif
 
 struct GpCurveView {
   int n;               // observations
@@ -160,25 +156,29 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, double
 // exp(x) for x <= 0, branch free so that several evaluations interleave: k = rint(x log2 e), r = x - k ln 2 (two-part
 // constant), degree-13 Taylor polynomial on |r| <= 0.347, 2^k by exponent arithmetic; results below 2^-1021 flush to zero.
 // Maximum error 0.63 ulp over [-708, 0] (tests/test_block_host.py::test_exp_neg_accuracy); the library exp is 0.5 ulp.
-GP_HD double gp_exp_neg(double x) {
-  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);   // low word of t = k
-  const double kf = t - 6755399441055744.0;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;
-  p = fma(p, r, 2.08767569878681e-09);
-  p = fma(p, r, 2.505210838544172e-08);
-  p = fma(p, r, 2.755731922398589e-07);
-  p = fma(p, r, 2.7557319223985893e-06);
-  p = fma(p, r, 2.48015873015873e-05);
-  p = fma(p, r, 0.0001984126984126984);
-  p = fma(p, r, 0.001388888888888889);
-  p = fma(p, r, 0.008333333333333333);
-  p = fma(p, r, 0.041666666666666664);
-  p = fma(p, r, 0.16666666666666666);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+#if defined(__CUDACC__)
+#define GP_CONST __constant__
+#else
+#define GP_CONST static const
+#endif
+// constants live in constant memory on the device: FP64 instructions take constant-bank operands directly, while immediates
+// would each cost two register moves
+GP_CONST double gp_exp_c[18] = {
+    1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+    2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664,
+    0.16666666666666666, 0.5, 1.0, -708.0};
+
+GP_DEV double gp_exp_neg(double x) {
+  const double t = fma(x, gp_exp_c[0], gp_exp_c[1]);   // low word of t = k
+  const double kf = t - gp_exp_c[1];
+  double r = fma(kf, gp_exp_c[2], x);
+  r = fma(kf, gp_exp_c[3], r);
+  double p = gp_exp_c[4];
+#pragma unroll
+  for (int i = 5; i <= 15; ++i) p = fma(p, r, gp_exp_c[i]);
+  p = fma(p, r, gp_exp_c[16]);
+  p = fma(p, r, gp_exp_c[16]);
 #if defined(__CUDA_ARCH__)
   const double res = __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
 #else
@@ -189,7 +189,7 @@ GP_HD double gp_exp_neg(double x) {
   double res;
   memcpy(&res, &pb, 8);
 #endif
-  return x < -708.0 ? 0.0 : res;
+  return x < gp_exp_c[17] ? 0.0 : res;
 }
 
 // c * exp(-1/2 |x_i/l - x_j/l|^2) for i != j  (kernels.py:1561-1565)
@@ -234,45 +234,67 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, double c
 // ---------------------------------------------------------------------------------------------- Cholesky
 // Warp-level Cholesky of one 8x8 diagonal block held in accumulator layout (lane (g, t): a0 = A[g][t], a1 = A[g][4 + t], the
 // block symmetric), together with the inverse of its factor: on exit z0/z1 hold X = L^-1 in the same layout (exact zeros above
-// the diagonal) and logdet has been reduced by sum_j log(1 / L_jj).  Right-looking, one pivot column per step:
+// the diagonal) and rdet has been multiplied by prod_j 1 / L_jj.  Right-looking, one pivot column per step:
 //   r = rsqrt(A_jj);  l_ij = A_ij r;  A_ic -= l_ij l_cj;        X_j: = Z_j: r;  Z_i: -= l_ij X_j:   (Z starts as I)
 // Same arithmetic as a scalar column Cholesky (division free: L_jj = A_jj r is never needed), but every lane carries two
 // matrix entries instead of one thread carrying 36, and the pivot column travels by shuffles.
-// 1 / sqrt(d) for a pivot d in (1e-300, 1e300): hardware seed (MUFU.RSQ64H, ~2^-20) and two Newton steps.  A few instructions
-// on the longest dependent chain of the whole evaluation (N of these in sequence), where the library rsqrt spends twenty.
+// 1 / sqrt(d) for a pivot d in (1e-300, 1e300): hardware seed (MUFU.RSQ64H, relative error < 2^-20) and one third-order step
+// y (1 + e/2 + 3 e^2 / 8), e = 1 - d y^2: four dependent FP64 operations (8 cycles each on B200) where the library rsqrt
+// takes 205 cycles (scripts/ubench/lat.cu) - this sits on the longest dependent chain of the evaluation, N pivots in sequence.
 GP_DEV double gp_rsqrt(double d) {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-(d * y), y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-(d * y), y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double e = fma(-(d * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 #else
   return 1.0 / sqrt(d);
 #endif
 }
 
+// log of a product of positive factors without a log per factor: mantissa and exponent are accumulated separately
+// (the library log is ~300 cycles; the factorisation folds its pivots in here and takes ONE log at the end)
+struct GpLogProd {
+  double m;   // in [1, 2)
+  int e;
+};
+GP_DEV void gp_logprod_mul(GpLogProd& lp, double x) {   // x in (1e-300, 1e300)
+  const double p = lp.m * x;
+#if defined(__CUDA_ARCH__)
+  const int hi = __double2hiint(p);
+  lp.e += (hi >> 20) - 1023;
+  lp.m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+#else
+  int ex;
+  const double fr = frexp(p, &ex);   // p = fr 2^ex, fr in [0.5, 1)
+  lp.m = 2.0 * fr;
+  lp.e += ex - 1;
+#endif
+}
+GP_DEV double gp_logprod_value(const GpLogProd& lp) { return log(lp.m) + (double)lp.e * 0.6931471805599453; }
+
 template <class Ctx>
-GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, double& logdet) {
+GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, GpLogProd& rdet) {
   const int g = c.lane >> 2, t = c.lane & 3;
   z0 = (g == t) ? 1.0 : 0.0;
   z1 = (g == 4 + t) ? 1.0 : 0.0;
   bool ok = true;
-  double rprod = 1.0;   // running product of 1 / L_jj, folded into the log every four pivots (pivots are within (1e-300, 1e300))
+  double rprod = 1.0;   // running product of 1 / L_jj, folded into rdet every four pivots (pivots are within (1e-300, 1e300))
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int jt = j & 3;
     const double aj = (j < 4) ? a0 : a1;           // this lane's entry of block column (j & 3) / (4 + (j & 3))
-    double d = c.shfl(aj, 4 * j + jt);              // A[j][j]
+    const double d = c.shfl(aj, 4 * j + jt);        // A[j][j]
     const double cg = c.shfl(aj, 4 * g + jt);       // A[g][j]
     const double c0 = c.shfl(aj, 4 * t + jt);       // A[t][j]
     const double c1 = c.shfl(aj, 4 * (4 + t) + jt); // A[4 + t][j]
     const double zj0 = c.shfl(z0, 4 * j + t);       // Z[j][t]
     const double zj1 = c.shfl(z1, 4 * j + t);       // Z[j][4 + t]
-    if (!(d > 1.0e-300) || !(d < 1.0e300)) { ok = false; d = 1.0; }
+    // a bad pivot is only recorded (the evaluation is discarded as "not positive definite"); nothing waits for the test
+    const bool good = (d > 1.0e-300) && (d < 1.0e300);
+    ok = ok && good;
     const double r = gp_rsqrt(d);
-    rprod *= r;
+    rprod *= good ? r : 1.0;
     const double lg = cg * r, l0 = c0 * r, l1 = c1 * r, x0 = zj0 * r, x1 = zj1 * r;
     if (g > j) {
       a0 -= lg * l0;
@@ -283,8 +305,8 @@ GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, 
       z0 = x0;
       z1 = x1;
     }
-    if ((j & 3) == 3) {   // fold into the running log every four pivots: rprod stays far from over/underflow
-      logdet -= log(rprod);
+    if ((j & 3) == 3) {
+      gp_logprod_mul(rdet, rprod);
       rprod = 1.0;
     }
   }
@@ -309,73 +331,102 @@ GP_DEV void gp_panel_mult(Ctx& c, const GpSmem& s, const GpFrag& f, int kb) {
   }
 }
 
-// Trailing update of step kb for the tiles q0, q0 + stride, ... < qend of the linear enumeration q = ta (ta + 1) / 2 + tb
-// (ta = 0..Tr, row Tr = the border):  C(ta, tb) -= P_ta P_tb^T  with P = the solved panel (block column kb).  Warp-wide.
+// Accumulation of finished block columns into one or two tiles of block column k:
+//   C(I, k) = C(I, k) - sum_{J0 <= J < J1} L(I, J) L(k, J)^T,
+// left in registers in accumulator layout (acc[r][0] = C[g][t], acc[r][1] = C[g][4 + t]).  The two rows share the B fragments
+// (L(k, J), read as rows: B[kk][n] = L(k, J)[n][kk]); each row runs two independent DMMA chains.  I2 < 0: one row only.
 template <class Ctx>
-GP_DEV void gp_chol_update_tiles(Ctx& c, const GpSmem& s, const GpFrag& f, int kb, int q0, int stride, int qend) {
-  if (q0 >= qend) return;
-  double* A = s.A;
-  const int base = kb + 1;
-  int ta = 0, tb = q0;
-  while (tb > ta) { tb -= ta + 1; ++ta; }
-  for (int q = q0; q < qend; q += stride) {
-    const double* Pa = A + gp_tile(base + ta, kb);
-    const double* Pb = A + gp_tile(base + tb, kb);
-    double* C = A + gp_tile(base + ta, base + tb);
-    double c0v = C[f.a0], c1v = C[f.a1];
-    c.mma(c0v, c1v, -Pa[f.a0], Pb[f.b0]);
-    c.mma(c0v, c1v, -Pa[f.a1], Pb[f.b1]);
-    C[f.a0] = c0v;
-    C[f.a1] = c1v;
-    tb += stride;
-    while (tb > ta) { tb -= ta + 1; ++ta; }
+GP_DEV void gp_chol_accumulate(Ctx& c, const GpSmem& s, const GpFrag& f, int k, int I1, int I2, int J0, int J1, double (&acc)[2][2]) {
+  const double* P1 = s.A + gp_tile(I1, 0);
+  const double* Pb = s.A + gp_tile(k, J0);
+  double d10 = 0.0, d11 = 0.0;
+  acc[0][0] = P1[64 * k + f.a0]; acc[0][1] = P1[64 * k + f.a1];
+  P1 += 64 * J0;
+  if (I2 < 0) {
+    for (int J = J0; J < J1; ++J) {
+      c.mma(acc[0][0], acc[0][1], -P1[f.a0], Pb[f.b0]);
+      c.mma(d10, d11, -P1[f.a1], Pb[f.b1]);
+      P1 += 64; Pb += 64;
+    }
+  } else {
+    const double* P2 = s.A + gp_tile(I2, 0);
+    double d20 = 0.0, d21 = 0.0;
+    acc[1][0] = P2[64 * k + f.a0]; acc[1][1] = P2[64 * k + f.a1];
+    P2 += 64 * J0;
+    for (int J = J0; J < J1; ++J) {
+      const double b0 = Pb[f.b0], b1 = Pb[f.b1];
+      c.mma(acc[0][0], acc[0][1], -P1[f.a0], b0);
+      c.mma(d10, d11, -P1[f.a1], b1);
+      c.mma(acc[1][0], acc[1][1], -P2[f.a0], b0);
+      c.mma(d20, d21, -P2[f.a1], b1);
+      P1 += 64; P2 += 64; Pb += 64;
+    }
+    acc[1][0] += d20; acc[1][1] += d21;
+  }
+  acc[0][0] += d10; acc[0][1] += d11;
+}
+
+// rows I = first, first + stride, ... <= T of block column k: apply the terms [J0, J1) and store (two rows per pass)
+template <class Ctx>
+GP_DEV void gp_chol_update_rows(Ctx& c, const GpSmem& s, const GpFrag& f, int k, int first, int stride, int J0, int J1) {
+  const int T = s.T;
+  double acc[2][2];
+  for (int I = first; I <= T; I += 2 * stride) {
+    const int I2 = (I + stride <= T) ? I + stride : -1;
+    gp_chol_accumulate(c, s, f, k, I, I2, J0, J1, acc);
+    double* C1 = s.A + gp_tile(I, k);
+    C1[f.a0] = acc[0][0];
+    C1[f.a1] = acc[0][1];
+    if (I2 >= 0) {
+      double* C2 = s.A + gp_tile(I2, k);
+      C2[f.a0] = acc[1][0];
+      C2[f.a1] = acc[1][1];
+    }
   }
 }
 
-// Blocked right-looking Cholesky of the bordered matrix with one-step lookahead: warp 0 brings the next diagonal tile up to
-// date and factors it in registers while the other warps apply the panel to the rest of the trailing matrix.  Sets flag on
-// breakdown.  On exit the strictly-lower tiles hold L, the diagonal tiles hold the INVERSES of L's diagonal blocks, row 0 of
-// the border tile-row holds z^T = (L^-1 y)^T, and logdet (valid in lane 0 of warp 0, zero elsewhere) = sum_i log L_ii.
+// Blocked Cholesky of the bordered matrix, left-looking with one column of lookahead.  At the top of step kb the block columns
+// < kb are final and block column kb already carries every term but the last (J = kb - 1).  Then
+//   warp 0        applies that term to the diagonal tile and factors it, all in registers (the serial chain of 8 pivots);
+//   other warps   apply it to the rows below, then run ahead: block column kb + 1 receives the terms J < kb in one
+//                 accumulation per tile (long independent DMMA chains, one load and one store of C);
+//   barrier; the rows of block column kb are multiplied by the inverted diagonal block; barrier.
+// So the critical path of a step is one tile update + the 8x8 factorisation, as in a right-looking sweep, while each tile of
+// the matrix is loaded and stored twice instead of once per step.  Sets flag on breakdown.  On exit the strictly-lower tiles
+// hold L, the diagonal tiles hold the INVERSES of L's diagonal blocks, row 0 of the border tile-row holds z^T = (L^-1 y)^T,
+// and logdet (valid in thread 0, zero elsewhere) = sum_i log L_ii.
 template <class Ctx>
 GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, double& logdet) {
   const int T = s.T;
   const GpFrag f = gp_frag(c.lane);
-  double ld = 0.0;
-  if (c.warp == 0) {
-    double* D = s.A + gp_tile(0, 0);
-    double z0, z1;
-    if (!gp_chol8_warp(c, D[f.a0], D[f.a1], z0, z1, ld) && c.lane == 0) s.flag[0] = 1;
-    D[f.a0] = z0;
-    D[f.a1] = z1;
-  }
-  c.sync();
-  gp_panel_mult(c, s, f, 0);
-  c.sync();
-  for (int kb = 0; kb + 1 < T; ++kb) {
-    // trailing matrix: Tr x Tr lower tiles plus the border tile-row (ta = Tr) over the Tr tile-columns
-    const int Tr = T - kb - 1, ntile = Tr * (Tr + 1) / 2 + Tr;
-    // segment A (tiles 1 .. nA) is shared by warps 1.., segment B (the rest) by all warps once warp 0 is back
-    int nA = GP_CHOL8_TILES * (c.nwarp - 1);
-    if (nA > ntile - 1) nA = ntile - 1;
+  GpLogProd rdet;
+  rdet.m = 1.0;
+  rdet.e = 0;
+  long long tdiag = 0;
+  const int nrow = c.nwarp > 1 ? c.nwarp - 1 : 1;          // warps that take the rows below the diagonal
+  const int wrow = c.nwarp > 1 ? c.warp - 1 : 0;
+  for (int kb = 0; kb < T; ++kb) {
+    const int Jlast = kb > 0 ? kb - 1 : 0;
     if (c.warp == 0) {
-      // critical path first: the next diagonal tile, updated and factored without leaving the registers
-      const double* P = s.A + gp_tile(kb + 1, kb);
-      double* D = s.A + gp_tile(kb + 1, kb + 1);
-      double a0 = D[f.a0], a1 = D[f.a1], z0, z1;
-      c.mma(a0, a1, -P[f.a0], P[f.b0]);
-      c.mma(a0, a1, -P[f.a1], P[f.b1]);
-      if (!gp_chol8_warp(c, a0, a1, z0, z1, ld) && c.lane == 0) s.flag[0] = 1;
+      double acc[2][2], z0, z1;
+      const long long t0 = c.clock();
+      gp_chol_accumulate(c, s, f, kb, kb, -1, Jlast, kb, acc);
+      if (!gp_chol8_warp(c, acc[0][0], acc[0][1], z0, z1, rdet) && c.lane == 0) s.flag[0] = 1;
+      double* D = s.A + gp_tile(kb, kb);
       D[f.a0] = z0;
       D[f.a1] = z1;
-    } else {
-      gp_chol_update_tiles(c, s, f, kb, c.warp, c.nwarp - 1, 1 + nA);
+      tdiag += c.clock() - t0;
     }
-    gp_chol_update_tiles(c, s, f, kb, 1 + nA + c.warp, c.nwarp, ntile);
+    if (c.warp > 0 || c.nwarp == 1) {
+      if (kb > 0) gp_chol_update_rows(c, s, f, kb, kb + 1 + wrow, nrow, Jlast, kb);
+      if (kb > 0 && kb + 1 < T) gp_chol_update_rows(c, s, f, kb + 1, kb + 1 + wrow, nrow, 0, kb);
+    }
     c.sync();
-    gp_panel_mult(c, s, f, kb + 1);
+    gp_panel_mult(c, s, f, kb);
     c.sync();
   }
-  logdet = (c.tid == 0) ? ld : 0.0;
+  c.mark_value(9, tdiag);   // diagnostics: cycles warp 0 spent on the diagonal tiles
+  logdet = (c.tid == 0) ? -gp_logprod_value(rdet) : 0.0;
 }
 
 // After gp_cholesky: this thread's share of z.z (= y^T K^-1 y).

@@ -26,10 +26,17 @@ namespace {
 struct DevCtx {
   int tid, nthr, lane, warp, nwarp;
   long long* marks;   // optional phase timestamps (fulu_gp_debug_phase_cycles); null in production launches
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so loops and branches on it stay convergent and
+  // the mma.sync sites need no WARPSYNC / collective wrappers
   __device__ __forceinline__ DevCtx() : tid((int)threadIdx.x), nthr((int)blockDim.x), lane((int)threadIdx.x & 31),
-                                        warp((int)threadIdx.x >> 5), nwarp(((int)blockDim.x + 31) >> 5), marks(nullptr) {}
+                                        warp(__shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0)), nwarp(((int)blockDim.x + 31) >> 5),
+                                        marks(nullptr) {}
   __device__ __forceinline__ void mark(int id) {
     if (marks != nullptr && tid == 0) marks[id] = clock64();
+  }
+  __device__ __forceinline__ long long clock() { return marks != nullptr ? clock64() : 0; }
+  __device__ __forceinline__ void mark_value(int id, long long v) {
+    if (marks != nullptr && tid == 0) marks[id] = v;
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void warp_sync() { __syncwarp(); }

@@ -184,7 +184,9 @@ class GPEngine:
                                                             self._p(marks), self._p(ws), ws.numel(), self._stream()))
             m = marks.cpu().numpy()
             names = ("load", "assemble", "cholesky", "collect_z", "inverse", "alpha", "traces", "reduce")
-            return {n: int(m[i + 1] - m[i]) for i, n in enumerate(names)}
+            out = {n: int(m[i + 1] - m[i]) for i, n in enumerate(names)}
+            out["diag_tiles_in_cholesky"] = int(m[9])
+            return out
 
     # ---- a6: optimiser
     def fit(self, batch: DeviceBatch, spec: KernelSpec = None, window=0, max_rounds=0, factr=1e7, pgtol=1e-5, maxiter=15000,

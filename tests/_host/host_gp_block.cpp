@@ -20,6 +20,8 @@ struct HostCtx {
   WarpShared* ws;
   void sync() { block_bar->arrive_and_wait(); }
   void mark(int) {}
+  long long clock() { return 0; }
+  void mark_value(int, long long) {}
   void warp_sync() { ws->bar.arrive_and_wait(); }
   // D = A(8x4, row) * B(4x8, col) + C; lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
   void mma(double& c0, double& c1, double a, double b) {
