@@ -46,13 +46,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise FuluGpError(f"fulu_b200: {LIB_PATH} is missing. Build it with `python -m fulu_b200.build` (needs nvcc); "
+    path = os.environ.get("FULU_GP_LIB", LIB_PATH)   # override: A/B runs of differently tuned builds of the same library
+    if not os.path.exists(path):
+        raise FuluGpError(f"fulu_b200: {path} is missing. Build it with `python -m fulu_b200.build` (needs nvcc); "
                           "this package has no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name in EXPORTS:
         if not hasattr(lib, name):
-            raise FuluGpError(f"fulu_b200: {LIB_PATH} does not export {name}")
+            raise FuluGpError(f"fulu_b200: {path} does not export {name}")
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
     lib.fulu_gp_abi_version.restype = ctypes.c_int
     lib.fulu_gp_strerror.restype = ctypes.c_char_p

@@ -17,8 +17,7 @@
 // FP64 rate with an eighth of the issue slots of a DFMA loop, measured 37.2 vs 33.9 TFLOP/s).  The diagonal 8x8 blocks are
 // factored by one warp holding the block in accumulator layout (two doubles per lane, shuffles for the pivot column), which
 // produces the block's inverse X_D = L_D^-1 in the same sweep; X_D is what gets stored on the diagonal, so the panel solve is a
-// DMMA product P X_D^T, the triangular inverse finds its diagonal blocks done, and nothing in the kernel needs more than a
-// handful of registers per thread (64 registers -> 1024 resident threads per SM).
+// DMMA product P X_D^T, the triangular inverse finds its diagonal blocks done, and no thread ever holds a whole 8x8 block.
 //
 // Storage (v3).  Only the lower triangle exists: tile (I, J), J <= I < T (T = np / 8, np = N padded to a multiple of 8 with an
 // identity block) lives at 64 (I (I + 1) / 2 + J) doubles, followed by one border tile-row I = T (tiles (T, 0..T-1)) whose row 0
@@ -55,6 +54,10 @@ struct GpCurveView {
   const double* y;     // [n] normalised flux
   const double* al;    // [n] noise diagonal (regressor alpha)
   const double* lam;   // [n_bands] standardised log10 wavelength (StandardScaler column 1 per band)
+};
+
+struct alignas(16) GpPair {
+  double x, y;
 };
 
 struct GpSmem {
@@ -503,6 +506,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double cst, double
   const double* A = s.A;
   const GpFrag f = gp_frag(c.lane);
   const double* bord = A + gp_tile(T, 0);
+  const int ob_g = gp_el(0, g), ob_0 = gp_el(0, 2 * t), ob_1 = gp_el(0, 2 * t + 1);
   tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
@@ -519,25 +523,20 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double cst, double
       Xj += 64 * (K + 1);
     }
     // epilogue: lane (g, t) owns (i, j) = (i0 + g, j0 + 2t) and (i0 + g, j0 + 2t + 1)
-    const int i = 8 * I + g;
-    const double ai = -bord[64 * I + gp_el(0, g)], ui = s.u[i], vi = s.v[i];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int jc = 2 * t + e, j = 8 * J + jc;
-      const double kinv = e ? (p1 + q1) : (p0 + q0);
-      const double w = ai * -bord[64 * J + gp_el(0, jc)] - kinv;
-      if (i > j) {
-        if (i < n) {
-          const double du = ui - s.u[j], dv = vi - s.v[j];
-          const double wk = w * (cst * gp_exp_neg(-0.5 * (du * du + dv * dv)));   // K_ij again (not stored)
-          tr[0] += wk;
-          tr[1] += wk * (du * du);
-          tr[2] += wk * (dv * dv);
-        }
-      } else if (i == j && i < n) {
-        tr[3] += w;
-      }
-    }
+    const int i = 8 * I + g, j = 8 * J + 2 * t;
+    const double ai = bord[64 * I + ob_g], ui = s.u[i], vi = s.v[i];                 // (the border row holds -alpha)
+    const double w0 = ai * bord[64 * J + ob_0] - (p0 + q0), w1 = ai * bord[64 * J + ob_1] - (p1 + q1);
+    const GpPair uj = *reinterpret_cast<const GpPair*>(s.u + j), vj = *reinterpret_cast<const GpPair*>(s.v + j);   // j is even
+    const double du0 = ui - uj.x, dv0 = vi - vj.x, du1 = ui - uj.y, dv1 = vi - vj.y;
+    const double du0s = du0 * du0, dv0s = dv0 * dv0, du1s = du1 * du1, dv1s = dv1 * dv1;
+    const double k0 = cst * gp_exp_neg(-0.5 * (du0s + dv0s)), k1 = cst * gp_exp_neg(-0.5 * (du1s + dv1s));   // K_ij again (not stored)
+    // strictly-lower entries inside the curve count; on a diagonal tile the diagonal feeds tr[3]
+    const bool in = i < n;
+    const double wk0 = (in && i > j) ? w0 * k0 : 0.0, wk1 = (in && i > j + 1) ? w1 * k1 : 0.0;
+    tr[0] += wk0 + wk1;
+    tr[1] += wk0 * du0s + wk1 * du1s;
+    tr[2] += wk0 * dv0s + wk1 * dv1s;
+    if (I == J) tr[3] += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
     J += c.nwarp;
     while (J > I) { J -= I + 1; ++I; }
   }

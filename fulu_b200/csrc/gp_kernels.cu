@@ -48,8 +48,14 @@ struct DevCtx {
   __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 };
 
-constexpr int kEvalMaxThreads = 1024;  // 64 registers per thread fill the register file at 1024 threads per SM:
-                                       // an evaluation CTA gets 1024 / (CTAs per SM) threads
+// Threads per SM given to the evaluation kernel, split evenly between the resident CTAs; it also fixes the register budget
+// (65536 / threads).  Measured on B200 at N = 100 (4 CTAs per SM), 10,000 curves: 1024 threads (64 registers) 229 ms,
+// 768 (80) 213 ms, 640 (96) 206 ms, 512 (128) 203 ms, 384 (168) 216 ms, 256 (255) 255 ms per fit - with few registers the
+// compiler funnels the fragment loads of the DMMA loops through one register pair and serialises load -> DMMA -> load.
+#ifndef GP_EVAL_MAX_THREADS
+#define GP_EVAL_MAX_THREADS 512
+#endif
+constexpr int kEvalMaxThreads = GP_EVAL_MAX_THREADS;
 constexpr int kPredictThreads = 128;
 constexpr int kPrepThreads = 128;
 constexpr size_t kMaxSmem = 227 * 1024;

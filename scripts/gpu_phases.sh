@@ -10,6 +10,6 @@ for B in (1, 2000):
     th = torch.tensor(np.tile([0.2, -1.5, 2.5, -4.5], (B, 1)))
     eng.phase_cycles(db, th)
     out = eng.phase_cycles(db, th)
-    print(B, json.dumps(out), "total", sum(v for k, v in out.items() if k != "diag_tiles_in_cholesky"))
+    print(B, json.dumps(out), "total", sum(v for k, v in out.items() if isinstance(v, int) and k != "diag_tiles_in_cholesky"))
 PY
 cat gpurun_out/phases.log
