@@ -7,6 +7,7 @@ import os
 from .build import LIB_PATH
 
 MAX_PARAMS = 6
+ABI_VERSION = 2   # FULU_GP_ABI_VERSION of include/fulu_gp.h this binding was written against
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
@@ -16,6 +17,7 @@ class Batch(ctypes.Structure):
         ("offsets", ctypes.c_void_p), ("t", ctypes.c_void_p), ("flux", ctypes.c_void_p), ("flux_err", ctypes.c_void_p),
         ("band", ctypes.c_void_p), ("loglam", ctypes.c_void_p),
         ("kernel", ctypes.c_int32), ("use_err", ctypes.c_int32), ("alpha0", ctypes.c_double),
+        ("order", ctypes.c_void_p), ("n_order", ctypes.c_int64),
     ]
 
 
@@ -68,7 +70,7 @@ def load():
     for name in EXPORTS:
         if name not in ("fulu_gp_strerror",):
             getattr(lib, name).restype = ctypes.c_int
-    if lib.fulu_gp_abi_version() != 1:
+    if lib.fulu_gp_abi_version() != ABI_VERSION:
         raise FuluGpError("fulu_b200: ABI version mismatch between the Python binding and libfulu_gp.so")
     _lib = lib
     return lib

@@ -113,7 +113,7 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   int occ_p = occ > 4 ? 4 : occ;   // 128-thread prediction CTAs
   w.grid_predict = sms * occ_p;
   if (window <= 0) window = kDefaultWindow;
-  size_t tasks = B * (size_t)(S > 0 ? S : 1);
+  size_t tasks = (size_t)(b.order ? b.n_order : b.n_curves) * (size_t)(S > 0 ? S : 1);
   if ((size_t)window > tasks) window = (int)(tasks > 0 ? tasks : 1);
   w.window = window;
   w.max_rounds = max_rounds > 0 ? max_rounds : kDefaultMaxRounds;
@@ -148,7 +148,8 @@ T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct PrepArgs {
-  int64_t B;
+  int64_t B;              // curves to prepare (entries of order, or all)
+  const int32_t* order;
   const int64_t* offsets;
   const double *t, *flux, *ferr, *loglam;
   const int32_t* band;
@@ -161,7 +162,8 @@ struct PrepArgs {
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
   __shared__ double red[GP_RED];
   DevCtx c;
-  for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
+  for (int64_t k = blockIdx.x; k < a.B; k += gridDim.x) {
+    const int64_t cu = a.order ? (int64_t)a.order[k] : k;
     const int64_t o = a.offsets[cu];
     const int n = (int)(a.offsets[cu + 1] - o);
     int st = gp_prepare_curve(c, n, a.t + o, a.flux + o, a.ferr + o, a.band + o, a.loglam, a.n_bands, a.use_err, a.alpha0, a.xs + o,
@@ -176,8 +178,12 @@ struct CurveTable {
   const double *xs, *y, *al, *lam, *stats;
   const int32_t* band;
   const int32_t* pstatus;
+  const int32_t* order;   // optional processing order (curve ids); null = identity
+  int64_t n_active;       // curves this call processes
   int n_bands;
 };
+
+__device__ __forceinline__ int64_t curve_of(const CurveTable& t, int64_t k) { return t.order ? (int64_t)t.order[k] : k; }
 
 __device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t cu) {
   const int64_t o = t.offsets[cu];
@@ -203,7 +209,8 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab,
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
   if (blockIdx.x == 0) c.marks = marks;
-  for (int64_t cu = blockIdx.x; cu < B; cu += gridDim.x) {
+  for (int64_t kk = blockIdx.x; kk < B; kk += gridDim.x) {
+    const int64_t cu = curve_of(tab, kk);
     if (tab.pstatus[cu] != 0) {
       if (threadIdx.x == 0) { lml[cu] = NAN; for (int k = 0; k < P; ++k) grad[cu * P + k] = NAN; }
       continue;
@@ -237,12 +244,12 @@ struct FitDev {
   size_t gA_stride;
 };
 
-// pulls the next runnable task into `slot`; returns false when the queue is empty
-__device__ bool acquire_task(const FitDev& d, int slot) {
+// pulls the next runnable task into `slot` (whose optimiser state is `state`); returns false when the queue is empty
+__device__ bool acquire_task(const FitDev& d, int slot, FgState& state) {
   for (;;) {
     unsigned long long nt = atomicAdd(d.next_task, 1ULL);
-    if (nt >= (unsigned long long)d.n_tasks) { d.slot_task[slot] = -1; d.slots[slot].task = FG_TASK_IDLE; return false; }
-    const int64_t cu = (int64_t)(nt / d.S);
+    if (nt >= (unsigned long long)d.n_tasks) { d.slot_task[slot] = -1; state.task = FG_TASK_IDLE; return false; }
+    const int64_t cu = curve_of(d.tab, (int64_t)(nt / d.S));
     const int st = (int)(nt % d.S);
     if (d.tab.pstatus[cu] != 0) {   // unusable curve: record and move on
       d.run_f[nt] = INFINITY;
@@ -251,7 +258,7 @@ __device__ bool acquire_task(const FitDev& d, int slot) {
       d.run_end[nt] = FG_TASK_ABNORMAL;
       continue;
     }
-    lbfgsb_init(d.slots[slot], d.opt, d.starts + st * FG_MAXP);
+    lbfgsb_init(state, d.opt, d.starts + st * FG_MAXP);
     d.slot_task[slot] = (int64_t)nt;
     d.slot_nev[slot] = 0;
     return true;
@@ -261,7 +268,7 @@ __device__ bool acquire_task(const FitDev& d, int slot) {
 __global__ void fit_init_kernel(FitDev d) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= d.window) return;
-  if (acquire_task(d, slot)) {
+  if (acquire_task(d, slot, d.slots[slot])) {
     const int pos = atomicAdd(&d.counts[0], 1);
     d.list[pos] = slot;
   }
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
   const int32_t* list = d.list + (size_t)(round & 1) * d.window;
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
     const int slot = list[i];
-    const int64_t cu = d.slot_task[slot] / d.S;
+    const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
     GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
     double l, g[4];
@@ -289,6 +296,8 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
   }
 }
 
+// One optimiser state per thread, advanced in place.  (Staging the 1.5 KB states through shared memory - warp-cooperative
+// coalesced copy in, advance there, copy out - was measured slower on B200: 19.3 ms instead of 14.1 ms per 188 rounds.)
 __global__ void fit_step_kernel(FitDev d, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.counts[round]) return;
@@ -303,7 +312,7 @@ __global__ void fit_step_kernel(FitDev d, int round) {
     for (int k = 0; k < FG_MAXP; ++k) d.run_x[task * FG_MAXP + k] = st.x[k];
     d.run_nev[task] = d.slot_nev[slot];
     d.run_end[task] = st.task;
-    live = acquire_task(d, slot);
+    live = acquire_task(d, slot, st);
   }
   if (live) {
     const int pos = atomicAdd(&d.counts[round + 1], 1);
@@ -326,7 +335,8 @@ __global__ void fit_flush_kernel(FitDev d) {
 }
 
 struct SelectArgs {
-  int64_t B;
+  int64_t B;              // curves processed
+  const int32_t* order;
   int S, P;
   const double *run_f, *run_x;
   const int32_t *run_nev, *run_end, *pstatus;
@@ -336,27 +346,28 @@ struct SelectArgs {
 };
 
 __global__ void fit_select_kernel(SelectArgs a) {
-  const int64_t cu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (cu >= a.B) return;
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= a.B) return;
+  const int64_t cu = a.order ? (int64_t)a.order[k] : k;   // runs are stored by position, results by curve id
   int best = 0, nev = 0;
-  double fb = a.run_f[cu * a.S];
+  double fb = a.run_f[k * a.S];
   for (int s = 0; s < a.S; ++s) {
-    const double f = a.run_f[cu * a.S + s];
+    const double f = a.run_f[k * a.S + s];
     if (f < fb) { fb = f; best = s; }   // np.argmin: first minimum (_gpr.py:336-340)
-    nev += a.run_nev[cu * a.S + s];
+    nev += a.run_nev[k * a.S + s];
     if (a.run_lml) a.run_lml[cu * a.S + s] = -f;
     if (a.run_theta)
-      for (int k = 0; k < a.P; ++k) a.run_theta[(cu * a.S + s) * a.P + k] = a.run_x[(cu * a.S + s) * FG_MAXP + k];
+      for (int q = 0; q < a.P; ++q) a.run_theta[(cu * a.S + s) * a.P + q] = a.run_x[(k * a.S + s) * FG_MAXP + q];
   }
   int st = 0;
   if (a.pstatus[cu] != 0) st |= FULU_GP_STATUS_BAD_INPUT;
-  const int end = a.run_end[cu * a.S + best];
+  const int end = a.run_end[k * a.S + best];
   if (end == FG_TASK_ABNORMAL || end == FG_TASK_MAXITER) st |= FULU_GP_STATUS_NOT_CONVERGED;
-  for (int k = 0; k < a.P; ++k) {
-    const double th = a.run_x[(cu * a.S + best) * FG_MAXP + k];
-    a.theta_opt[cu * a.P + k] = th;
+  for (int q = 0; q < a.P; ++q) {
+    const double th = a.run_x[(k * a.S + best) * FG_MAXP + q];
+    a.theta_opt[cu * a.P + q] = th;
     const double tol = 1e-8 + 1e-5 * fabs(th);   // np.isclose(bound, theta)  (kernels.py:436-464)
-    if (fabs(a.lo[k] - th) <= tol || fabs(a.hi[k] - th) <= tol) st |= FULU_GP_STATUS_AT_BOUND;
+    if (fabs(a.lo[q] - th) <= tol || fabs(a.hi[q] - th) <= tol) st |= FULU_GP_STATUS_AT_BOUND;
   }
   a.lml_opt[cu] = -fb;
   a.n_eval[cu] = nev;
@@ -386,7 +397,8 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs
   __shared__ double tlim[2];
   DevCtx c;
   double* V = a.gV + (size_t)blockIdx.x * a.gV_stride;
-  for (int64_t cu = blockIdx.x; cu < a.B; cu += gridDim.x) {
+  for (int64_t kk = blockIdx.x; kk < a.B; kk += gridDim.x) {
+    const int64_t cu = curve_of(a.tab, kk);
     GpCurveView cv = curve_view(a.tab, cu);
     GpQuery qd;
     int64_t out0;
@@ -426,16 +438,19 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs
   }
 }
 
-__global__ void export_stats_kernel(int64_t B, const double* stats, double* scaler, double* ynorm) {
-  const int64_t cu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (cu >= B) return;
+__global__ void export_stats_kernel(int64_t B, const int32_t* order, const double* stats, double* scaler, double* ynorm) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  const int64_t cu = order ? (int64_t)order[k] : k;
   if (scaler) for (int k = 0; k < 4; ++k) scaler[cu * 4 + k] = stats[cu * 6 + k];
   if (ynorm) { ynorm[cu * 2] = stats[cu * 6 + 4]; ynorm[cu * 2 + 1] = stats[cu * 6 + 5]; }
 }
 
-__global__ void copy_status_kernel(int64_t B, const int32_t* src, int32_t* dst) {
-  const int64_t cu = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (cu < B) dst[cu] = src[cu] ? FULU_GP_STATUS_BAD_INPUT : 0;
+__global__ void copy_status_kernel(int64_t B, const int32_t* order, const int32_t* src, int32_t* dst) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  const int64_t cu = order ? (int64_t)order[k] : k;
+  dst[cu] = src[cu] ? FULU_GP_STATUS_BAD_INPUT : 0;
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 peak probes
@@ -474,20 +489,23 @@ int check_batch(const fulu_gp_batch* b, int P) {
   if (b->kernel != FULU_GP_KERNEL_RBF_WHITE) return FULU_GP_E_UNSUPPORTED;
   if (P != 4) return FULU_GP_E_UNSUPPORTED;
   if (b->n_max < 1 && b->n_curves > 0) return FULU_GP_E_BADARG;
+  if (b->order && (b->n_order < 0 || b->n_order > b->n_curves)) return FULU_GP_E_BADARG;
   return 0;
 }
 
+inline int64_t n_active(const fulu_gp_batch& b) { return b.order ? b.n_order : b.n_curves; }
+
 int run_prep(const fulu_gp_batch& b, const WsLayout& w, void* ws, int sms, cudaStream_t st, CurveTable& tab) {
   PrepArgs a;
-  a.B = b.n_curves; a.offsets = b.offsets; a.t = b.t; a.flux = b.flux; a.ferr = b.flux_err; a.loglam = b.loglam; a.band = b.band;
+  a.B = n_active(b); a.order = b.order; a.offsets = b.offsets; a.t = b.t; a.flux = b.flux; a.ferr = b.flux_err; a.loglam = b.loglam; a.band = b.band;
   a.n_bands = b.n_bands; a.use_err = b.use_err; a.alpha0 = b.alpha0;
   a.xs = at<double>(ws, w.xs); a.y = at<double>(ws, w.y); a.al = at<double>(ws, w.al); a.lam = at<double>(ws, w.lam);
   a.stats = at<double>(ws, w.stats); a.pstatus = at<int32_t>(ws, w.pstatus);
-  int64_t grid = b.n_curves < (int64_t)sms * 16 ? b.n_curves : (int64_t)sms * 16;
+  int64_t grid = a.B < (int64_t)sms * 16 ? a.B : (int64_t)sms * 16;
   if (grid > 0) prep_kernel<<<(unsigned)grid, kPrepThreads, 0, st>>>(a);
   CU_TRY(cudaGetLastError());
   tab.offsets = b.offsets; tab.xs = a.xs; tab.y = a.y; tab.al = a.al; tab.lam = a.lam; tab.stats = a.stats; tab.band = b.band;
-  tab.pstatus = a.pstatus; tab.n_bands = b.n_bands;
+  tab.pstatus = a.pstatus; tab.n_bands = b.n_bands; tab.order = b.order; tab.n_active = a.B;
   return 0;
 }
 
@@ -544,7 +562,7 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
                     double* ynorm, int32_t* status, void* workspace, size_t workspace_bytes, void* stream, long long* marks) {
   int rc = check_batch(batch, n_params);
   if (rc) return rc;
-  if (batch->n_curves == 0) return 0;
+  if (n_active(*batch) == 0) return 0;
   if (!theta || !lml || !grad || !workspace) return FULU_GP_E_BADARG;
   DeviceInfo di;
   if (device_info(di)) return FULU_GP_E_NOCUDA;
@@ -555,7 +573,7 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
   CurveTable tab;
   rc = run_prep(*batch, w, workspace, di.sms, st, tab);
   if (rc) return rc;
-  const int64_t B = batch->n_curves;
+  const int64_t B = n_active(*batch);
   unsigned grid = (unsigned)(B < w.grid_eval ? B : w.grid_eval);
   if (w.globalA) {
     rc = set_smem(lml_kernel<true>, w.smem_eval);
@@ -568,8 +586,8 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
   }
   CU_TRY(cudaGetLastError());
   const unsigned g1 = (unsigned)((B + 255) / 256);
-  if (scaler || ynorm) export_stats_kernel<<<g1, 256, 0, st>>>(B, tab.stats, scaler, ynorm);
-  if (status) copy_status_kernel<<<g1, 256, 0, st>>>(B, tab.pstatus, status);
+  if (scaler || ynorm) export_stats_kernel<<<g1, 256, 0, st>>>(B, tab.order, tab.stats, scaler, ynorm);
+  if (status) copy_status_kernel<<<g1, 256, 0, st>>>(B, tab.order, tab.pstatus, status);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -580,7 +598,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   if (!opt) return FULU_GP_E_BADARG;
   int rc = check_batch(batch, opt->n_params);
   if (rc) return rc;
-  if (batch->n_curves == 0) return 0;
+  if (n_active(*batch) == 0) return 0;
   if (!theta_starts || !theta_opt || !lml_opt || !n_eval || !status || !workspace) return FULU_GP_E_BADARG;
   if (opt->n_starts < 1 || opt->m < 1 || opt->m > FG_LBFGS_M) return FULU_GP_E_BADARG;
   DeviceInfo di;
@@ -599,7 +617,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   d.opt.n = P; d.opt.m = opt->m; d.opt.maxiter = opt->maxiter; d.opt.maxfun = opt->maxfun; d.opt.maxls = opt->maxls; d.opt.pad = 0;
   d.opt.factr = opt->factr; d.opt.pgtol = opt->pgtol;
   for (int k = 0; k < FG_MAXP; ++k) { d.opt.lo[k] = k < P ? opt->lower[k] : 0.0; d.opt.hi[k] = k < P ? opt->upper[k] : 0.0; }
-  d.n_tasks = batch->n_curves * (int64_t)S;
+  d.n_tasks = n_active(*batch) * (int64_t)S;
   d.S = S; d.P = P; d.window = w.window;
   d.slots = at<FgState>(workspace, w.slots);
   d.slot_task = at<int64_t>(workspace, w.slot_task);
@@ -675,11 +693,11 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     CU_TRY(cudaGetLastError());
   }
   SelectArgs sa;
-  sa.B = batch->n_curves; sa.S = S; sa.P = P;
+  sa.B = n_active(*batch); sa.order = batch->order; sa.S = S; sa.P = P;
   sa.run_f = d.run_f; sa.run_x = d.run_x; sa.run_nev = d.run_nev; sa.run_end = d.run_end; sa.pstatus = tab.pstatus;
   for (int k = 0; k < FG_MAXP; ++k) { sa.lo[k] = d.opt.lo[k]; sa.hi[k] = d.opt.hi[k]; }
   sa.theta_opt = theta_opt; sa.lml_opt = lml_opt; sa.run_lml = run_lml; sa.run_theta = run_theta; sa.n_eval = n_eval; sa.status = status;
-  fit_select_kernel<<<(unsigned)((batch->n_curves + 127) / 128), 128, 0, st>>>(sa);
+  fit_select_kernel<<<(unsigned)((sa.B + 127) / 128), 128, 0, st>>>(sa);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -687,7 +705,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
 static int predict_common(const fulu_gp_batch* batch, int32_t n_params, PredictArgs& a, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_batch(batch, n_params);
   if (rc) return rc;
-  if (batch->n_curves == 0) return 0;
+  if (n_active(*batch) == 0) return 0;
   if (!a.theta || !a.mean || !a.stdv || !workspace) return FULU_GP_E_BADARG;
   DeviceInfo di;
   if (device_info(di)) return FULU_GP_E_NOCUDA;
@@ -698,7 +716,7 @@ static int predict_common(const fulu_gp_batch* batch, int32_t n_params, PredictA
   CurveTable tab;
   rc = run_prep(*batch, w, workspace, di.sms, st, tab);
   if (rc) return rc;
-  a.tab = tab; a.B = batch->n_curves; a.P = n_params; a.t_raw = batch->t;
+  a.tab = tab; a.B = n_active(*batch); a.P = n_params; a.t_raw = batch->t;
   a.gA = at<double>(workspace, w.gA); a.gV = at<double>(workspace, w.gV);
   a.gA_stride = w.gA_stride; a.gV_stride = w.gV_stride;
   unsigned grid = (unsigned)(a.B < w.grid_predict ? a.B : w.grid_predict);

@@ -99,7 +99,20 @@ class DeviceBatch:
         c.offsets, c.t, c.flux, c.flux_err = offsets.data_ptr(), t.data_ptr(), flux.data_ptr(), flux_err.data_ptr()
         c.band, c.loglam = band.data_ptr(), loglam.data_ptr()
         c.kernel, c.use_err, c.alpha0 = family, int(use_err), alpha0
+        c.order, c.n_order = None, 0
         self.c = c
+        self.order = None
+        self.family, self.alpha0 = family, alpha0
+
+    def select(self, order, n_max=None):
+        """The same batch restricted to the curves `order` (int32 curve ids, processing order), with launch geometry for curves
+        of up to `n_max` observations.  Nothing is copied: the library follows the index list (fulu_gp_batch.order)."""
+        sub = DeviceBatch(self.offsets, self.t, self.flux, self.flux_err, self.band, self.loglam, self.n_max if n_max is None else n_max,
+                          self.use_err, self.alpha0, self.family)
+        if order is not None:
+            sub.order = torch.as_tensor(order, dtype=torch.int32).to(self.device).contiguous()
+            sub.c.order, sub.c.n_order = sub.order.data_ptr(), int(sub.order.numel())
+        return sub
 
     @staticmethod
     def from_host(b: CurveBatch, device=None, use_err=False, pinned=None, n_max=None):
@@ -190,8 +203,9 @@ class GPEngine:
 
     # ---- a6: optimiser
     def fit(self, batch: DeviceBatch, spec: KernelSpec = None, window=0, max_rounds=0, factr=1e7, pgtol=1e-5, maxiter=15000,
-            maxfun=15000, maxls=20, m=10, return_runs=False, profile=False):
-        """S = 1 + n_restarts L-BFGS-B runs per curve -> dict(theta [B,P], lml [B], n_eval [B], status [B])."""
+            maxfun=15000, maxls=20, m=10, return_runs=False, profile=False, out=None):
+        """S = 1 + n_restarts L-BFGS-B runs per curve -> dict(theta [B,P], lml [B], n_eval [B], status [B]).
+        `out`: a dict of such tensors to write into (rows of the curves `batch` selects; the others are left alone)."""
         spec = spec or KernelSpec()
         with torch.cuda.device(self.device):
             B, P = batch.n_curves, spec.n_params
@@ -203,7 +217,10 @@ class GPEngine:
             o.factr, o.pgtol = factr, pgtol
             for k in range(P):
                 o.lower[k], o.upper[k] = spec.lower[k], spec.upper[k]
-            out = dict(theta=self._new(B, P), lml=self._new(B), n_eval=self._new(B, dtype=torch.int32), status=self._new(B, dtype=torch.int32))
+            if out is None:
+                out = dict(theta=self._new(B, P), lml=self._new(B), n_eval=self._new(B, dtype=torch.int32), status=self._new(B, dtype=torch.int32))
+            else:
+                out = dict(out)
             if return_runs:
                 out["run_lml"] = self._new(B, S)
                 out["run_theta"] = self._new(B, S, P)
@@ -221,8 +238,9 @@ class GPEngine:
             return out
 
     # ---- a7-a9: augmentation grid / arbitrary points
-    def predict_grid(self, batch: DeviceBatch, theta, n_obs, t_min=None, t_max=None):
-        """-> dict(mean [B,n_bands,n_obs], std [...], lml [B], status [B]); t_min/t_max [B] default to each curve's span."""
+    def predict_grid(self, batch: DeviceBatch, theta, n_obs, t_min=None, t_max=None, out=None):
+        """-> dict(mean [B,n_bands,n_obs], std [...], lml [B], status [B]); t_min/t_max [B] default to each curve's span.
+        `out`: a dict of such tensors to write into (rows of the curves `batch` selects)."""
         with torch.cuda.device(self.device):
             B, P = batch.n_curves, theta.shape[1]
             theta = theta.to(self.device, torch.float64).contiguous()
@@ -231,8 +249,9 @@ class GPEngine:
             if t_min is not None:
                 t_min = torch.as_tensor(t_min, dtype=torch.float64).to(self.device).contiguous().reshape(B)
                 t_max = torch.as_tensor(t_max, dtype=torch.float64).to(self.device).contiguous().reshape(B)
-            out = dict(mean=self._new(B, batch.n_bands, n_obs), std=self._new(B, batch.n_bands, n_obs), lml=self._new(B),
-                       status=self._new(B, dtype=torch.int32))
+            if out is None:
+                out = dict(mean=self._new(B, batch.n_bands, n_obs), std=self._new(B, batch.n_bands, n_obs), lml=self._new(B),
+                           status=self._new(B, dtype=torch.int32))
             ws = self._workspace(batch, P, 1, 1)
             _capi.check(self.lib.fulu_gp_predict_grid_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(t_min), self._p(t_max), n_obs,
                                                             self._p(out["mean"]), self._p(out["std"]), self._p(out["lml"]),
@@ -288,33 +307,59 @@ def bucket_curves(lengths, buckets=N_BUCKETS):
     return [(int(buckets[min(k, len(buckets) - 1)]), np.nonzero(which == k)[0]) for k in np.unique(which)]
 
 
+def pin_results(n_curves, n_bands, n_obs, n_params=4):
+    """Pinned host buffers for the results of fit_augment_batch (reusable across calls: what a production loop double-buffers)."""
+    mk = lambda *shape, dtype=torch.float64: torch.empty(shape, dtype=dtype, pin_memory=True)
+    return dict(mean=mk(n_curves, n_bands, n_obs), std=mk(n_curves, n_bands, n_obs), theta=mk(n_curves, n_params), lml=mk(n_curves),
+                n_eval=mk(n_curves, dtype=torch.int32), status=mk(n_curves, dtype=torch.int32))
+
+
 def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use_err=False, spec: KernelSpec = None, engine: GPEngine = None,
-                      device=None, window=0, pinned=None):
+                      device=None, window=0, pinned=None, out=None):
     """The batched ragged entry point: GP fit + augmentation for every curve of `curves` (host arrays in, host arrays out).
 
     Equivalent to, for each curve i:  aug = fulu.GaussianProcessesAugmentation(passband2lam, use_err=use_err).fit(t, flux, flux_err, band);
     aug.augmentation(t_min[i], t_max[i], n_obs)  (t_min/t_max default to the curve's own span).
+
+    The batch is uploaded once and stays where it is: each length class (N_BUCKETS) is one pass of the library over an index list
+    of its curves, longest class first, and every pass writes its rows of the same device result tensors, which come back in one
+    copy.  `pinned`: pinned staging of the inputs (pin_batch); `out`: pinned result buffers (pin_results) - the returned arrays
+    are then views of them.
     """
     engine = engine or GPEngine(device)
     spec = spec or KernelSpec()
     B, nb, P = curves.n_curves, curves.n_bands, spec.n_params
-    res = AugmentResult(np.empty((B, nb, n_obs)), np.empty((B, nb, n_obs)), np.empty((B, P)), np.empty(B), np.zeros(B, np.int32), np.zeros(B, np.int32))
+    if B == 0:
+        return AugmentResult(np.empty((0, nb, n_obs)), np.empty((0, nb, n_obs)), np.empty((0, P)), np.empty(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
     lengths = curves.lengths()
-    groups = bucket_curves(lengths) if B else []
-    single = len(groups) == 1 and len(groups[0][1]) == B
-    for bound, idx in groups:
-        sub = curves if single else curves.take(idx)
-        db = DeviceBatch.from_host(sub, engine.device, use_err=use_err, pinned=pinned if single else None, n_max=bound)
-        fit = engine.fit(db, spec, window=window)
-        tmn = None if t_min is None else np.asarray(t_min, np.float64)[idx]
-        tmx = None if t_max is None else np.asarray(t_max, np.float64)[idx]
-        pred = engine.predict_grid(db, fit["theta"], n_obs, tmn, tmx)
-        res.flux_aug[idx] = pred["mean"].cpu().numpy()
-        res.flux_err_aug[idx] = pred["std"].cpu().numpy()
-        res.theta[idx] = fit["theta"].cpu().numpy()
-        res.lml[idx] = fit["lml"].cpu().numpy()
-        res.n_eval[idx] = fit["n_eval"].cpu().numpy()
-        res.status[idx] = (fit["status"] | pred["status"]).cpu().numpy()
-        res.h2d_bytes += db.h2d_bytes()
-        res.d2h_bytes += len(idx) * (2 * nb * n_obs * 8 + P * 8 + 8 + 8)
+    groups = bucket_curves(lengths)
+    single = len(groups) == 1
+    with torch.cuda.device(engine.device):
+        db = DeviceBatch.from_host(curves, engine.device, use_err=use_err, pinned=pinned)
+        tmn = None if t_min is None else torch.as_tensor(np.asarray(t_min, np.float64)).to(engine.device)
+        tmx = None if t_max is None else torch.as_tensor(np.asarray(t_max, np.float64)).to(engine.device)
+        new = engine._new
+        fit = dict(theta=new(B, P), lml=new(B), n_eval=new(B, dtype=torch.int32), status=new(B, dtype=torch.int32))
+        pred = dict(mean=new(B, nb, n_obs), std=new(B, nb, n_obs), lml=new(B), status=new(B, dtype=torch.int32))
+        for bound, idx in reversed(groups):   # longest curves first
+            order = None
+            if not single:
+                # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
+                order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
+            sub = db.select(order, n_max=bound)
+            engine.fit(sub, spec, window=window, out=fit)
+            engine.predict_grid(sub, fit["theta"], n_obs, tmn, tmx, out=pred)
+        status = fit["status"] | pred["status"]
+        dev = dict(mean=pred["mean"], std=pred["std"], theta=fit["theta"], lml=fit["lml"], n_eval=fit["n_eval"], status=status)
+        if out is None:
+            host = {k: v.cpu() for k, v in dev.items()}
+        else:
+            host = {k: out[k][:B] for k in dev}
+            for k, v in dev.items():
+                host[k].copy_(v, non_blocking=True)
+            torch.cuda.current_stream(engine.device).synchronize()
+    res = AugmentResult(host["mean"].numpy(), host["std"].numpy(), host["theta"].numpy(), host["lml"].numpy(), host["n_eval"].numpy(),
+                        host["status"].numpy())
+    res.h2d_bytes = db.h2d_bytes()
+    res.d2h_bytes = sum(int(v.numel() * v.element_size()) for v in dev.values())
     return res

@@ -16,6 +16,8 @@
  *   - return value: 0 ok, <0 argument error (FULU_GP_E_*), >0 a cudaError_t;
  *   - per-curve problems never fail the call: they are reported in status[] (FULU_GP_STATUS_* bits).
  *   - batches are ragged CSR: curve i owns observations offsets[i] .. offsets[i+1]-1.
+ *   - results are bitwise reproducible for a given curve and launch geometry; the geometry (shared memory, CTAs per SM, threads
+ *     per CTA) is a function of n_max only.
  */
 #ifndef FULU_GP_H
 #define FULU_GP_H
@@ -27,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FULU_GP_ABI_VERSION 1
+#define FULU_GP_ABI_VERSION 2
 #define FULU_GP_MAX_PARAMS 6
 #define FULU_GP_MAX_BANDS 16
 
@@ -62,6 +64,11 @@ typedef struct fulu_gp_batch {
   int32_t kernel;            /* FULU_GP_KERNEL_* */
   int32_t use_err;           /* fulu use_err flag (gp_aug.py:72-73) */
   double alpha0;             /* regressor alpha when !use_err: 1e-10 (_gpr.py:215) */
+  const int32_t* order;      /* optional [n_order]: the curves (indices into the CSR arrays) this call processes, in processing
+                                order; NULL = all n_curves.  Lets a caller run one launch per length class (n_max = the class
+                                bound) over a batch that stays where it is in HBM - no repacking.  Inputs and outputs are always
+                                indexed by curve id; rows of curves that are not listed are left untouched. */
+  int64_t n_order;
 } fulu_gp_batch;
 
 typedef struct fulu_gp_fit_options {

@@ -28,7 +28,7 @@ def test_binding_loads_and_reports_version(lib_path):
     from fulu_b200 import _capi
 
     lib = _capi.load()
-    assert lib.fulu_gp_abi_version() == 1
+    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 2
     assert b"workspace" in lib.fulu_gp_strerror(-2)
     assert set(_capi.EXPORTS) <= {n for n in dir(lib)} | set(_capi.EXPORTS)
 
@@ -36,8 +36,8 @@ def test_binding_loads_and_reports_version(lib_path):
 def test_struct_layout_matches_header():
     from fulu_b200 import _capi
 
-    # fulu_gp_batch: 2*i64 + 2*i32 + 6 pointers + 2*i32 + f64 = 88 bytes; fit options: 8*i32 + 2*f64 + 12*f64 + pointer = 152
-    assert ctypes.sizeof(_capi.Batch) == 88
+    # fulu_gp_batch: 2*i64 + 2*i32 + 6 pointers + 2*i32 + f64 + pointer + i64 = 104 bytes; fit options: 8*i32 + 2*f64 + 12*f64 + pointer = 152
+    assert ctypes.sizeof(_capi.Batch) == 104
     assert ctypes.sizeof(_capi.FitOptions) == 152
 
 

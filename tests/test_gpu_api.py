@@ -104,6 +104,32 @@ def test_batched_entry_point_equals_per_curve_and_is_batch_independent():
     np.testing.assert_array_equal(res2.lml, res.lml)
 
 
+def test_order_list_processes_only_the_listed_curves_in_place():
+    """fulu_gp_batch.order: a launch over an index list reads the batch where it lies and writes only the listed rows."""
+    import fulu_b200
+    from fulu_b200 import DeviceBatch, datasets
+
+    eng = fulu_b200.GPEngine()
+    hb = datasets.ztf_like(24, first=900, n_lo=20, n_hi=100)
+    db = DeviceBatch.from_host(hb, eng.device)
+    theta = torch.tensor(np.tile([0.1, -1.0, 1.5, -3.0], (24, 1)))
+    full = eng.lml(db, theta)
+    order = np.array([17, 3, 8, 21], np.int32)
+    sub = db.select(order, n_max=104)
+    part = eng.lml(sub, theta)
+    np.testing.assert_allclose(part["lml"].cpu().numpy()[order], full["lml"].cpu().numpy()[order], rtol=1e-13)
+    np.testing.assert_allclose(part["grad"].cpu().numpy()[order], full["grad"].cpu().numpy()[order], rtol=1e-9, atol=1e-9)
+    sentinel = dict(theta=torch.full((24, 4), -7.0, dtype=torch.float64, device=eng.device), lml=torch.full((24,), -7.0, dtype=torch.float64, device=eng.device),
+                    n_eval=torch.full((24,), -7, dtype=torch.int32, device=eng.device), status=torch.full((24,), -7, dtype=torch.int32, device=eng.device))
+    eng.fit(sub, out=sentinel)
+    rest = np.setdiff1d(np.arange(24), order)
+    assert np.all(sentinel["lml"].cpu().numpy()[rest] == -7.0) and np.all(sentinel["n_eval"].cpu().numpy()[rest] == -7)
+    assert np.all(sentinel["n_eval"].cpu().numpy()[order] > 0) and np.all(np.isfinite(sentinel["lml"].cpu().numpy()[order]))
+    # the same curves fitted as their own batch (same length class => same launch geometry) give the same bits
+    own = eng.fit(DeviceBatch.from_host(hb.take(order), eng.device, n_max=104))
+    np.testing.assert_array_equal(own["theta"].cpu().numpy(), sentinel["theta"].cpu().numpy()[order])
+
+
 def test_edge_cases():
     import fulu_b200
     from fulu_b200 import CurveBatch, DeviceBatch
