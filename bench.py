@@ -300,6 +300,15 @@ def run_gpu(args):
     f_eval = N_POINTS ** 3 + 12 * N_POINTS ** 2
     achieved = (evals_all / world) * f_eval / (eval_ms_all * 1e-3) / 1e12   # TFLOP/s of the evaluation kernel on one GPU
     pr = fit["profile"]
+    # DRAM traffic of the dominant kernel per launch: bytes per evaluation from the committed ncu --set full capture, times the
+    # evaluations an average launch of THIS run carried
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_eval_kernel_traffic.json")))
+        traffic = tj["dram_bytes_per_evaluation"] * (evals_all / world) / max(rounds, 1)
+        traffic_src = "profiles/r01_v4_eval_kernel_traffic.json (dram__bytes_read+write per evaluation, ncu --set full) x evaluations per launch of this run"
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": "curves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -311,7 +320,8 @@ def run_gpu(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
-                     "frac": achieved / peak_dfma if peak_dfma else None, "traffic": None,
+                     "frac": achieved / peak_dfma if peak_dfma else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": (28 * N_POINTS + 8 + 8 * 4 + 8 * 5) * (evals_all / world) / max(rounds, 1),
                      "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",
                      "peak_dmma": peak_dmma, "flops_per_eval": f_eval, "evals_per_curve": evals_all / (world * B * args.steps),
                      "eval_kernel_ms_per_step": eval_ms_all / args.steps, "eval_kernel_share_of_step": eval_ms_all / ms_max,
