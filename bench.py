@@ -180,13 +180,34 @@ class ClockSampler:
                 "samples": len(sm), "how": "nvidia-smi -lms 500"}
 
 
+WORKLOADS = {
+    # name: (description, default curves per GPU per step, n_obs)
+    "plasticc": ("BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands), one batch per GPU per step", 10000, N_OBS),
+    "ztf": ("BASELINE config #4 sample (ZTF-like, 2 bands g/r, ragged N = round(exp(U(ln 20, ln 300))), 128-point grid x 2 bands), "
+            "one batch per GPU per step, length classes run as index-list launches over the resident batch", 20000, N_OBS),
+    "ddf": ("BASELINE config #5 (LSST-DDF-like, 6 bands, N in {1024, 1536, 2048} in equal parts, 128-point grid x 6 bands), "
+            "one CTA per (curve, start) with the matrix in an L2/HBM-resident slab", 48, N_OBS),
+}
+
+
+def make_workload(name, B, rank):
+    from fulu_b200 import CurveBatch, datasets
+
+    if name == "plasticc":
+        return datasets.plasticc_like(B, n_points=N_POINTS, first=rank * B)   # each rank: its own B curves (weak scaling)
+    if name == "ztf":
+        return datasets.ztf_like(B, first=rank * B)
+    parts = [datasets.ddf_like((B + 2 - k) // 3, n_points=n, first=rank * B + k * B) for k, n in enumerate((1024, 1536, 2048))]
+    curves = [p.curve(i) for p in parts for i in range(p.n_curves)]
+    return CurveBatch.from_curves(curves, parts[0].loglam)
+
+
 def run_gpu(args):
     import numpy as np
     import torch
 
     import fulu_b200
-    from fulu_b200 import datasets
-    from fulu_b200.engine import DeviceBatch, pin_batch, pin_results
+    from fulu_b200.engine import DeviceBatch, fit_augment_device, pin_batch, pin_results
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,9 +227,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    desc, default_b, n_obs = WORKLOADS[args.workload]
+    headline = args.workload == "plasticc"
     # CPU baseline first (rank 0, N=1 only), before this process's CUDA context is busy
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and headline:
         cores = os.cpu_count() or 1
         sample_n = max(2 * cores, min(args.ref_curves, 24 * cores))
         v, dt, cores, _ = cpu_reference_throughput(sample_n, cores)
@@ -217,22 +240,23 @@ def run_gpu(args):
                               "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"}
 
     engine = fulu_b200.GPEngine(torch.device("cuda", local))
-    B = args.curves
-    host = datasets.plasticc_like(B, n_points=N_POINTS, first=rank * B)   # each rank: its own B curves (weak scaling)
+    B = args.curves or default_b
+    host = make_workload(args.workload, B, rank)
+    lengths = host.lengths()
+    nb = host.n_bands
     pinned = pin_batch(host)
-    pinned_out = pin_results(B, N_BANDS, N_OBS)
+    pinned_out = pin_results(B, nb, n_obs)
     dev = DeviceBatch.from_host(host, engine.device, pinned=pinned)
+    in_bytes = dev.h2d_bytes()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=engine.device)   # > 126 MB L2
 
     def step_resident(profile=False):
-        flush.zero_()   # L2 flush between timed iterations (inputs are 28 MB, smaller than L2)
-        fit = engine.fit(dev, profile=profile)
-        pred = engine.predict_grid(dev, fit["theta"], N_OBS)
-        return fit, pred
+        flush.zero_()   # L2 flush between timed iterations (the headline inputs are 28 MB, smaller than L2)
+        return fit_augment_device(engine, dev, lengths, n_obs, profile=profile)
 
     def step_e2e():
         flush.zero_()
-        return fulu_b200.fit_augment_batch(host, n_obs=N_OBS, engine=engine, pinned=pinned, out=pinned_out)
+        return fulu_b200.fit_augment_batch(host, n_obs=n_obs, engine=engine, pinned=pinned, out=pinned_out)
 
     for _ in range(args.warmup):
         step_resident()
@@ -246,16 +270,16 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     e0.record()
-    evals, launches = 0, 0
-    n_eval_sums = []
+    kept = []
     for _ in range(args.steps):
-        fit, pred = step_resident()
-        n_eval_sums.append(fit["n_eval"].sum())          # stays on the device: no host sync inside the timed region
+        kept.append(step_resident()["n_eval"])          # stays on the device: no host sync inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    evals = int(sum(int(x.item()) for x in n_eval_sums))
+    f_eval_curve = lengths.astype(np.float64) ** 3 + 12.0 * lengths.astype(np.float64) ** 2      # SURVEY 8d, per evaluation
+    evals = float(sum(float(x.sum().item()) for x in kept))
+    flops = float(sum(float(np.dot(x.cpu().numpy().astype(np.float64), f_eval_curve)) for x in kept))
     t = torch.tensor([ms], dtype=torch.float64, device=engine.device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -264,11 +288,11 @@ def run_gpu(args):
 
     # ---- the same K steps once more with the library's per-launch CUDA events switched on (outside the timed region: creating
     # and recording three events per round costs ~10 % of a step): kernel durations for the roofline, launch counts
-    eval_ms, step_ms, rounds = 0.0, 0.0, 0
+    eval_ms, step_ms, rounds, launches, classes = 0.0, 0.0, 0, 0, []
     for _ in range(args.steps):
-        fit, pred = step_resident(profile=True)
-        pr = fit["profile"]
-        eval_ms += pr["eval_ms"]; step_ms += pr["step_ms"]; rounds += int(pr["rounds"]); launches += int(pr["launches"]) + 3
+        classes = step_resident(profile=True)["profile"]
+        for pr in classes:
+            eval_ms += pr["eval_ms"]; step_ms += pr["step_ms"]; rounds += int(pr["rounds"]); launches += int(pr["launches"]) + 3
     torch.cuda.synchronize()
 
     # ---- timed: end to end through the public API (pinned host in, host out)
@@ -289,47 +313,55 @@ def run_gpu(args):
 
     status = res.status
     flagged = float(np.count_nonzero(status & ~8))   # anything but "theta on a bound"
-    stats = torch.tensor([evals, eval_ms, flagged], dtype=torch.float64, device=engine.device)
+    stats = torch.tensor([evals, eval_ms, flagged, flops], dtype=torch.float64, device=engine.device)
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    evals_all, eval_ms_all = float(stats[0]), float(stats[1]) / world
-    f_eval = N_POINTS ** 3 + 12 * N_POINTS ** 2
-    achieved = (evals_all / world) * f_eval / (eval_ms_all * 1e-3) / 1e12   # TFLOP/s of the evaluation kernel on one GPU
-    pr = fit["profile"]
-    # DRAM traffic of the dominant kernel per launch: bytes per evaluation from the committed ncu --set full capture, times the
-    # evaluations an average launch of THIS run carried
+    evals_all, eval_ms_all, flops_all = float(stats[0]), float(stats[1]) / world, float(stats[3])
+    achieved = (flops_all / world) / (eval_ms_all * 1e-3) / 1e12   # TFLOP/s of the evaluation kernel on one GPU (algorithmic flops)
+    # DRAM traffic of the dominant kernel per launch: bytes per evaluation from the committed ncu --set full capture (N = 100), times
+    # the evaluations an average launch of THIS run carried
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_eval_kernel_traffic.json")))
-        traffic = tj["dram_bytes_per_evaluation"] * (evals_all / world) / max(rounds, 1)
-        traffic_src = "profiles/r01_v4_eval_kernel_traffic.json (dram__bytes_read+write per evaluation, ncu --set full) x evaluations per launch of this run"
-    except (OSError, KeyError, ValueError):
-        pass
+    if headline:
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_eval_kernel_traffic.json")))
+            traffic = tj["dram_bytes_per_evaluation"] * (evals_all / world) / max(rounds, 1)
+            traffic_src = ("profiles/r01_v4_eval_kernel_traffic.json (dram__bytes_read+write per evaluation, ncu --set full) x evaluations "
+                           "per launch of this run")
+        except (OSError, KeyError, ValueError):
+            pass
+    mean_in = in_bytes / B
+    out_bytes = 16 * nb * n_obs + 8 * 4 + 16
+    cfg = {"workload": desc, "curves_per_gpu_per_step": B, "n_points": N_POINTS if headline else f"{int(lengths.min())}..{int(lengths.max())} (mean {lengths.mean():.0f})",
+           "n_bands": nb, "n_obs": n_obs, "n_starts": 6,
+           "l2": f"flushed between steps (256 MiB memset); inputs {in_bytes / 1e6:.0f} MB", "parallelism": f"curve-sharded x{world}, no collective"}
     line = {
-        "metric": METRIC, "value": value, "unit": "curves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if headline else f"light curves/sec GP fit+augment ({args.workload} workload)", "value": value, "unit": "curves/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands), one batch per GPU per step",
-                   "curves_per_gpu_per_step": B, "n_points": N_POINTS, "n_bands": N_BANDS, "n_obs": N_OBS, "n_starts": 6,
-                   "l2": "flushed between steps (256 MiB memset); inputs 28 MB", "parallelism": f"curve-sharded x{world}, no collective"},
+        "config": cfg,
         "e2e": {"value": e2e_value, "unit": "curves/s", "h2d_bytes_per_step": int(res.h2d_bytes), "d2h_bytes_per_step": int(res.d2h_bytes)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
                      "frac": achieved / peak_dfma if peak_dfma else None, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": (28 * N_POINTS + 8 + 8 * 4 + 8 * 5) * (evals_all / world) / max(rounds, 1),
+                     "algorithmic_bytes_per_launch": (mean_in + 8 * 4 + 8 * 5) * (evals_all / world) / max(rounds, 1),
                      "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",
-                     "peak_dmma": peak_dmma, "flops_per_eval": f_eval, "evals_per_curve": evals_all / (world * B * args.steps),
+                     "peak_dmma": peak_dmma, "flops_per_eval": (N_POINTS ** 3 + 12 * N_POINTS ** 2) if headline else flops_all / max(evals_all, 1),
+                     "evals_per_curve": evals_all / (world * B * args.steps),
                      "eval_kernel_ms_per_step": eval_ms_all / args.steps, "eval_kernel_share_of_step": eval_ms_all / ms_max,
                      "timing": "kernel durations from CUDA events on the launching stream in a separate pass of the same K steps; "
                                "the timed region itself runs without them",
                      "step_kernel_ms_per_step": step_ms / args.steps, "rounds_per_step": rounds / args.steps,
-                     "hbm_gbs_algorithmic": value / world * (28 * N_POINTS + 8 + 16 * N_BANDS * N_OBS + 8 * 4 + 16) / 1e9,
-                     "grid": int(pr["grid_eval"]), "smem_per_cta": int(pr["smem_eval"])},
+                     "hbm_gbs_algorithmic": value / world * (mean_in + out_bytes) / 1e9,
+                     "launch_classes": [{"n_max": int(c["bound"]), "curves": int(c["curves"]), "ctas": int(c["grid_eval"]), "threads": int(c["threads_eval"]),
+                                         "ctas_per_sm": int(c["ctas_per_sm"]), "smem_per_cta": int(c["smem_eval"]), "matrix_in_global": bool(c["global_a"]),
+                                         "eval_ms": c["eval_ms"]} for c in classes],
+                     "grid": int(classes[0]["grid_eval"]), "smem_per_cta": int(classes[0]["smem_eval"])},
         "cpu_baseline": cpu_base,
         "parity": {"curves_flagged": int(stats[2]), "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)]))},
     }
@@ -343,7 +375,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--curves", type=int, default=10000, help="curves per GPU per step (config #3: 10,000)")
+    ap.add_argument("--curves", type=int, default=0, help="curves per GPU per step (default: the workload's own, 10,000 for config #3)")
+    ap.add_argument("--workload", default="plasticc", choices=sorted(WORKLOADS), help="plasticc = the headline config #3 (default); ztf = config #4 sample; ddf = config #5")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-curves", type=int, default=256, help="CPU sample size per step (bounded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

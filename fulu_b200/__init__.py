@@ -3,7 +3,7 @@
 Importing the package does not need a GPU; constructing an engine / fitting does, and fails loudly without one.
 """
 from .datasets import CurveBatch  # noqa: F401
-from .engine import AugmentResult, DeviceBatch, GPEngine, KernelSpec, fit_augment_batch  # noqa: F401
+from .engine import AugmentResult, DeviceBatch, GPEngine, KernelSpec, fit_augment_batch, fit_augment_device, pin_results  # noqa: F401
 from .gp_aug import ConvergenceWarning, GaussianProcessesAugmentation, add_log_lam, create_aug_data  # noqa: F401
 
 __all__ = ["GaussianProcessesAugmentation", "fit_augment_batch", "GPEngine", "DeviceBatch", "CurveBatch", "KernelSpec", "AugmentResult",

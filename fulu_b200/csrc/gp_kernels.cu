@@ -102,6 +102,8 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.smem_predict = w.smem_eval;
   // residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation is latency bound, so as many curves per
   // SM as fit, and the 512 threads the register file allows are split between them
+  // (matrix in global memory: one 512-thread CTA per SM above np = 512 - two 256-thread CTAs per SM were measured 37 % slower at
+  // N = 1024..2048, the slab traffic is what limits that path)
   int occ = w.globalA ? (np <= 512 ? 2 : 1) : (int)((228 * 1024) / (w.smem_eval + 1024));
   if (occ < 1) occ = 1;
   if (occ > 16) occ = 16;

@@ -70,7 +70,8 @@ class CurveBatch:
 
 def _bazin(t, lam, A, t0, tr, tf):
     colour = 1.0 + 0.15 * (lam / 6000.0 - 1.0)
-    return colour * A * np.exp(-(t - t0) / tf) / (1.0 + np.exp(-(t - t0) / tr))
+    with np.errstate(over="ignore"):   # exp overflow far before the rise: the quotient is exactly 0 there
+        return colour * A * np.exp(-(t - t0) / tf) / (1.0 + np.exp(-(t - t0) / tr))
 
 
 def _bazin_curve(rng, n, lams, span, t_start=59000.0, n_bumps=1, const=0.0):

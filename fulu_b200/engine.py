@@ -314,6 +314,36 @@ def pin_results(n_curves, n_bands, n_obs, n_params=4):
                 n_eval=mk(n_curves, dtype=torch.int32), status=mk(n_curves, dtype=torch.int32))
 
 
+def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, t_min=None, t_max=None, spec: KernelSpec = None, window=0,
+                       profile=False):
+    """Fit + augmentation of a batch that is already resident in HBM: one pass of the library per length class (N_BUCKETS) over
+    an index list of the class's curves, longest class first; every pass writes its rows of the same result tensors.
+    Returns device tensors dict(mean, std [B,n_bands,n_obs], theta [B,P], lml, n_eval, status [B]) (+ "profile": per-class list)."""
+    spec = spec or KernelSpec()
+    lengths = np.asarray(lengths)
+    B, nb, P = db.n_curves, db.n_bands, spec.n_params
+    groups = bucket_curves(lengths)
+    single = len(groups) == 1
+    new = engine._new
+    fit = dict(theta=new(B, P), lml=new(B), n_eval=new(B, dtype=torch.int32), status=new(B, dtype=torch.int32))
+    pred = dict(mean=new(B, nb, n_obs), std=new(B, nb, n_obs), lml=new(B), status=new(B, dtype=torch.int32))
+    profiles = []
+    for bound, idx in reversed(groups):   # longest curves first
+        order = None
+        if not single:
+            # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
+            order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
+        sub = db.select(order, n_max=bound)
+        f = engine.fit(sub, spec, window=window, out=fit, profile=profile)
+        engine.predict_grid(sub, fit["theta"], n_obs, t_min, t_max, out=pred)
+        if profile:
+            profiles.append(dict(f["profile"], bound=bound, curves=len(idx)))
+    out = dict(mean=pred["mean"], std=pred["std"], theta=fit["theta"], lml=fit["lml"], n_eval=fit["n_eval"], status=fit["status"] | pred["status"])
+    if profile:
+        out["profile"] = profiles
+    return out
+
+
 def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use_err=False, spec: KernelSpec = None, engine: GPEngine = None,
                       device=None, window=0, pinned=None, out=None):
     """The batched ragged entry point: GP fit + augmentation for every curve of `curves` (host arrays in, host arrays out).
@@ -331,26 +361,11 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     B, nb, P = curves.n_curves, curves.n_bands, spec.n_params
     if B == 0:
         return AugmentResult(np.empty((0, nb, n_obs)), np.empty((0, nb, n_obs)), np.empty((0, P)), np.empty(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
-    lengths = curves.lengths()
-    groups = bucket_curves(lengths)
-    single = len(groups) == 1
     with torch.cuda.device(engine.device):
         db = DeviceBatch.from_host(curves, engine.device, use_err=use_err, pinned=pinned)
         tmn = None if t_min is None else torch.as_tensor(np.asarray(t_min, np.float64)).to(engine.device)
         tmx = None if t_max is None else torch.as_tensor(np.asarray(t_max, np.float64)).to(engine.device)
-        new = engine._new
-        fit = dict(theta=new(B, P), lml=new(B), n_eval=new(B, dtype=torch.int32), status=new(B, dtype=torch.int32))
-        pred = dict(mean=new(B, nb, n_obs), std=new(B, nb, n_obs), lml=new(B), status=new(B, dtype=torch.int32))
-        for bound, idx in reversed(groups):   # longest curves first
-            order = None
-            if not single:
-                # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
-                order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
-            sub = db.select(order, n_max=bound)
-            engine.fit(sub, spec, window=window, out=fit)
-            engine.predict_grid(sub, fit["theta"], n_obs, tmn, tmx, out=pred)
-        status = fit["status"] | pred["status"]
-        dev = dict(mean=pred["mean"], std=pred["std"], theta=fit["theta"], lml=fit["lml"], n_eval=fit["n_eval"], status=status)
+        dev = fit_augment_device(engine, db, curves.lengths(), n_obs, tmn, tmx, spec, window)
         if out is None:
             host = {k: v.cpu() for k, v in dev.items()}
         else:

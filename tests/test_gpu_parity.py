@@ -153,9 +153,9 @@ def test_fixed_theta_prediction_against_live_sklearn(engine):
         assert abs(float(out["lml"][i]) - ref.reg.log_marginal_likelihood_value_) < 1e-9 * max(1, abs(ref.reg.log_marginal_likelihood_value_))
 
 
-@pytest.mark.parametrize("n", [164, 200, 300])
+@pytest.mark.parametrize("n", [164, 216, 217, 300])
 def test_long_curves_use_the_global_memory_path(engine, n):
-    """N above the shared-memory limit: K lives in an L2-resident slab; same numbers as the oracle."""
+    """Around and above the shared-memory limit (N = 216): K lives in an L2-resident slab; same numbers as the oracle."""
     from fulu_b200 import DeviceBatch, datasets
     from oracle import gp_oracle as O
 
@@ -175,3 +175,45 @@ def test_long_curves_use_the_global_memory_path(engine, n):
         _, m, s, _ = gp.augmentation(t.min(), t.max(), 16)
         assert relerr(pred["mean"][i].cpu().numpy().reshape(-1), m, floor=1e-3 * gp.y_std) < 1e-9
         assert relerr(pred["std"][i].cpu().numpy().reshape(-1), s) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_config5_long_curves_fixed_theta_parity(engine, n):
+    """BASELINE config #5 (LSST-DDF-like, 6 bands, N = 1024 / 2048): LML, gradient, predictive mean and std at fixed
+    hyperparameters against the closed-form oracle, 1e-9 relative."""
+    from fulu_b200 import DeviceBatch, datasets
+    from oracle import gp_oracle as O
+
+    hb = datasets.ddf_like(2, n_points=n, first=40)
+    db = DeviceBatch.from_host(hb, engine.device)
+    theta = np.array([[0.5, -1.0, 1.0, -3.0], [1.0, -2.5, 0.5, -5.0]])
+    out = engine.lml(db, torch.tensor(theta))
+    pred = engine.predict_grid(db, torch.tensor(theta), 24)
+    p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
+    for i in range(2):
+        t, f, e, b = hb.curve(i)
+        gp = O.ClosedFormGP(p2l).fit(t, f, e, b, theta=theta[i])
+        l, g, gs = O.lml_and_grad(gp.X, gp.y, gp.alpha, theta[i], return_scale=True)
+        assert abs(float(out["lml"][i]) - l) <= 1e-9 * max(1, abs(l))
+        assert np.max(np.abs(out["grad"][i].cpu().numpy() - g) / np.maximum(np.abs(g), 1e-2 * gs)) < 1e-9
+        _, m, s_, _ = gp.augmentation(t.min(), t.max(), 24)
+        assert relerr(pred["mean"][i].cpu().numpy().reshape(-1), m, floor=1e-3 * gp.y_std) < 1e-9
+        assert relerr(pred["std"][i].cpu().numpy().reshape(-1), s_) < 1e-9
+
+
+def test_config5_fit_reaches_oracle_lml(engine):
+    """A long curve through the whole optimiser (N = 400, global-memory path): final LML no worse than SciPy's L-BFGS-B on the
+    closed-form objective from the same six starts, by more than 1e-6."""
+    from fulu_b200 import DeviceBatch, datasets
+    from oracle import gp_oracle as O
+
+    hb = datasets.ddf_like(2, n_points=400, first=7)
+    db = DeviceBatch.from_host(hb, engine.device)
+    fit = engine.fit(db)
+    p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
+    for i in range(2):
+        gp = O.ClosedFormGP(p2l).prepare(*hb.curve(i))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _, lml_ref, _ = O.fit_theta(gp.X, gp.y, gp.alpha)
+        assert float(fit["lml"][i]) >= lml_ref - 1e-6, (i, float(fit["lml"][i]), lml_ref)
