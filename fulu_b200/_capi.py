@@ -7,7 +7,7 @@ import os
 from .build import LIB_PATH
 
 MAX_PARAMS = 6
-ABI_VERSION = 2   # FULU_GP_ABI_VERSION of include/fulu_gp.h this binding was written against
+ABI_VERSION = 3   # FULU_GP_ABI_VERSION of include/fulu_gp.h this binding was written against
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
@@ -25,6 +25,7 @@ class FitOptions(ctypes.Structure):
     _fields_ = [
         ("n_params", ctypes.c_int32), ("n_starts", ctypes.c_int32), ("m", ctypes.c_int32), ("maxiter", ctypes.c_int32),
         ("maxfun", ctypes.c_int32), ("maxls", ctypes.c_int32), ("window", ctypes.c_int32), ("max_rounds", ctypes.c_int32),
+        ("starts_per_curve", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("factr", ctypes.c_double), ("pgtol", ctypes.c_double),
         ("lower", ctypes.c_double * MAX_PARAMS), ("upper", ctypes.c_double * MAX_PARAMS),
         ("profile", ctypes.POINTER(ctypes.c_double)),

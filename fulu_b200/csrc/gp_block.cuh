@@ -195,15 +195,125 @@ GP_DEV double gp_exp_neg(double x) {
   return x < gp_exp_c[17] ? 0.0 : res;
 }
 
-// c * exp(-1/2 |x_i/l - x_j/l|^2) for i != j  (kernels.py:1561-1565)
-GP_DEV double gp_kernel_value(double cst, double ui, double vi, double uj, double vj) {
-  const double du = ui - uj, dv = vi - vj;
-  return cst * gp_exp_neg(-0.5 * (du * du + dv * dv));
-}
+// ---------------------------------------------------------------------------------------------- covariance families
+// The covariance is   K = c * [M1(r_1)] * RBF([l_t, l_lambda]) + [EX(r_e)] + s2 I   with optional isotropic factors:
+//   M1  a Matern factor multiplying the anisotropic RBF   (sklearn: ConstantKernel * Matern * RBF, kernels.py:964-971)
+//   EX  an added isotropic Matern or RationalQuadratic    (sklearn: ... + Matern() / + RationalQuadratic(), kernels.py:866-871)
+// theta (log-transformed, canonical device order) = [c, (l_1), l_t, l_lambda, (EX: l | alpha, l), s2]; the host permutes between
+// sklearn's tree order (kernels.py:739-752) and this one.  Families are compile-time (template arguments), so the default
+// family's code is exactly what it was as a dedicated path and the others cost nothing when unused.
+// Coordinates live in shared memory divided by the RBF length scales (u = x0 / l_t, v = x1 / l_lambda, kernels.py:1561); an
+// isotropic factor with length l sees r^2 = (l_t / l)^2 du^2 + (l_lambda / l)^2 dv^2.
+enum { GP_F_NONE = 0, GP_F_MAT05 = 1, GP_F_MAT15 = 2, GP_F_MAT25 = 3, GP_F_RQ = 4 };
+
+GP_DEV double gp_rsqrt(double d);
+
+// sqrt(q) for q >= 0 through the lean reciprocal square root (zero and denormal-range arguments give 0: the factor is 1 there)
+GP_DEV double gp_sqrt_pos(double q) { return q > 1.0e-290 ? q * gp_rsqrt(q) : 0.0; }
+
+template <int KIND>
+struct GpIso {
+  double au, av;   // r^2 = au du^2 + av dv^2
+  double alpha;    // RationalQuadratic scale mixture
+  GP_DEV void init(double lt, double ll, double l, double al) {
+    const double ru = lt / l, rv = ll / l;
+    au = ru * ru; av = rv * rv; alpha = al;
+  }
+  // value k, dk/dlog(l) (gl) and, for RQ, dk/dlog(alpha) (ga)  (kernels.py:1722-1729,1757-1774 Matern; :1917-1947 RQ)
+  template <bool GRAD>
+  GP_DEV void eval(double du2, double dv2, double& k, double& gl, double& ga) const {
+    const double s = fma(au, du2, av * dv2);
+    gl = 0.0; ga = 0.0;
+    if constexpr (KIND == GP_F_MAT05) {
+      const double r = gp_sqrt_pos(s);
+      k = gp_exp_neg(-r);
+      if (GRAD) gl = k * r;
+    } else if constexpr (KIND == GP_F_MAT15) {
+      const double a = gp_sqrt_pos(3.0 * s), e = gp_exp_neg(-a);
+      k = (1.0 + a) * e;
+      if (GRAD) gl = 3.0 * s * e;
+    } else if constexpr (KIND == GP_F_MAT25) {
+      const double a = gp_sqrt_pos(5.0 * s), e = gp_exp_neg(-a);
+      k = (1.0 + a + a * a / 3.0) * e;
+      if (GRAD) gl = (5.0 / 3.0) * s * (a + 1.0) * e;
+    } else if constexpr (KIND == GP_F_RQ) {
+      const double base = 1.0 + s / (2.0 * alpha), lb = log(base);
+      k = gp_exp_neg(-alpha * lb);
+      if (GRAD) {
+        gl = s * k / base;
+        ga = k * (s / (2.0 * base) - alpha * lb);
+      }
+    } else {
+      k = 1.0;
+    }
+  }
+};
+
+template <int F1, int EX>
+struct GpKern {
+  static_assert(F1 != GP_F_RQ, "the product factor is a Matern");
+  static constexpr int NF1 = (F1 == GP_F_NONE) ? 0 : 1;
+  static constexpr int NEX = (EX == GP_F_NONE) ? 0 : (EX == GP_F_RQ ? 2 : 1);
+  static constexpr int P = 4 + NF1 + NEX;   // hyperparameters
+  static constexpr int NTR = P - 1;         // traces over the strictly-lower pairs: every parameter but the noise level
+  double cst, s2, lt, ll;
+  GpIso<F1> f1;
+  GpIso<EX> ex;
+
+  GP_DEV void init(const double* theta) {
+    cst = exp(theta[0]);
+    lt = exp(theta[1 + NF1]);
+    ll = exp(theta[2 + NF1]);
+    s2 = exp(theta[P - 1]);
+    if constexpr (NF1 > 0) f1.init(lt, ll, exp(theta[1]), 0.0);
+    if constexpr (EX == GP_F_RQ) ex.init(lt, ll, exp(theta[4 + NF1]), exp(theta[3 + NF1]));   // sklearn orders alpha before length_scale
+    else if constexpr (NEX > 0) ex.init(lt, ll, exp(theta[3 + NF1]), 0.0);
+  }
+  // K_ij, i != j, from the squared scaled differences
+  GP_DEV double value(double du2, double dv2) const {
+    double k = cst * gp_exp_neg(-0.5 * (du2 + dv2));
+    double f, g0, g1;
+    if constexpr (NF1 > 0) { f1.template eval<false>(du2, dv2, f, g0, g1); k *= f; }
+    if constexpr (NEX > 0) { ex.template eval<false>(du2, dv2, f, g0, g1); k += f; }
+    return k;
+  }
+  // K_ii without the regressor's alpha: every stationary factor is 1 at zero distance, White adds s2 (kernels.py:490,1438-1440)
+  GP_DEV double diag() const { return NEX ? (cst + 1.0) + s2 : cst + s2; }
+  // tr[k] += w dK_ij / dtheta_k for the NTR parameters that act off the diagonal
+  GP_DEV void accumulate(double w, double du2, double dv2, double (&tr)[NTR]) const {
+    const double e = cst * gp_exp_neg(-0.5 * (du2 + dv2));
+    double f, gl, ga;
+    if constexpr (NF1 > 0) {
+      f1.template eval<true>(du2, dv2, f, gl, ga);
+      const double wk = w * (e * f);
+      tr[0] += wk;
+      tr[1] += w * (e * gl);
+      tr[2] += wk * du2;
+      tr[3] += wk * dv2;
+    } else {
+      const double wk = w * e;
+      tr[0] += wk;
+      tr[1] += wk * du2;
+      tr[2] += wk * dv2;
+    }
+    if constexpr (NEX > 0) {
+      ex.template eval<true>(du2, dv2, f, gl, ga);
+      if constexpr (EX == GP_F_RQ) { tr[3 + NF1] += w * ga; tr[NTR - 1] += w * gl; }
+      else tr[3 + NF1] += w * gl;
+    }
+  }
+  // gradient of the LML from the pair traces and trd = sum_i W_ii (the 1/2 of Eq. 5.9 cancels against the two triangles)
+  GP_DEV void gradient(const double* tr, double trd, double* grad) const {
+    grad[0] = tr[0] + 0.5 * cst * trd;
+    for (int k = 1; k < NTR; ++k) grad[k] = tr[k];
+    grad[P - 1] = 0.5 * s2 * trd;
+  }
+};
+using GpKernDefault = GpKern<GP_F_NONE, GP_F_NONE>;   // C * RBF([l_t, l_lambda]) + White  (fulu/gp_aug.py:29)
 
 // K into the lower tiles, y^T into row 0 of the border tile-row.  One warp per tile; lane (g, t) writes (g, t) and (g, 4 + t).
-template <class Ctx>
-GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, double cst, double s2) {
+template <class Ctx, class Kern>
+GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Kern& kn) {
   const int T = s.T, n = cv.n, ntile = T * (T + 1) / 2 + T, g = c.lane >> 2, t = c.lane & 3;
   const GpFrag f = gp_frag(c.lane);
   int I = 0, J = c.warp;
@@ -219,13 +329,14 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, double c
       const int i = 8 * I + g;
       const double ui = s.u[i], vi = s.v[i];
       // diagonal tiles are assembled in full (both triangles): the warp-level factorisation keeps them symmetric
-      v0 = gp_kernel_value(cst, ui, vi, s.u[j0], s.v[j0]);
-      v1 = gp_kernel_value(cst, ui, vi, s.u[j1], s.v[j1]);
+      const double du0 = ui - s.u[j0], dv0 = vi - s.v[j0], du1 = ui - s.u[j1], dv1 = vi - s.v[j1];
+      v0 = kn.value(du0 * du0, dv0 * dv0);
+      v1 = kn.value(du1 * du1, dv1 * dv1);
       if (i >= n || j0 >= n) v0 = 0.0;
       if (i >= n || j1 >= n) v1 = 0.0;
       // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding
-      if (i == j0) v0 = (i < n) ? (cst + s2) + cv.al[i] : 1.0;
-      if (i == j1) v1 = (i < n) ? (cst + s2) + cv.al[i] : 1.0;
+      if (i == j0) v0 = (i < n) ? kn.diag() + cv.al[i] : 1.0;
+      if (i == j1) v1 = (i < n) ? kn.diag() + cv.al[i] : 1.0;
     }
     tp[f.a0] = v0;
     tp[f.a1] = v1;
@@ -498,16 +609,19 @@ GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
   c.sync();
 }
 
-// Fused K^-1 = X^T X (8x8 DMMA tiles), recomputed K and gradient traces.  tr[0] = sum_{i>j} W_ij K_ij, tr[1]/tr[2] the same
-// weighted by the squared scaled time / wavelength differences, tr[3] = sum_i W_ii  (W = alpha alpha^T - K^-1).
-template <class Ctx>
-GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double cst, double tr[4]) {
+// Fused K^-1 = X^T X (8x8 DMMA tiles), recomputed K and gradient traces.  tr[k] = sum_{i>j} W_ij dK_ij/dtheta_k for the
+// parameters that act off the diagonal (default family: tr[0] = sum W_ij K_ij, tr[1]/tr[2] the same weighted by the squared
+// scaled time / wavelength differences), trd = sum_i W_ii  (W = alpha alpha^T - K^-1).
+template <class Ctx, class Kern>
+GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, double (&tr)[Kern::NTR], double& trd) {
   const int T = s.T, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const double* A = s.A;
   const GpFrag f = gp_frag(c.lane);
   const double* bord = A + gp_tile(T, 0);
   const int ob_g = gp_el(0, g), ob_0 = gp_el(0, 2 * t), ob_1 = gp_el(0, 2 * t + 1);
-  tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
+#pragma unroll
+  for (int k = 0; k < Kern::NTR; ++k) tr[k] = 0.0;
+  trd = 0.0;
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
@@ -529,66 +643,68 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, double cst, double
     const GpPair uj = *reinterpret_cast<const GpPair*>(s.u + j), vj = *reinterpret_cast<const GpPair*>(s.v + j);   // j is even
     const double du0 = ui - uj.x, dv0 = vi - vj.x, du1 = ui - uj.y, dv1 = vi - vj.y;
     const double du0s = du0 * du0, dv0s = dv0 * dv0, du1s = du1 * du1, dv1s = dv1 * dv1;
-    const double k0 = cst * gp_exp_neg(-0.5 * (du0s + dv0s)), k1 = cst * gp_exp_neg(-0.5 * (du1s + dv1s));   // K_ij again (not stored)
-    // strictly-lower entries inside the curve count; on a diagonal tile the diagonal feeds tr[3]
+    // strictly-lower entries inside the curve count (K_ij and its derivatives are recomputed, not stored); on a diagonal tile
+    // the diagonal feeds trd
     const bool in = i < n;
-    const double wk0 = (in && i > j) ? w0 * k0 : 0.0, wk1 = (in && i > j + 1) ? w1 * k1 : 0.0;
-    tr[0] += wk0 + wk1;
-    tr[1] += wk0 * du0s + wk1 * du1s;
-    tr[2] += wk0 * dv0s + wk1 * dv1s;
-    if (I == J) tr[3] += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
+    kn.accumulate((in && i > j) ? w0 : 0.0, du0s, dv0s, tr);
+    kn.accumulate((in && i > j + 1) ? w1 : 0.0, du1s, dv1s, tr);
+    if (I == J) trd += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
     J += c.nwarp;
     while (J > I) { J -= I + 1; ++I; }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- one LML + gradient evaluation
-// theta = log[c, l_t, l_lambda, s2].  Result valid in every thread.  ok=false <=> K not positive definite.
-template <class Ctx>
-GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta, const GpSmem& s, double& lml, double grad[4], bool& ok) {
-  const double cst = exp(theta[0]), lt = exp(theta[1]), ll = exp(theta[2]), s2 = exp(theta[3]);
+// theta = the family's log hyperparameters (default: log[c, l_t, l_lambda, s2]).  Result valid in every thread.
+// ok=false <=> K not positive definite.  grad has Kern::P entries.
+template <class Kern, class Ctx>
+GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta, const GpSmem& s, double& lml, double* grad, bool& ok) {
+  Kern kn;
+  kn.init(theta);
   c.mark(0);
-  gp_load_curve(c, cv, s, lt, ll);
+  gp_load_curve(c, cv, s, kn.lt, kn.ll);
   c.sync();
   c.mark(1);
-  gp_assemble(c, cv, s, cst, s2);
+  gp_assemble(c, cv, s, kn);
   c.sync();
   c.mark(2);
-  double v[6];
-  gp_cholesky(c, s, v[5]);
+  constexpr int NT = Kern::NTR;
+  double v[NT + 3];   // traces, trd, quadratic form, log-determinant
+  gp_cholesky(c, s, v[NT + 2]);
   c.mark(3);
   ok = (s.flag[0] == 0);
   if (!ok) {
     lml = -INFINITY;
-    grad[0] = grad[1] = grad[2] = grad[3] = 0.0;
+    for (int k = 0; k < Kern::P; ++k) grad[k] = 0.0;
     c.sync();
     return;
   }
-  v[4] = gp_collect(c, s);   // the border row is next written after the inverse's first barrier
+  v[NT + 1] = gp_collect(c, s);   // the border row is next written after the inverse's first barrier
   c.mark(4);
   gp_trtri(c, s);
   c.mark(5);
   c.mark(6);
-  gp_inverse_traces(c, s, cv.n, cst, v);
+  {
+    double tr[NT];
+    gp_inverse_traces(c, s, cv.n, kn, tr, v[NT]);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) v[k] = tr[k];
+  }
   c.mark(7);
   gp_block_sum(c, v, s.red);
   c.mark(8);
-  lml = -0.5 * v[4] - v[5] - 0.5 * (double)cv.n * GP_LOG_2PI;
-  grad[0] = v[0] + 0.5 * cst * v[3];
-  grad[1] = v[1];
-  grad[2] = v[2];
-  grad[3] = 0.5 * s2 * v[3];
+  lml = -0.5 * v[NT + 1] - v[NT + 2] - 0.5 * (double)cv.n * GP_LOG_2PI;
+  kn.gradient(v, v[NT], grad);
 }
 
 // ---------------------------------------------------------------------------------------------- factor for prediction
 // L_ = chol(K(theta)) and z = L^-1 y (_gpr.py:349-367; alpha_ = L^-T z is never needed: mean* = v.z with v = L^-1 k*).
 // Returns LML as a by-product.
-template <class Ctx>
-GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const double* theta, const GpSmem& s, double& lml, bool& ok) {
-  const double cst = exp(theta[0]), lt = exp(theta[1]), ll = exp(theta[2]), s2 = exp(theta[3]);
-  gp_load_curve(c, cv, s, lt, ll);
+template <class Ctx, class Kern>
+GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const Kern& kn, const GpSmem& s, double& lml, bool& ok) {
+  gp_load_curve(c, cv, s, kn.lt, kn.ll);
   c.sync();
-  gp_assemble(c, cv, s, cst, s2);
+  gp_assemble(c, cv, s, kn);
   c.sync();
   double v[2];
   gp_cholesky(c, s, v[1]);
@@ -610,7 +726,8 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const double* theta, const 
 // with X_II = L_II^-1 from gp_cholesky (explicit inverses only of the 8x8 diagonal blocks; between blocks it is substitution).
 #define GP_QC 128   // query columns per pass (= threads that own a column)
 
-GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, double vq, double* V, int ldv, double& mean, double& v2) {
+template <class Kern>
+GP_DEV void gp_predict_column(const GpSmem& s, int n, const Kern& kn, double uq, double vq, double* V, int ldv, double& mean, double& v2) {
   const double* A = s.A;
   const double* bord = A + gp_tile(s.T, 0);
   double m = 0.0, q2 = 0.0;
@@ -619,7 +736,8 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, double cst, double uq, dou
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = 8 * I + r;
-      acc[r] = (i < n) ? gp_kernel_value(cst, uq, vq, s.u[i], s.v[i]) : 0.0;
+      const double du = uq - s.u[i], dv = vq - s.v[i];
+      acc[r] = (i < n) ? kn.value(du * du, dv * dv) : 0.0;
     }
     const double* row = A + gp_tile(I, 0);
     double* vp = V;
@@ -732,17 +850,19 @@ GP_DEV double gp_linspace(double t_min, double t_max, int n_obs, int k) {
 // mean/std [m] of one curve at hyperparameters theta.  stats = per-curve (t mean, t scale, ., ., flux mean, flux std).
 // V: scratch of gp_pad(n) * GP_QC doubles (column q of thread q).  Threads >= GP_QC only help with the factorisation.
 // Returns status bits (valid in all threads): 2 = not PD, 16 = a negative variance was clamped.
-template <class Ctx>
+template <class Kern, class Ctx>
 GP_DEV int gp_predict_curve(Ctx& c, const GpCurveView& cv, const double* theta, const double* stats, const GpQuery& qd,
                             const GpSmem& s, double* V, double* mean, double* stdv, double& lml) {
   bool ok;
-  gp_factor(c, cv, theta, s, lml, ok);
+  Kern kn;
+  kn.init(theta);
+  gp_factor(c, cv, kn, s, lml, ok);
   if (!ok) {
     for (int q = c.tid; q < qd.m; q += c.nthr) { mean[q] = NAN; stdv[q] = NAN; }
     return 2;
   }
-  const double cst = exp(theta[0]), lt = exp(theta[1]), ll = exp(theta[2]), s2 = exp(theta[3]);
-  const double kss = cst + s2;                       // kernel_.diag(X*) (kernels.py:490,1315-1319,1438-1440)
+  const double lt = kn.lt, ll = kn.ll;
+  const double kss = kn.diag();                      // kernel_.diag(X*) (kernels.py:490,1315-1319,1438-1440)
   const double ymean = stats[4], ystd = stats[5];
   double neg[1] = {0.0};
   const int ncol = c.nthr < GP_QC ? c.nthr : GP_QC;
@@ -754,7 +874,7 @@ GP_DEV int gp_predict_curve(Ctx& c, const GpCurveView& cv, const double* theta, 
       const double uq = ((tq - stats[0]) / stats[1]) / lt;   // ss.transform then X / length_scale
       const double vq = cv.lam[bq] / ll;
       double m, v2;
-      gp_predict_column(s, cv.n, cst, uq, vq, V + c.tid, GP_QC, m, v2);
+      gp_predict_column(s, cv.n, kn, uq, vq, V + c.tid, GP_QC, m, v2);
       double var = kss - v2;
       if (var < 0.0) { var = 0.0; neg[0] = 1.0; }      // _gpr.py:485-491
       mean[q] = ystd * m + ymean;                      // _gpr.py:450

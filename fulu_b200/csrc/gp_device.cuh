@@ -1,0 +1,273 @@
+// Device-side pieces shared by the per-family translation units (gp_family.cu, one per covariance family) and the C ABI
+// (gp_kernels.cu): the CUDA block context, the curve table, the optimiser-window descriptor, and the three kernels whose code
+// depends on the covariance family - fixed-theta LML, the evaluation kernel of the fit, and prediction.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/fulu_gp.h"
+#include "gp_block.cuh"
+#include "lbfgsb.cuh"
+
+namespace {
+
+struct DevCtx {
+  int tid, nthr, lane, warp, nwarp;
+  long long* marks;   // optional phase timestamps (fulu_gp_debug_phase_cycles); null in production launches
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so loops and branches on it stay convergent and
+  // the mma.sync sites need no WARPSYNC / collective wrappers
+  __device__ __forceinline__ DevCtx() : tid((int)threadIdx.x), nthr((int)blockDim.x), lane((int)threadIdx.x & 31),
+                                        warp(__shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0)), nwarp(((int)blockDim.x + 31) >> 5),
+                                        marks(nullptr) {}
+  __device__ __forceinline__ void mark(int id) {
+    if (marks != nullptr && tid == 0) marks[id] = clock64();
+  }
+  __device__ __forceinline__ long long clock() { return marks != nullptr ? clock64() : 0; }
+  __device__ __forceinline__ void mark_value(int id, long long v) {
+    if (marks != nullptr && tid == 0) marks[id] = v;
+  }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void warp_sync() { __syncwarp(); }
+  // FP64 tensor-core tile: C(8x8) += A(8x4, row) * B(4x8, col); lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
+  __device__ __forceinline__ void mma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  }
+  __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+};
+
+// Threads per SM given to the evaluation kernel, split evenly between the resident CTAs; it also fixes the register budget
+// (65536 / threads).  Measured on B200 at N = 100 (4 CTAs per SM), 10,000 curves: 1024 threads (64 registers) 229 ms,
+// 768 (80) 213 ms, 640 (96) 206 ms, 512 (128) 203 ms, 384 (168) 216 ms, 256 (255) 255 ms per fit - with few registers the
+// compiler funnels the fragment loads of the DMMA loops through one register pair and serialises load -> DMMA -> load.
+#ifndef GP_EVAL_MAX_THREADS
+#define GP_EVAL_MAX_THREADS 512
+#endif
+constexpr int kEvalMaxThreads = GP_EVAL_MAX_THREADS;
+constexpr int kPredictThreads = 128;
+constexpr int kPrepThreads = 128;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+struct CurveTable {
+  const int64_t* offsets;
+  const double *xs, *y, *al, *lam, *stats;
+  const int32_t* band;
+  const int32_t* pstatus;
+  const int32_t* order;   // optional processing order (curve ids); null = identity
+  int64_t n_active;       // curves this call processes
+  int n_bands;
+};
+
+__device__ __forceinline__ int64_t curve_of(const CurveTable& t, int64_t k) { return t.order ? (int64_t)t.order[k] : k; }
+
+__device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t cu) {
+  const int64_t o = t.offsets[cu];
+  GpCurveView v;
+  v.n = (int)(t.offsets[cu + 1] - o);
+  v.xs = t.xs + o; v.band = t.band + o; v.y = t.y + o; v.al = t.al + o; v.lam = t.lam + cu * t.n_bands;
+  return v;
+}
+
+template <bool kGlobalA>
+__device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
+  if (!kGlobalA) {
+    return gp_carve(smem, smem + gp_mat_doubles(gp_pad(n)), n);
+  }
+  // vectors in shared memory, the matrix in this CTA's global slab (stays in L2)
+  return gp_carve(gA + (size_t)blockIdx.x * gA_stride, smem, n);
+}
+
+// LML + gradient at one theta per curve (fixed-theta parity entry point)
+template <class Kern, bool kGlobalA>
+__global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
+                                                            double* gA, size_t gA_stride, long long* marks) {
+  extern __shared__ __align__(16) double smem[];
+  DevCtx c;
+  if (blockIdx.x == 0) c.marks = marks;
+  for (int64_t kk = blockIdx.x; kk < B; kk += gridDim.x) {
+    const int64_t cu = curve_of(tab, kk);
+    if (tab.pstatus[cu] != 0) {
+      if (threadIdx.x == 0) { lml[cu] = NAN; for (int k = 0; k < P; ++k) grad[cu * P + k] = NAN; }
+      continue;
+    }
+    GpCurveView cv = curve_view(tab, cu);
+    GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
+    double l, g[Kern::P];
+    bool ok;
+    gp_eval_lml_grad<Kern>(c, cv, theta + cu * P, s, l, g, ok);
+    if (threadIdx.x == 0) { lml[cu] = l; for (int k = 0; k < Kern::P; ++k) grad[cu * P + k] = g[k]; }
+    __syncthreads();
+  }
+}
+
+struct FitDev {
+  CurveTable tab;
+  FgOptions opt;
+  int64_t n_tasks;
+  int S, P, window;
+  FgState* slots;
+  int64_t* slot_task;
+  int32_t* slot_nev;
+  double *f_out, *g_out;
+  int32_t* list;     // [2][window]
+  int32_t* counts;   // [max_rounds + 2]
+  unsigned long long* next_task;
+  double *run_f, *run_x;
+  int32_t *run_nev, *run_end;
+  const double* starts;   // [S, P], or [B, S, P] by curve id when starts_per_curve
+  bool starts_per_curve;
+  double* gA;
+  size_t gA_stride;
+};
+
+template <class Kern, bool kGlobalA>
+__global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
+  extern __shared__ __align__(16) double smem[];
+  DevCtx c;
+  const int count = d.counts[round];
+  const int32_t* list = d.list + (size_t)(round & 1) * d.window;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int slot = list[i];
+    const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
+    GpCurveView cv = curve_view(d.tab, cu);
+    GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
+    double l, g[Kern::P];
+    bool ok;
+    gp_eval_lml_grad<Kern>(c, cv, d.slots[slot].x, s, l, g, ok);
+    if (threadIdx.x == 0) {
+      d.f_out[slot] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
+      for (int k = 0; k < Kern::P; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
+    }
+    __syncthreads();
+  }
+}
+
+struct PredictArgs {
+  CurveTable tab;
+  int64_t B;
+  int P;
+  const double* theta;
+  int n_obs;                  // grid mode if > 0
+  const double *t_min, *t_max;
+  const double* t_raw;        // raw times (for default t_min/t_max)
+  const int64_t* q_offsets;   // explicit mode
+  const double* q_t;
+  const int32_t* q_band;
+  double *mean, *stdv, *lml;
+  int32_t* status;
+  double *gA, *gV;
+  size_t gA_stride, gV_stride;
+};
+
+template <class Kern, bool kGlobalA>
+__global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double tlim[2];
+  DevCtx c;
+  double* V = a.gV + (size_t)blockIdx.x * a.gV_stride;
+  for (int64_t kk = blockIdx.x; kk < a.B; kk += gridDim.x) {
+    const int64_t cu = curve_of(a.tab, kk);
+    GpCurveView cv = curve_view(a.tab, cu);
+    GpQuery qd;
+    int64_t out0;
+    if (a.n_obs > 0) {
+      qd.n_obs = a.n_obs; qd.m = a.n_obs * a.tab.n_bands; qd.qt = nullptr; qd.qband = nullptr;
+      out0 = cu * (int64_t)qd.m;
+      if (a.t_min && a.t_max) { qd.t_min = a.t_min[cu]; qd.t_max = a.t_max[cu]; }
+      else {
+        // default: the curve's own time span
+        if (threadIdx.x == 0) {
+          const double* tr = a.t_raw + a.tab.offsets[cu];
+          double lo = tr[0], hi = tr[0];
+          for (int i = 1; i < cv.n; ++i) { lo = fmin(lo, tr[i]); hi = fmax(hi, tr[i]); }
+          tlim[0] = lo; tlim[1] = hi;
+        }
+        __syncthreads();
+        qd.t_min = tlim[0]; qd.t_max = tlim[1];
+      }
+    } else {
+      out0 = a.q_offsets[cu];
+      qd.n_obs = 0; qd.m = (int)(a.q_offsets[cu + 1] - out0); qd.qt = a.q_t + out0; qd.qband = a.q_band + out0;
+      qd.t_min = qd.t_max = 0.0;
+    }
+    int st = a.tab.pstatus[cu] != 0 ? FULU_GP_STATUS_BAD_INPUT : 0;
+    double l = NAN;
+    if (st) {
+      for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }
+    } else {
+      GpSmem s = carve<kGlobalA>(smem, a.gA, a.gA_stride, cv.n);
+      st = gp_predict_curve<Kern>(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, s, V, a.mean + out0, a.stdv + out0, l);
+    }
+    if (threadIdx.x == 0) {
+      if (a.status) a.status[cu] = st;
+      if (a.lml) a.lml[cu] = l;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ per-family launchers
+// What gp_kernels.cu needs from a family: its parameter count and three launch functions (return a cudaError_t as int).
+struct GpFamilyOps {
+  int n_params;
+  int (*lml)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P, const double* theta,
+             double* lml, double* grad, double* gA, size_t gA_stride, long long* marks);
+  int (*eval_prepare)(bool globalA, size_t smem);
+  int (*eval)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
+  int (*predict)(bool globalA, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a);
+};
+
+template <class K>
+inline int gp_set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return 0;
+}
+
+template <class Kern>
+struct GpFamilyLaunch {
+  static int lml(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P,
+                 const double* theta, double* lml, double* grad, double* gA, size_t gA_stride, long long* marks) {
+    int rc;
+    if (globalA) {
+      if ((rc = gp_set_smem(lml_kernel<Kern, true>, smem))) return rc;
+      lml_kernel<Kern, true><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
+    } else {
+      if ((rc = gp_set_smem(lml_kernel<Kern, false>, smem))) return rc;
+      lml_kernel<Kern, false><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, nullptr, 0, marks);
+    }
+    return (int)cudaGetLastError();
+  }
+  static int eval_prepare(bool globalA, size_t smem) {
+    return globalA ? gp_set_smem(fit_eval_kernel<Kern, true>, smem) : gp_set_smem(fit_eval_kernel<Kern, false>, smem);
+  }
+  static int eval(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
+    if (globalA) fit_eval_kernel<Kern, true><<<grid, threads, smem, st>>>(d, round);
+    else fit_eval_kernel<Kern, false><<<grid, threads, smem, st>>>(d, round);
+    return 0;
+  }
+  static int predict(bool globalA, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a) {
+    int rc;
+    if (globalA) {
+      if ((rc = gp_set_smem(predict_kernel<Kern, true>, smem))) return rc;
+      predict_kernel<Kern, true><<<grid, kPredictThreads, smem, st>>>(a);
+    } else {
+      if ((rc = gp_set_smem(predict_kernel<Kern, false>, smem))) return rc;
+      predict_kernel<Kern, false><<<grid, kPredictThreads, smem, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+  }
+  static const GpFamilyOps* ops() {
+    static const GpFamilyOps o = {Kern::P, &lml, &eval_prepare, &eval, &predict};
+    return &o;
+  }
+};
+
+}  // namespace
+
+// the compiled families: one translation unit each (gp_family.cu with -DGP_FAM_F1= -DGP_FAM_EX=)
+#define GP_FAMILY_LIST(X) X(0, 0) X(0, 2) X(2, 2) X(0, 4) X(0, 1) X(0, 3) X(2, 0)
+#define GP_FAMILY_SYMBOL_(f1, ex) gp_family_ops_##f1##_##ex
+#define GP_FAMILY_SYMBOL(f1, ex) GP_FAMILY_SYMBOL_(f1, ex)
+#define GP_FAMILY_DECL(f1, ex) const GpFamilyOps* GP_FAMILY_SYMBOL(f1, ex)();
+GP_FAMILY_LIST(GP_FAMILY_DECL)

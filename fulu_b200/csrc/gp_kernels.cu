@@ -10,55 +10,13 @@
 //   select kernel    best of the S runs per curve                                                    (a6)
 //   predict kernel   one CTA per curve: final factorisation + augmentation grid / query points       (a7-a9)
 // There is no collective anywhere: curves are independent, multi-GPU runs shard the batch.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdint.h>
 #include <stdio.h>
 
 #include <vector>
 
-#include "../../include/fulu_gp.h"
-#include "gp_block.cuh"
-#include "lbfgsb.cuh"
+#include "gp_device.cuh"
 
 namespace {
-
-struct DevCtx {
-  int tid, nthr, lane, warp, nwarp;
-  long long* marks;   // optional phase timestamps (fulu_gp_debug_phase_cycles); null in production launches
-  // warp index through a shuffle: the compiler then knows it is warp-uniform, so loops and branches on it stay convergent and
-  // the mma.sync sites need no WARPSYNC / collective wrappers
-  __device__ __forceinline__ DevCtx() : tid((int)threadIdx.x), nthr((int)blockDim.x), lane((int)threadIdx.x & 31),
-                                        warp(__shfl_sync(0xffffffffu, (int)threadIdx.x >> 5, 0)), nwarp(((int)blockDim.x + 31) >> 5),
-                                        marks(nullptr) {}
-  __device__ __forceinline__ void mark(int id) {
-    if (marks != nullptr && tid == 0) marks[id] = clock64();
-  }
-  __device__ __forceinline__ long long clock() { return marks != nullptr ? clock64() : 0; }
-  __device__ __forceinline__ void mark_value(int id, long long v) {
-    if (marks != nullptr && tid == 0) marks[id] = v;
-  }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
-  __device__ __forceinline__ void warp_sync() { __syncwarp(); }
-  // FP64 tensor-core tile: C(8x8) += A(8x4, row) * B(4x8, col); lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
-  __device__ __forceinline__ void mma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-  }
-  __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-  __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-};
-
-// Threads per SM given to the evaluation kernel, split evenly between the resident CTAs; it also fixes the register budget
-// (65536 / threads).  Measured on B200 at N = 100 (4 CTAs per SM), 10,000 curves: 1024 threads (64 registers) 229 ms,
-// 768 (80) 213 ms, 640 (96) 206 ms, 512 (128) 203 ms, 384 (168) 216 ms, 256 (255) 255 ms per fit - with few registers the
-// compiler funnels the fragment loads of the DMMA loops through one register pair and serialises load -> DMMA -> load.
-#ifndef GP_EVAL_MAX_THREADS
-#define GP_EVAL_MAX_THREADS 512
-#endif
-constexpr int kEvalMaxThreads = GP_EVAL_MAX_THREADS;
-constexpr int kPredictThreads = 128;
-constexpr int kPrepThreads = 128;
-constexpr size_t kMaxSmem = 227 * 1024;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -175,77 +133,6 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
   }
 }
 
-struct CurveTable {
-  const int64_t* offsets;
-  const double *xs, *y, *al, *lam, *stats;
-  const int32_t* band;
-  const int32_t* pstatus;
-  const int32_t* order;   // optional processing order (curve ids); null = identity
-  int64_t n_active;       // curves this call processes
-  int n_bands;
-};
-
-__device__ __forceinline__ int64_t curve_of(const CurveTable& t, int64_t k) { return t.order ? (int64_t)t.order[k] : k; }
-
-__device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t cu) {
-  const int64_t o = t.offsets[cu];
-  GpCurveView v;
-  v.n = (int)(t.offsets[cu + 1] - o);
-  v.xs = t.xs + o; v.band = t.band + o; v.y = t.y + o; v.al = t.al + o; v.lam = t.lam + cu * t.n_bands;
-  return v;
-}
-
-template <bool kGlobalA>
-__device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
-  if (!kGlobalA) {
-    return gp_carve(smem, smem + gp_mat_doubles(gp_pad(n)), n);
-  }
-  // vectors in shared memory, the matrix in this CTA's global slab (stays in L2)
-  return gp_carve(gA + (size_t)blockIdx.x * gA_stride, smem, n);
-}
-
-// LML + gradient at one theta per curve (fixed-theta parity entry point)
-template <bool kGlobalA>
-__global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
-                                                            double* gA, size_t gA_stride, long long* marks) {
-  extern __shared__ __align__(16) double smem[];
-  DevCtx c;
-  if (blockIdx.x == 0) c.marks = marks;
-  for (int64_t kk = blockIdx.x; kk < B; kk += gridDim.x) {
-    const int64_t cu = curve_of(tab, kk);
-    if (tab.pstatus[cu] != 0) {
-      if (threadIdx.x == 0) { lml[cu] = NAN; for (int k = 0; k < P; ++k) grad[cu * P + k] = NAN; }
-      continue;
-    }
-    GpCurveView cv = curve_view(tab, cu);
-    GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
-    double l, g[4];
-    bool ok;
-    gp_eval_lml_grad(c, cv, theta + cu * P, s, l, g, ok);
-    if (threadIdx.x == 0) { lml[cu] = l; for (int k = 0; k < 4; ++k) grad[cu * P + k] = g[k]; }
-    __syncthreads();
-  }
-}
-
-struct FitDev {
-  CurveTable tab;
-  FgOptions opt;
-  int64_t n_tasks;
-  int S, P, window;
-  FgState* slots;
-  int64_t* slot_task;
-  int32_t* slot_nev;
-  double *f_out, *g_out;
-  int32_t* list;     // [2][window]
-  int32_t* counts;   // [max_rounds + 2]
-  unsigned long long* next_task;
-  double *run_f, *run_x;
-  int32_t *run_nev, *run_end;
-  const double* starts;
-  double* gA;
-  size_t gA_stride;
-};
-
 // pulls the next runnable task into `slot` (whose optimiser state is `state`); returns false when the queue is empty
 __device__ bool acquire_task(const FitDev& d, int slot, FgState& state) {
   for (;;) {
@@ -253,14 +140,16 @@ __device__ bool acquire_task(const FitDev& d, int slot, FgState& state) {
     if (nt >= (unsigned long long)d.n_tasks) { d.slot_task[slot] = -1; state.task = FG_TASK_IDLE; return false; }
     const int64_t cu = curve_of(d.tab, (int64_t)(nt / d.S));
     const int st = (int)(nt % d.S);
+    // start points: [S, P] shared by all curves, or [B, S, P] by curve id
+    const double* x0 = d.starts + ((d.starts_per_curve ? cu * d.S : 0) + st) * d.P;
     if (d.tab.pstatus[cu] != 0) {   // unusable curve: record and move on
       d.run_f[nt] = INFINITY;
-      for (int k = 0; k < d.P; ++k) d.run_x[nt * FG_MAXP + k] = d.starts[st * FG_MAXP + k];
+      for (int k = 0; k < d.P; ++k) d.run_x[nt * FG_MAXP + k] = x0[k];
       d.run_nev[nt] = 0;
       d.run_end[nt] = FG_TASK_ABNORMAL;
       continue;
     }
-    lbfgsb_init(state, d.opt, d.starts + st * FG_MAXP);
+    lbfgsb_init(state, d.opt, x0);
     d.slot_task[slot] = (int64_t)nt;
     d.slot_nev[slot] = 0;
     return true;
@@ -273,28 +162,6 @@ __global__ void fit_init_kernel(FitDev d) {
   if (acquire_task(d, slot, d.slots[slot])) {
     const int pos = atomicAdd(&d.counts[0], 1);
     d.list[pos] = slot;
-  }
-}
-
-template <bool kGlobalA>
-__global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
-  extern __shared__ __align__(16) double smem[];
-  DevCtx c;
-  const int count = d.counts[round];
-  const int32_t* list = d.list + (size_t)(round & 1) * d.window;
-  for (int i = blockIdx.x; i < count; i += gridDim.x) {
-    const int slot = list[i];
-    const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
-    GpCurveView cv = curve_view(d.tab, cu);
-    GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
-    double l, g[4];
-    bool ok;
-    gp_eval_lml_grad(c, cv, d.slots[slot].x, s, l, g, ok);
-    if (threadIdx.x == 0) {
-      d.f_out[slot] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
-      for (int k = 0; k < 4; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
-    }
-    __syncthreads();
   }
 }
 
@@ -376,70 +243,6 @@ __global__ void fit_select_kernel(SelectArgs a) {
   a.status[cu] = st;
 }
 
-struct PredictArgs {
-  CurveTable tab;
-  int64_t B;
-  int P;
-  const double* theta;
-  int n_obs;                  // grid mode if > 0
-  const double *t_min, *t_max;
-  const double* t_raw;        // raw times (for default t_min/t_max)
-  const int64_t* q_offsets;   // explicit mode
-  const double* q_t;
-  const int32_t* q_band;
-  double *mean, *stdv, *lml;
-  int32_t* status;
-  double *gA, *gV;
-  size_t gA_stride, gV_stride;
-};
-
-template <bool kGlobalA>
-__global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ double tlim[2];
-  DevCtx c;
-  double* V = a.gV + (size_t)blockIdx.x * a.gV_stride;
-  for (int64_t kk = blockIdx.x; kk < a.B; kk += gridDim.x) {
-    const int64_t cu = curve_of(a.tab, kk);
-    GpCurveView cv = curve_view(a.tab, cu);
-    GpQuery qd;
-    int64_t out0;
-    if (a.n_obs > 0) {
-      qd.n_obs = a.n_obs; qd.m = a.n_obs * a.tab.n_bands; qd.qt = nullptr; qd.qband = nullptr;
-      out0 = cu * (int64_t)qd.m;
-      if (a.t_min && a.t_max) { qd.t_min = a.t_min[cu]; qd.t_max = a.t_max[cu]; }
-      else {
-        // default: the curve's own time span
-        if (threadIdx.x == 0) {
-          const double* tr = a.t_raw + a.tab.offsets[cu];
-          double lo = tr[0], hi = tr[0];
-          for (int i = 1; i < cv.n; ++i) { lo = fmin(lo, tr[i]); hi = fmax(hi, tr[i]); }
-          tlim[0] = lo; tlim[1] = hi;
-        }
-        __syncthreads();
-        qd.t_min = tlim[0]; qd.t_max = tlim[1];
-      }
-    } else {
-      out0 = a.q_offsets[cu];
-      qd.n_obs = 0; qd.m = (int)(a.q_offsets[cu + 1] - out0); qd.qt = a.q_t + out0; qd.qband = a.q_band + out0;
-      qd.t_min = qd.t_max = 0.0;
-    }
-    int st = a.tab.pstatus[cu] != 0 ? FULU_GP_STATUS_BAD_INPUT : 0;
-    double l = NAN;
-    if (st) {
-      for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }
-    } else {
-      GpSmem s = carve<kGlobalA>(smem, a.gA, a.gA_stride, cv.n);
-      st = gp_predict_curve(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, s, V, a.mean + out0, a.stdv + out0, l);
-    }
-    if (threadIdx.x == 0) {
-      if (a.status) a.status[cu] = st;
-      if (a.lml) a.lml[cu] = l;
-    }
-    __syncthreads();
-  }
-}
-
 __global__ void export_stats_kernel(int64_t B, const int32_t* order, const double* stats, double* scaler, double* ynorm) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= B) return;
@@ -484,12 +287,24 @@ __global__ void __launch_bounds__(256) dmma_probe(double* out, int iters, double
     if (e__ != cudaSuccess) return (int)e__; \
   } while (0)
 
+// the compiled covariance families (gp_family.cu, one translation unit each)
+const GpFamilyOps* family_ops(int kernel) {
+  switch (kernel) {
+#define GP_FAMILY_CASE(f1, ex) \
+  case FULU_GP_KERNEL(f1, ex): return GP_FAMILY_SYMBOL(f1, ex)();
+    GP_FAMILY_LIST(GP_FAMILY_CASE)
+#undef GP_FAMILY_CASE
+    default: return nullptr;
+  }
+}
+
 int check_batch(const fulu_gp_batch* b, int P) {
   if (!b) return FULU_GP_E_BADARG;
   if (b->n_curves < 0 || b->n_obs_total < 0 || b->n_bands < 1 || b->n_bands > FULU_GP_MAX_BANDS) return FULU_GP_E_BADARG;
   if (b->n_curves > 0 && (!b->offsets || !b->t || !b->flux || !b->flux_err || !b->band || !b->loglam)) return FULU_GP_E_BADARG;
-  if (b->kernel != FULU_GP_KERNEL_RBF_WHITE) return FULU_GP_E_UNSUPPORTED;
-  if (P != 4) return FULU_GP_E_UNSUPPORTED;
+  const GpFamilyOps* ops = family_ops(b->kernel);
+  if (!ops) return FULU_GP_E_UNSUPPORTED;
+  if (P != ops->n_params) return FULU_GP_E_BADARG;
   if (b->n_max < 1 && b->n_curves > 0) return FULU_GP_E_BADARG;
   if (b->order && (b->n_order < 0 || b->n_order > b->n_curves)) return FULU_GP_E_BADARG;
   return 0;
@@ -508,12 +323,6 @@ int run_prep(const fulu_gp_batch& b, const WsLayout& w, void* ws, int sms, cudaS
   CU_TRY(cudaGetLastError());
   tab.offsets = b.offsets; tab.xs = a.xs; tab.y = a.y; tab.al = a.al; tab.lam = a.lam; tab.stats = a.stats; tab.band = b.band;
   tab.pstatus = a.pstatus; tab.n_bands = b.n_bands; tab.order = b.order; tab.n_active = a.B;
-  return 0;
-}
-
-template <class K>
-int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
 
@@ -577,16 +386,9 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
   if (rc) return rc;
   const int64_t B = n_active(*batch);
   unsigned grid = (unsigned)(B < w.grid_eval ? B : w.grid_eval);
-  if (w.globalA) {
-    rc = set_smem(lml_kernel<true>, w.smem_eval);
-    if (rc) return rc;
-    lml_kernel<true><<<grid, w.threads_eval, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, at<double>(workspace, w.gA), w.gA_stride, marks);
-  } else {
-    rc = set_smem(lml_kernel<false>, w.smem_eval);
-    if (rc) return rc;
-    lml_kernel<false><<<grid, w.threads_eval, w.smem_eval, st>>>(tab, B, n_params, theta, lml, grad, nullptr, 0, marks);
-  }
-  CU_TRY(cudaGetLastError());
+  rc = family_ops(batch->kernel)->lml(w.globalA, grid, w.threads_eval, w.smem_eval, st, tab, B, n_params, theta, lml, grad,
+                                      at<double>(workspace, w.gA), w.gA_stride, marks);
+  if (rc) return rc;
   const unsigned g1 = (unsigned)((B + 255) / 256);
   if (scaler || ynorm) export_stats_kernel<<<g1, 256, 0, st>>>(B, tab.order, tab.stats, scaler, ynorm);
   if (status) copy_status_kernel<<<g1, 256, 0, st>>>(B, tab.order, tab.pstatus, status);
@@ -633,20 +435,17 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   d.run_x = at<double>(workspace, w.run_x);
   d.run_nev = at<int32_t>(workspace, w.run_nev);
   d.run_end = at<int32_t>(workspace, w.run_end);
-  double* starts = at<double>(workspace, w.starts);
-  d.starts = starts;
+  d.starts = theta_starts;
+  d.starts_per_curve = opt->starts_per_curve != 0;
   d.gA = at<double>(workspace, w.gA);
   d.gA_stride = w.gA_stride;
 
-  // starts [S,P] -> padded [S,FG_MAXP] (device-to-device strided copy)
-  CU_TRY(cudaMemsetAsync(starts, 0, (size_t)S * FG_MAXP * 8, st));
-  CU_TRY(cudaMemcpy2DAsync(starts, FG_MAXP * 8, theta_starts, (size_t)P * 8, (size_t)P * 8, S, cudaMemcpyDeviceToDevice, st));
   CU_TRY(cudaMemsetAsync(d.counts, 0, ((size_t)w.max_rounds + 2) * 4, st));
   CU_TRY(cudaMemsetAsync(d.next_task, 0, 8, st));
   fit_init_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
   CU_TRY(cudaGetLastError());
-  if (w.globalA) rc = set_smem(fit_eval_kernel<true>, w.smem_eval);
-  else rc = set_smem(fit_eval_kernel<false>, w.smem_eval);
+  const GpFamilyOps* ops = family_ops(batch->kernel);
+  rc = ops->eval_prepare(w.globalA, w.smem_eval);
   if (rc) return rc;
 
   const unsigned step_grid = (unsigned)((w.window + 127) / 128);
@@ -663,8 +462,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
         for (int i = 0; i < 3; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); ev.push_back(e); }
         cudaEventRecord(ev[3 * round], st);
       }
-      if (w.globalA) fit_eval_kernel<true><<<w.grid_eval, w.threads_eval, w.smem_eval, st>>>(d, round);
-      else fit_eval_kernel<false><<<w.grid_eval, w.threads_eval, w.smem_eval, st>>>(d, round);
+      ops->eval(w.globalA, w.grid_eval, w.threads_eval, w.smem_eval, st, d, round);
       if (prof) cudaEventRecord(ev[3 * round + 1], st);
       fit_step_kernel<<<step_grid, 128, 0, st>>>(d, round);
       if (prof) cudaEventRecord(ev[3 * round + 2], st);
@@ -722,17 +520,7 @@ static int predict_common(const fulu_gp_batch* batch, int32_t n_params, PredictA
   a.gA = at<double>(workspace, w.gA); a.gV = at<double>(workspace, w.gV);
   a.gA_stride = w.gA_stride; a.gV_stride = w.gV_stride;
   unsigned grid = (unsigned)(a.B < w.grid_predict ? a.B : w.grid_predict);
-  if (w.globalA) {
-    rc = set_smem(predict_kernel<true>, w.smem_predict);
-    if (rc) return rc;
-    predict_kernel<true><<<grid, kPredictThreads, w.smem_predict, st>>>(a);
-  } else {
-    rc = set_smem(predict_kernel<false>, w.smem_predict);
-    if (rc) return rc;
-    predict_kernel<false><<<grid, kPredictThreads, w.smem_predict, st>>>(a);
-  }
-  CU_TRY(cudaGetLastError());
-  return 0;
+  return family_ops(batch->kernel)->predict(w.globalA, grid, w.smem_predict, st, a);
 }
 
 int fulu_gp_predict_grid_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const double* t_min, const double* t_max,

@@ -16,14 +16,38 @@ from . import _capi
 from .datasets import CurveBatch
 
 LOG_BOUND = math.log(1e5)  # sklearn's default (1e-5, 1e5) hyperparameter bounds, log space (kernels.py:1236,1366,1511)
-KERNEL_RBF_WHITE = 0
+
+# Covariance families (include/fulu_gp.h): K = c * [M1] * RBF([lt, ll]) + [EX] + White, code = f1 | ex << 4
+F_NONE, F_MAT05, F_MAT15, F_MAT25, F_RQ = 0, 1, 2, 3, 4
+
+
+def family_code(f1=F_NONE, ex=F_NONE):
+    return f1 | (ex << 4)
+
+
+KERNEL_RBF_WHITE = family_code()  # C * RBF([lt, ll]) + White                           (fulu/gp_aug.py:29 default)
+KERNEL_RBF_MATERN_WHITE = family_code(ex=F_MAT15)  # C * RBF + Matern() + White         (fulu/gp_aug.py:24, tests/test_aug.py:37)
+KERNEL_MATERN_RBF_MATERN_WHITE = family_code(F_MAT15, F_MAT15)  # C * Matern() * RBF + Matern() + White  (plotting.ipynb:33)
+KERNEL_RBF_RQ_WHITE = family_code(ex=F_RQ)  # C * RBF + RationalQuadratic() + White     (fulu/gp_aug.py:5)
+# families compiled into libfulu_gp (fulu_b200/build.py FAMILIES)
+COMPILED_FAMILIES = {family_code(*fe) for fe in ((0, 0), (0, 2), (2, 2), (0, 4), (0, 1), (0, 3), (2, 0))}
 
 STATUS_BAD_INPUT, STATUS_NOT_PD, STATUS_NOT_CONVERGED, STATUS_AT_BOUND, STATUS_NEG_VARIANCE = 1, 2, 4, 8, 16
 
 
+def family_n_params(family):
+    f1, ex = family & 15, family >> 4
+    return 4 + (1 if f1 else 0) + (2 if ex == F_RQ else 1 if ex else 0)
+
+
 @dataclass
 class KernelSpec:
-    """The covariance family and its optimiser configuration (what sklearn derives from the kernel object)."""
+    """The covariance family and its optimiser configuration (what sklearn derives from the kernel object).
+
+    theta0 / lower / upper are in the library's CANONICAL order [c, (l_1), lt, ll, (ex: l | alpha, l), s2]; `perm` maps it onto
+    the order sklearn uses for the kernel object the spec was built from: theta_canonical = theta_sklearn[perm] (identity for
+    kernels written as C*[Matern*]RBF + [Matern|RQ] + White).  The restart points are drawn in sklearn's order, as sklearn
+    draws them, and then permuted."""
 
     family: int = KERNEL_RBF_WHITE
     theta0: np.ndarray = None  # start 0 = the kernel's own hyperparameters (log)
@@ -31,50 +55,126 @@ class KernelSpec:
     upper: np.ndarray = None
     n_restarts: int = 5  # fulu/gp_aug.py:69
     seed: int = 42  # fulu/gp_aug.py:69 random_state
+    perm: np.ndarray = None
+    polish: int = None  # continuation runs from the best point (see GPEngine.fit); default 0 for the default family, 1 otherwise
 
     def __post_init__(self):
-        p = 4
+        if self.family not in COMPILED_FAMILIES:
+            raise NotImplementedError(f"kernel family {self.family} is not compiled into libfulu_gp")
+        p = family_n_params(self.family)
+        if self.polish is None:
+            self.polish = 0 if self.family == KERNEL_RBF_WHITE else 1
         if self.theta0 is None:
             self.theta0 = np.zeros(p)
         if self.lower is None:
             self.lower = np.full(p, -LOG_BOUND)
         if self.upper is None:
             self.upper = np.full(p, LOG_BOUND)
+        if self.perm is None:
+            self.perm = np.arange(p)
         self.theta0 = np.asarray(self.theta0, np.float64)
         self.lower = np.asarray(self.lower, np.float64)
         self.upper = np.asarray(self.upper, np.float64)
+        self.perm = np.asarray(self.perm, np.int64)
+        if not (len(self.theta0) == len(self.lower) == len(self.upper) == len(self.perm) == p):
+            raise ValueError(f"kernel family {self.family} has {p} hyperparameters")
 
     @property
     def n_params(self):
         return len(self.theta0)
 
+    def to_sklearn(self, theta):
+        """Canonical -> sklearn order along the last axis."""
+        theta = np.asarray(theta)
+        out = np.empty_like(theta)
+        out[..., self.perm] = theta
+        return out
+
+    def from_sklearn(self, theta):
+        """sklearn -> canonical order along the last axis."""
+        return np.asarray(theta)[..., self.perm]
+
     def start_points(self):
-        """theta0, then n_restarts draws of RandomState(seed).uniform(lower, upper) (_gpr.py:251,312-333)."""
+        """theta0, then n_restarts draws of RandomState(seed).uniform(lower, upper) in sklearn's hyperparameter order
+        (_gpr.py:251,312-333); returned in canonical order."""
         rng = np.random.RandomState(self.seed)
+        lo, hi = self.to_sklearn(self.lower), self.to_sklearn(self.upper)
         pts = [self.theta0.copy()]
         for _ in range(self.n_restarts):
-            pts.append(rng.uniform(self.lower, self.upper))
+            pts.append(self.from_sklearn(rng.uniform(lo, hi)))
         return np.ascontiguousarray(np.array(pts), np.float64)
 
 
+def _flatten(kernel, op):
+    """Leaves of a (left- or right-nested) Sum / Product tree, left to right."""
+    if type(kernel).__name__ == op:
+        return _flatten(kernel.k1, op) + _flatten(kernel.k2, op)
+    return [kernel]
+
+
 def kernel_spec_from_sklearn(kernel):
-    """Map an sklearn kernel object onto a supported family; anything else is refused (there is no CPU fallback)."""
+    """Map an sklearn kernel object onto a compiled family; anything else is refused (there is no CPU fallback).
+
+    Accepted: any ordering of  ConstantKernel * [Matern(nu in {0.5, 1.5, 2.5})] * RBF([l_t, l_lambda])  +  [Matern | RationalQuadratic]
+    +  WhiteKernel  whose (product factor, added term) pair is compiled (COMPILED_FAMILIES) - this covers the reference's default
+    (fulu/gp_aug.py:29), its docstring/test kernel C*RBF+Matern()+White (gp_aug.py:24, tests/test_aug.py:37), the notebook's
+    C*Matern()*RBF+Matern()+White (plotting.ipynb:33) and the RationalQuadratic the reference imports (gp_aug.py:5).
+    Initial values and bounds of the kernel object are honoured; fixed hyperparameters are refused."""
     if kernel is None:
         return KernelSpec()
-    names = lambda k: type(k).__name__
-    try:
-        ok = (names(kernel) == "Sum" and names(kernel.k1) == "Product" and names(kernel.k1.k1) == "ConstantKernel"
-              and names(kernel.k1.k2) == "RBF" and names(kernel.k2) == "WhiteKernel" and np.size(kernel.k1.k2.length_scale) == 2)
-        fixed = any(isinstance(b, str) for b in (kernel.k1.k1.constant_value_bounds, kernel.k1.k2.length_scale_bounds,
-                                                 kernel.k2.noise_level_bounds)) if ok else False
-    except AttributeError:
-        ok, fixed = False, False
-    if not ok or fixed:
+    name = lambda k: type(k).__name__
+    nu_code = {0.5: F_MAT05, 1.5: F_MAT15, 2.5: F_MAT25}
+
+    def refuse(why):
         raise NotImplementedError(
-            "fulu_b200 supports kernel = ConstantKernel * RBF([l_t, l_lambda]) + WhiteKernel (the fulu default) on the GPU path; "
-            f"got {kernel!r}")
+            "fulu_b200 runs kernels of the form ConstantKernel * [Matern] * RBF([l_t, l_lambda]) + [Matern | RationalQuadratic] + "
+            f"WhiteKernel on the GPU path ({why}); got {kernel!r}")
+
+    # leaves in sklearn's theta order (KernelOperator.theta = k1.theta ++ k2.theta, kernels.py:739-752)
+    offset = 0
+    terms = []
+    for term in _flatten(kernel, "Sum"):
+        leaves = []
+        for leaf in _flatten(term, "Product"):
+            if name(leaf) in ("Sum", "Exponentiation", "CompoundKernel"):
+                refuse("nested sums / exponentiation are not supported")
+            if any(h.fixed for h in leaf.hyperparameters):
+                refuse("fixed hyperparameters are not supported")
+            leaves.append((leaf, offset))
+            offset += leaf.n_dims
+        terms.append(leaves)
+
+    def iso_matern(leaf):
+        return name(leaf) == "Matern" and np.ndim(leaf.length_scale) == 0 and leaf.nu in nu_code
+
+    white = [t for t in terms if len(t) == 1 and name(t[0][0]) == "WhiteKernel"]
+    extra = [t for t in terms if len(t) == 1 and (iso_matern(t[0][0]) or name(t[0][0]) == "RationalQuadratic")]
+    main = [t for t in terms if t not in white and t not in extra]
+    if len(white) != 1 or len(main) != 1 or len(extra) > 1:
+        refuse("need exactly one WhiteKernel term, one ConstantKernel*RBF term and at most one added Matern/RationalQuadratic term")
+    consts = [(l, o) for l, o in main[0] if name(l) == "ConstantKernel"]
+    rbfs = [(l, o) for l, o in main[0] if name(l) == "RBF" and np.size(l.length_scale) == 2]
+    mats = [(l, o) for l, o in main[0] if iso_matern(l)]
+    if len(consts) != 1 or len(rbfs) != 1 or len(mats) > 1 or len(consts) + len(rbfs) + len(mats) != len(main[0]):
+        refuse("the product term must be ConstantKernel * [isotropic Matern, nu in {0.5, 1.5, 2.5}] * RBF with two length scales")
+    f1 = nu_code[mats[0][0].nu] if mats else F_NONE
+    perm = [consts[0][1]] + ([mats[0][1]] if mats else []) + [rbfs[0][1], rbfs[0][1] + 1]
+    ex = F_NONE
+    if extra:
+        leaf, o = extra[0][0]
+        if name(leaf) == "RationalQuadratic":
+            ex = F_RQ
+            perm += [o, o + 1]  # alpha, length_scale (hyperparameters sort by name, kernels.py:280-288)
+        else:
+            ex = nu_code[leaf.nu]
+            perm += [o]
+    perm.append(white[0][0][1])
+    family = family_code(f1, ex)
+    if family not in COMPILED_FAMILIES:
+        refuse(f"the family (product factor {f1}, added term {ex}) is not compiled into libfulu_gp")
+    perm = np.asarray(perm, np.int64)
     b = np.asarray(kernel.bounds, np.float64)
-    return KernelSpec(KERNEL_RBF_WHITE, np.asarray(kernel.theta, np.float64), b[:, 0].copy(), b[:, 1].copy())
+    return KernelSpec(family, np.asarray(kernel.theta, np.float64)[perm], b[perm, 0].copy(), b[perm, 1].copy(), perm=perm)
 
 
 def _require_cuda(device=None):
@@ -104,6 +204,15 @@ class DeviceBatch:
         self.order = None
         self.family, self.alpha0 = family, alpha0
 
+    def with_family(self, family):
+        """The same batch (nothing copied) read under another covariance family."""
+        if family == self.family:
+            return self
+        sub = DeviceBatch(self.offsets, self.t, self.flux, self.flux_err, self.band, self.loglam, self.n_max, self.use_err, self.alpha0, family)
+        sub.order = self.order
+        sub.c.order, sub.c.n_order = self.c.order, self.c.n_order
+        return sub
+
     def select(self, order, n_max=None):
         """The same batch restricted to the curves `order` (int32 curve ids, processing order), with launch geometry for curves
         of up to `n_max` observations.  Nothing is copied: the library follows the index list (fulu_gp_batch.order)."""
@@ -115,7 +224,7 @@ class DeviceBatch:
         return sub
 
     @staticmethod
-    def from_host(b: CurveBatch, device=None, use_err=False, pinned=None, n_max=None):
+    def from_host(b: CurveBatch, device=None, use_err=False, pinned=None, n_max=None, family=KERNEL_RBF_WHITE):
         """H2D copy of a host batch.  `pinned`: optional dict of pinned staging tensors (see HostStaging).  `n_max`: an upper
         bound on the curve length (default: the batch's own maximum); it fixes the launch geometry."""
         device = _require_cuda(device)
@@ -127,7 +236,7 @@ class DeviceBatch:
         else:
             src = pinned
         dev = {k: v.to(device, non_blocking=True) for k, v in src.items()}
-        return DeviceBatch(dev["offsets"], dev["t"], dev["flux"], dev["flux_err"], dev["band"], dev["loglam"], n_max, use_err)
+        return DeviceBatch(dev["offsets"], dev["t"], dev["flux"], dev["flux_err"], dev["band"], dev["loglam"], n_max, use_err, family=family)
 
     def h2d_bytes(self):
         return sum(x.numel() * x.element_size() for x in (self.offsets, self.t, self.flux, self.flux_err, self.band, self.loglam))
@@ -203,10 +312,17 @@ class GPEngine:
 
     # ---- a6: optimiser
     def fit(self, batch: DeviceBatch, spec: KernelSpec = None, window=0, max_rounds=0, factr=1e7, pgtol=1e-5, maxiter=15000,
-            maxfun=15000, maxls=20, m=10, return_runs=False, profile=False, out=None):
+            maxfun=15000, maxls=20, m=10, return_runs=False, profile=False, out=None, polish=None):
         """S = 1 + n_restarts L-BFGS-B runs per curve -> dict(theta [B,P], lml [B], n_eval [B], status [B]).
-        `out`: a dict of such tensors to write into (rows of the curves `batch` selects; the others are left alone)."""
-        spec = spec or KernelSpec()
+        `out`: a dict of such tensors to write into (rows of the curves `batch` selects; the others are left alone).
+
+        `polish` (default spec.polish) continuation runs: a fresh L-BFGS-B run per curve started at its best point, kept where
+        it improves the LML.  The kernels with 5-6 hyperparameters have nearly flat valleys (a Matern length or the RQ alpha
+        drifting to its bound) in which L-BFGS-B stops on its relative-reduction test at a point that depends on rounding;
+        sklearn's own runs stop at a different point of the same valley, sometimes 1e-6..1e-4 higher in LML.  One continuation
+        run (a few dozen evaluations, counted in n_eval) removes that dependence on the stopping accident."""
+        spec = spec or KernelSpec(batch.family)
+        batch = batch.with_family(spec.family)
         with torch.cuda.device(self.device):
             B, P = batch.n_curves, spec.n_params
             starts_h = spec.start_points()
@@ -235,6 +351,19 @@ class GPEngine:
             if profile:
                 keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a", "threads_eval", "ctas_per_sm")
                 out["profile"] = {k: float(prof[i]) for i, k in enumerate(keys)}
+            for _ in range(spec.polish if polish is None else polish):
+                # rows the batch does not select hold copies of the current values, so they compare equal and stay
+                o.n_starts, o.starts_per_curve, o.profile = 1, 1, None
+                cont = dict(theta=out["theta"].clone(), lml=out["lml"].clone(), n_eval=torch.zeros_like(out["n_eval"]), status=out["status"].clone())
+                starts2 = out["theta"].contiguous()
+                _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts2), self._p(cont["theta"]),
+                                                       self._p(cont["lml"]), self._p(cont["n_eval"]), self._p(cont["status"]), None, None,
+                                                       self._p(ws), ws.numel(), self._stream()))
+                better = cont["lml"] > out["lml"]
+                out["theta"].copy_(torch.where(better[:, None], cont["theta"], out["theta"]))
+                out["status"].copy_(torch.where(better, cont["status"], out["status"]))
+                out["lml"].copy_(torch.where(better, cont["lml"], out["lml"]))
+                out["n_eval"].add_(cont["n_eval"])
             return out
 
     # ---- a7-a9: augmentation grid / arbitrary points
@@ -307,7 +436,7 @@ def bucket_curves(lengths, buckets=N_BUCKETS):
     return [(int(buckets[min(k, len(buckets) - 1)]), np.nonzero(which == k)[0]) for k in np.unique(which)]
 
 
-def pin_results(n_curves, n_bands, n_obs, n_params=4):
+def pin_results(n_curves, n_bands, n_obs, n_params=4):  # n_params: KernelSpec.n_params of the family that will be fitted
     """Pinned host buffers for the results of fit_augment_batch (reusable across calls: what a production loop double-buffers)."""
     mk = lambda *shape, dtype=torch.float64: torch.empty(shape, dtype=dtype, pin_memory=True)
     return dict(mean=mk(n_curves, n_bands, n_obs), std=mk(n_curves, n_bands, n_obs), theta=mk(n_curves, n_params), lml=mk(n_curves),
@@ -319,7 +448,8 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
     """Fit + augmentation of a batch that is already resident in HBM: one pass of the library per length class (N_BUCKETS) over
     an index list of the class's curves, longest class first; every pass writes its rows of the same result tensors.
     Returns device tensors dict(mean, std [B,n_bands,n_obs], theta [B,P], lml, n_eval, status [B]) (+ "profile": per-class list)."""
-    spec = spec or KernelSpec()
+    spec = spec or KernelSpec(db.family)
+    db = db.with_family(spec.family)
     lengths = np.asarray(lengths)
     B, nb, P = db.n_curves, db.n_bands, spec.n_params
     groups = bucket_curves(lengths)
@@ -354,7 +484,8 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     The batch is uploaded once and stays where it is: each length class (N_BUCKETS) is one pass of the library over an index list
     of its curves, longest class first, and every pass writes its rows of the same device result tensors, which come back in one
     copy.  `pinned`: pinned staging of the inputs (pin_batch); `out`: pinned result buffers (pin_results) - the returned arrays
-    are then views of them.
+    are then views of them.  `spec`: the covariance family (KernelSpec / kernel_spec_from_sklearn); `theta` comes back in the
+    order of the sklearn kernel the spec was built from (KernelSpec.perm).
     """
     engine = engine or GPEngine(device)
     spec = spec or KernelSpec()
@@ -362,7 +493,7 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     if B == 0:
         return AugmentResult(np.empty((0, nb, n_obs)), np.empty((0, nb, n_obs)), np.empty((0, P)), np.empty(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
     with torch.cuda.device(engine.device):
-        db = DeviceBatch.from_host(curves, engine.device, use_err=use_err, pinned=pinned)
+        db = DeviceBatch.from_host(curves, engine.device, use_err=use_err, pinned=pinned, family=spec.family)
         tmn = None if t_min is None else torch.as_tensor(np.asarray(t_min, np.float64)).to(engine.device)
         tmx = None if t_max is None else torch.as_tensor(np.asarray(t_max, np.float64)).to(engine.device)
         dev = fit_augment_device(engine, db, curves.lengths(), n_obs, tmn, tmx, spec, window)
@@ -373,8 +504,10 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
             for k, v in dev.items():
                 host[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream(engine.device).synchronize()
-    res = AugmentResult(host["mean"].numpy(), host["std"].numpy(), host["theta"].numpy(), host["lml"].numpy(), host["n_eval"].numpy(),
-                        host["status"].numpy())
+    theta = host["theta"].numpy()
+    if not np.array_equal(spec.perm, np.arange(P)):
+        theta = spec.to_sklearn(theta)
+    res = AugmentResult(host["mean"].numpy(), host["std"].numpy(), theta, host["lml"].numpy(), host["n_eval"].numpy(), host["status"].numpy())
     res.h2d_bytes = db.h2d_bytes()
     res.d2h_bytes = sum(int(v.numel() * v.element_size()) for v in dev.values())
     return res

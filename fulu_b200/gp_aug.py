@@ -46,6 +46,9 @@ class _Scaler:
 
 
 class _KernelView:
+    """``reg.kernel_`` when the class was built with the default kernel (kernel=None); with an sklearn kernel object
+    ``reg.kernel_`` is that object cloned with the fitted theta."""
+
     def __init__(self, theta, bounds):
         self.theta, self.bounds = np.asarray(theta), bounds
 
@@ -59,7 +62,11 @@ class _FittedGP:
 
     def __init__(self, owner, theta, lml, n_eval):
         self._owner = owner
-        self.kernel_ = _KernelView(theta, np.c_[owner._spec.lower, owner._spec.upper])
+        spec = owner._spec
+        if owner.kernel is not None:   # theta is in the kernel object's own (sklearn) order
+            self.kernel_ = owner.kernel.clone_with_theta(np.asarray(theta, np.float64))
+        else:
+            self.kernel_ = _KernelView(theta, np.c_[spec.to_sklearn(spec.lower), spec.to_sklearn(spec.upper)])
         self.log_marginal_likelihood_value_ = float(lml)
         self.n_eval_ = int(n_eval)
 
@@ -69,10 +76,10 @@ class _FittedGP:
                 raise ValueError("Gradient can only be evaluated for theta!=None")
             return self.log_marginal_likelihood_value_
         o = self._owner
-        th = torch.as_tensor(np.asarray(theta, np.float64).reshape(1, -1))
+        th = torch.as_tensor(np.ascontiguousarray(o._spec.from_sklearn(np.asarray(theta, np.float64).reshape(1, -1))))
         out = o._engine.lml(o._batch, th)
         lml = float(out["lml"].cpu()[0])
-        return (lml, out["grad"].cpu().numpy()[0]) if eval_gradient else lml
+        return (lml, o._spec.to_sklearn(out["grad"].cpu().numpy()[0])) if eval_gradient else lml
 
 
 class GaussianProcessesAugmentation:
@@ -84,8 +91,10 @@ class GaussianProcessesAugmentation:
     passband2lam : dict
         A dictionary, where key is a passband ID and value is Log10 of its wave length.
     kernel : kernel object from sklearn, optional
-        Only the reference's default family ``C(1.0) * RBF([1.0, 1.0]) + WhiteKernel()`` runs on the GPU path (its initial values and
-        bounds are honoured); other kernels raise NotImplementedError.
+        ``C * [Matern] * RBF([l_t, l_lambda]) + [Matern | RationalQuadratic] + WhiteKernel`` in any order (the reference's default
+        ``C(1.0)*RBF([1.0, 1.0]) + WhiteKernel()``, its docstring kernel ``C(1.0)*RBF([1, 1]) + Matern() + WhiteKernel()``, the
+        notebook's ``C*Matern()*RBF([1, 1]) + Matern() + WhiteKernel()``, ...; see ``engine.kernel_spec_from_sklearn``).  Initial
+        values and bounds are honoured; other kernels raise NotImplementedError (there is no CPU fallback).
     use_err : bool
         Flag responsible for using flux error by GP Regressor.
     """
@@ -128,12 +137,12 @@ class GaussianProcessesAugmentation:
         if self._engine is None:
             self._engine = GPEngine(self._device)
         host = CurveBatch(np.array([0, len(t)], np.int64), t, flux, flux_err, band, loglam)
-        self._batch = DeviceBatch.from_host(host, self._engine.device, use_err=self.use_err)
+        self._batch = DeviceBatch.from_host(host, self._engine.device, use_err=self.use_err, family=self._spec.family)
         fit = self._engine.fit(self._batch, self._spec)
         status = int(fit["status"].cpu()[0])
         if status & STATUS_BAD_INPUT:
             raise ValueError("Input contains NaN, infinity or an unusable noise term.")
-        theta = fit["theta"].cpu().numpy()[0]
+        theta = self._spec.to_sklearn(fit["theta"].cpu().numpy()[0])   # reg.kernel_.theta is in the kernel object's order
         self._theta = fit["theta"]
         stats = self._engine.lml(self._batch, fit["theta"])
         self.ss = _Scaler(stats["scaler"].cpu().numpy()[0, [0, 2]], stats["scaler"].cpu().numpy()[0, [1, 3]])

@@ -29,12 +29,26 @@
 extern "C" {
 #endif
 
-#define FULU_GP_ABI_VERSION 2
+#define FULU_GP_ABI_VERSION 3
 #define FULU_GP_MAX_PARAMS 6
 #define FULU_GP_MAX_BANDS 16
 
-/* kernel families (theta is log-transformed, sklearn order; kernels.py:739-752) */
-#define FULU_GP_KERNEL_RBF_WHITE 0        /* C*RBF([lt,ll]) + White : theta = log[c, lt, ll, s2]  (fulu/gp_aug.py:29 default) */
+/* Covariance families:  K = c * [M1] * RBF([lt, ll]) + [EX] + White, a kernel code is FULU_GP_KERNEL(f1, ex) with
+ *   f1 (an isotropic Matern factor multiplying the RBF) and ex (an added isotropic term) one of FULU_GP_F_*.
+ * theta is log-transformed, in CANONICAL order [c, (l_1), lt, ll, (ex: l | alpha, l), s2]; for kernels written as
+ * C*[Matern*]RBF + [Matern|RationalQuadratic] + White this is sklearn's own order (kernels.py:739-752, hyperparameters of one
+ * kernel sorted by name :280-288); other orderings of the same sum/product are permuted by the host binding.
+ * Families compiled into this build: (0,0) (0,MAT15) (MAT15,MAT15) (0,RQ) (0,MAT05) (0,MAT25) (MAT15,0); others -> E_UNSUPPORTED. */
+#define FULU_GP_F_NONE 0
+#define FULU_GP_F_MAT05 1                 /* Matern nu = 1/2  (kernels.py:1722-1723) */
+#define FULU_GP_F_MAT15 2                 /* Matern nu = 3/2  (kernels.py:1724-1726; sklearn's default nu) */
+#define FULU_GP_F_MAT25 3                 /* Matern nu = 5/2  (kernels.py:1727-1729) */
+#define FULU_GP_F_RQ 4                    /* RationalQuadratic (kernels.py:1917-1947); ex only */
+#define FULU_GP_KERNEL(f1, ex) ((f1) | ((ex) << 4))
+#define FULU_GP_KERNEL_RBF_WHITE FULU_GP_KERNEL(0, 0)                 /* C*RBF([lt,ll]) + White, P = 4  (fulu/gp_aug.py:29 default) */
+#define FULU_GP_KERNEL_RBF_MATERN_WHITE FULU_GP_KERNEL(0, 2)          /* C*RBF + Matern() + White, P = 5  (fulu/gp_aug.py:24, tests/test_aug.py:37) */
+#define FULU_GP_KERNEL_MATERN_RBF_MATERN_WHITE FULU_GP_KERNEL(2, 2)   /* C*Matern()*RBF + Matern() + White, P = 6  (notebook_examples/plotting.ipynb:33) */
+#define FULU_GP_KERNEL_RBF_RQ_WHITE FULU_GP_KERNEL(0, 4)              /* C*RBF + RationalQuadratic() + White, P = 6  (fulu/gp_aug.py:5) */
 
 /* argument errors */
 #define FULU_GP_E_BADARG (-1)
@@ -72,7 +86,7 @@ typedef struct fulu_gp_batch {
 } fulu_gp_batch;
 
 typedef struct fulu_gp_fit_options {
-  int32_t n_params;          /* P (4 for the default kernel) */
+  int32_t n_params;          /* P of the batch's kernel family (4 for the default kernel, up to FULU_GP_MAX_PARAMS) */
   int32_t n_starts;          /* S = 1 + n_restarts_optimizer = 6 */
   int32_t m;                 /* L-BFGS history, 10 */
   int32_t maxiter;           /* 15000 */
@@ -80,6 +94,9 @@ typedef struct fulu_gp_fit_options {
   int32_t maxls;             /* 20 */
   int32_t window;            /* optimiser instances resident at once (0 = default) */
   int32_t max_rounds;        /* hard cap on evaluation rounds (0 = default) */
+  int32_t starts_per_curve;  /* 0: theta_starts is [S,P], shared by all curves (sklearn's restarts); 1: [B,S,P], indexed by curve id
+                                (e.g. S = 1 continuation runs from each curve's current optimum) */
+  int32_t reserved;
   double factr;              /* 1e7  (ftol = factr * eps) */
   double pgtol;              /* 1e-5 */
   double lower[FULU_GP_MAX_PARAMS];   /* log-bounds, ln(1e-5) */
@@ -105,6 +122,7 @@ int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double
 
 /* Hyperparameter optimisation: S bound-constrained L-BFGS-B runs per curve from theta_starts [S,P], best LML wins.
  * Replaces GaussianProcessRegressor.fit's optimiser loop (_gpr.py:299-340,658-668).
+ * theta_starts is read in place (see starts_per_curve); points outside the bounds are clipped (_lbfgsb_py.py:359).
  * theta_opt [B,P], lml_opt [B], n_eval [B] (LML+gradient evaluations spent on the curve), status [B] out.
  * run_lml [B,S] (final LML of every run) and run_theta [B,S,P] may be NULL. */
 int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,

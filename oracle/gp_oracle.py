@@ -39,11 +39,37 @@ from scipy.optimize import minimize
 
 LOG_BOUND = float(np.log(1e5))  # sklearn default hyperparameter bounds (1e-5, 1e5) in log space
 
-# Kernel families (same integer codes as include/fulu_gp.h FULU_GP_KERNEL_*).
-KERNEL_RBF_WHITE = 0  # C(1.0) * RBF([1, 1]) + WhiteKernel()                     theta = [c, lt, ll, s2]
-KERNEL_RBF_MATERN_WHITE = 1  # C(1.0) * RBF([1, 1]) + Matern(nu=1.5) + WhiteKernel()   theta = [c, lt, ll, lm, s2]
+# Kernel families (same integer codes as include/fulu_gp.h: FULU_GP_KERNEL(f1, ex) = f1 | ex << 4).
+#   K = c * [M1] * RBF([lt, ll]) + [EX] + White;  f1 / ex in {0 none, 1 Matern 1/2, 2 Matern 3/2, 3 Matern 5/2, 4 RationalQuadratic}
+#   theta in CANONICAL order: [c, (l_1), lt, ll, (EX: l | alpha, l), s2]   (log-transformed)
+F_NONE, F_MAT05, F_MAT15, F_MAT25, F_RQ = 0, 1, 2, 3, 4
 
-KERNEL_NPARAMS = {KERNEL_RBF_WHITE: 4, KERNEL_RBF_MATERN_WHITE: 5}
+
+def family_code(f1=F_NONE, ex=F_NONE):
+    return f1 | (ex << 4)
+
+
+KERNEL_RBF_WHITE = family_code()  # C(1.0) * RBF([1, 1]) + WhiteKernel()                      theta = [c, lt, ll, s2]
+KERNEL_RBF_MATERN_WHITE = family_code(ex=F_MAT15)  # C * RBF([1, 1]) + Matern() + White       theta = [c, lt, ll, lm, s2]
+KERNEL_MATERN_RBF_MATERN_WHITE = family_code(F_MAT15, F_MAT15)  # C * Matern() * RBF([1, 1]) + Matern() + White  [c, l1, lt, ll, lm, s2]
+KERNEL_RBF_RQ_WHITE = family_code(ex=F_RQ)  # C * RBF([1, 1]) + RationalQuadratic() + White   theta = [c, lt, ll, alpha, lq, s2]
+
+
+def family_parts(kind):
+    return kind & 15, kind >> 4
+
+
+def n_params(kind):
+    f1, ex = family_parts(kind)
+    return 4 + (1 if f1 else 0) + (2 if ex == F_RQ else 1 if ex else 0)
+
+
+class _NParams(dict):
+    def __missing__(self, kind):
+        return n_params(kind)
+
+
+KERNEL_NPARAMS = _NParams()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -114,39 +140,104 @@ def _sqdist(A, B):
     return np.einsum("ijk,ijk->ij", d, d)
 
 
-def kernel_train(X, theta, kind=KERNEL_RBF_WHITE, eval_gradient=False):
-    """K(X, X) (without the regressor's alpha) and dK/dtheta_k.
+def _iso_factor(kind, D2, params, eval_gradient):
+    """One isotropic stationary factor from squared RAW distances D2: value and d/dlog(hyperparameter) list.
 
-    sklearn/gaussian_process/kernels.py:1558-1585 (anisotropic RBF), :1278-1292 (Constant),
-    :1403-1413 (White), :964-969 (Product rule), :866-869 (Sum rule), :1716-1784 (Matern 1.5).
+    Matern nu = 1/2, 3/2, 5/2: sklearn/gaussian_process/kernels.py:1716-1729 (value), :1757-1774 (gradient);
+    RationalQuadratic: :1917-1947 (theta order alpha, length_scale: hyperparameters sort by name, :280-288).
     """
-    theta = np.asarray(theta, np.float64)
-    n = X.shape[0]
-    c = np.exp(theta[0])
-    ell = np.exp(theta[1:3])
-    s2 = np.exp(theta[-1])
-    Xs = X / ell
-    E = np.exp(-0.5 * _sqdist(Xs, Xs))
-    np.fill_diagonal(E, 1.0)
-    K = c * E
-    grads = []
-    if eval_gradient:
-        grads.append(c * E)
-        for d in range(2):
-            D = (X[:, d][:, None] - X[:, d][None, :]) ** 2 / ell[d] ** 2
-            grads.append(c * E * D)
-    if kind == KERNEL_RBF_MATERN_WHITE:
-        lm = np.exp(theta[3])
-        r = np.sqrt(_sqdist(X / lm, X / lm))
-        np.fill_diagonal(r, 0.0)
+    if kind == F_RQ:
+        alpha, ell = params
+        tmp = D2 / (2.0 * alpha * ell**2)
+        base = 1.0 + tmp
+        K = base**-alpha
+        if not eval_gradient:
+            return K, []
+        g_len = D2 * K / (ell**2 * base)
+        g_alpha = K * (-alpha * np.log(base) + D2 / (2.0 * ell**2 * base))
+        return K, [g_alpha, g_len]
+    (ell,) = params
+    S = D2 / ell**2
+    r = np.sqrt(S)
+    if kind == F_MAT05:
+        K = np.exp(-r)
+        return K, ([K * r] if eval_gradient else [])
+    if kind == F_MAT15:
         a = np.sqrt(3.0) * r
-        Km = (1.0 + a) * np.exp(-a)
-        K = K + Km
-        if eval_gradient:
-            # sklearn: K_gradient = 3 * D * exp(-sqrt(3 D.sum)) with D = squared scaled diffs (isotropic -> r^2)
-            grads.append(3.0 * r * r * np.exp(-a))
-    elif kind != KERNEL_RBF_WHITE:
-        raise NotImplementedError(kind)
+        K = (1.0 + a) * np.exp(-a)
+        return K, ([3.0 * S * np.exp(-np.sqrt(3.0 * S))] if eval_gradient else [])
+    if kind == F_MAT25:
+        a = np.sqrt(5.0) * r
+        K = (1.0 + a + a**2 / 3.0) * np.exp(-a)
+        tmp = np.sqrt(5.0 * S)
+        return K, ([5.0 / 3.0 * S * (tmp + 1.0) * np.exp(-tmp)] if eval_gradient else [])
+    raise NotImplementedError(kind)
+
+
+def _split_theta(theta, kind):
+    f1, ex = family_parts(kind)
+    th = np.exp(np.asarray(theta, np.float64))
+    k = 1
+    p1 = None
+    if f1:
+        p1 = (th[k],)
+        k += 1
+    ell = th[k:k + 2]
+    k += 2
+    pe = None
+    if ex == F_RQ:
+        pe = (th[k], th[k + 1])
+        k += 2
+    elif ex:
+        pe = (th[k],)
+        k += 1
+    assert k == len(th) - 1, "theta length does not match the kernel family"
+    return f1, ex, th[0], p1, ell, pe, th[-1]
+
+
+def _kernel_pairs(XA, XB, theta, kind, eval_gradient):
+    """Noise-free covariance between two point sets and (optionally) its gradient planes in canonical theta order (no White)."""
+    f1, ex, c, p1, ell, pe, _ = _split_theta(theta, kind)
+    E = np.exp(-0.5 * _sqdist(XA / ell, XB / ell))
+    D2 = _sqdist(XA, XB) if (f1 or ex) else None
+    grads = []
+    if f1:
+        M, gM = _iso_factor(f1, D2, p1, eval_gradient)
+        T = c * E * M
+    else:
+        M, gM = 1.0, []
+        T = c * E
+    K = T
+    if eval_gradient:
+        grads.append(T)  # d/dlog c (kernels.py:1290-1292 with the product rule :967-969)
+        grads += [c * E * g for g in gM]
+        for d in range(2):  # anisotropic RBF (kernels.py:1581-1584)
+            D = (XA[:, d][:, None] - XB[:, d][None, :]) ** 2 / ell[d] ** 2
+            grads.append(T * D)
+    if ex:
+        A, gA = _iso_factor(ex, D2, pe, eval_gradient)
+        K = K + A
+        grads += gA
+    return K, grads
+
+
+def kernel_train(X, theta, kind=KERNEL_RBF_WHITE, eval_gradient=False):
+    """K(X, X) (without the regressor's alpha) and dK/dtheta_k, canonical theta order.
+
+    sklearn/gaussian_process/kernels.py:1558-1585 (anisotropic RBF), :1278-1292 (Constant), :1403-1413 (White),
+    :964-969 (Product rule), :866-869 (Sum rule), :1716-1784 (Matern), :1917-1947 (RationalQuadratic).
+    """
+    n = X.shape[0]
+    s2 = np.exp(np.asarray(theta, np.float64)[-1])
+    K, grads = _kernel_pairs(X, X, theta, kind, eval_gradient)
+    # pdist/squareform + fill_diagonal(K, 1) in sklearn: exact ones on the diagonal of every stationary factor, exact zeros on
+    # the diagonal of its gradient
+    c = np.exp(np.asarray(theta, np.float64)[0])
+    K = K.copy()
+    K[np.diag_indices(n)] = c + 1.0 if family_parts(kind)[1] else c
+    if eval_gradient:
+        for k, G in enumerate(grads):
+            G[np.diag_indices(n)] = c if k == 0 else 0.0
     K = K + s2 * np.eye(n)
     if eval_gradient:
         grads.append(s2 * np.eye(n))
@@ -156,24 +247,35 @@ def kernel_train(X, theta, kind=KERNEL_RBF_WHITE, eval_gradient=False):
 
 def kernel_cross(Xq, X, theta, kind=KERNEL_RBF_WHITE):
     """K(X*, X): WhiteKernel contributes zeros.  kernels.py:1569-1570, :1418-1419."""
-    theta = np.asarray(theta, np.float64)
-    c = np.exp(theta[0])
-    ell = np.exp(theta[1:3])
-    K = c * np.exp(-0.5 * _sqdist(Xq / ell, X / ell))
-    if kind == KERNEL_RBF_MATERN_WHITE:
-        lm = np.exp(theta[3])
-        a = np.sqrt(3.0) * np.sqrt(_sqdist(Xq / lm, X / lm))
-        K = K + (1.0 + a) * np.exp(-a)
-    return K
+    return _kernel_pairs(Xq, X, theta, kind, False)[0]
 
 
 def kernel_diag(theta, m, kind=KERNEL_RBF_WHITE):
-    """kernel_.diag(X*) = c + noise_level (+1 for Matern).  kernels.py:890,990,1315-1319,1438-1440."""
+    """kernel_.diag(X*) = c + noise_level (+1 for an added Matern / RQ term).  kernels.py:890,990,1315-1319,1438-1440."""
     theta = np.asarray(theta, np.float64)
     v = np.exp(theta[0]) + np.exp(theta[-1])
-    if kind == KERNEL_RBF_MATERN_WHITE:
+    if family_parts(kind)[1]:
         v = v + 1.0
     return np.full(m, v)
+
+
+# ---- sklearn kernel object <-> family (used by the tests to run live sklearn on the same kernel)
+def sklearn_kernel(kind, theta=None):
+    """The sklearn kernel object of a family, hyperparameters in CANONICAL order == sklearn's tree order for this construction."""
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, RationalQuadratic, WhiteKernel
+
+    f1, ex = family_parts(kind)
+    nu = {F_MAT05: 0.5, F_MAT15: 1.5, F_MAT25: 2.5}
+    k = ConstantKernel(1.0)
+    if f1:
+        k = k * Matern(nu=nu[f1])
+    k = k * RBF([1.0, 1.0])
+    if ex == F_RQ:
+        k = k + RationalQuadratic()
+    elif ex:
+        k = k + Matern(nu=nu[ex])
+    k = k + WhiteKernel()
+    return k if theta is None else k.clone_with_theta(np.asarray(theta, np.float64))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -221,7 +323,7 @@ def start_points(nparams, n_restarts=5, seed=42, theta0=None):
 
 def fit_theta(X, y, alpha, kind=KERNEL_RBF_WHITE, starts=None, return_all=False):
     """Six bound-constrained L-BFGS-B runs, best -LML wins.  _gpr.py:299-340,658-668."""
-    p = KERNEL_NPARAMS[kind]
+    p = n_params(kind)
     if starts is None:
         starts = start_points(p)
     bounds = [(-LOG_BOUND, LOG_BOUND)] * p

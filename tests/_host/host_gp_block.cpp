@@ -78,25 +78,38 @@ extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const
   return status;
 }
 
-extern "C" int host_gp_lml(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
-                           const double* theta, int nthr, double* lml, double* grad) {
+// family code = F1 | EX << 4 (include/fulu_gp.h FULU_GP_KERNEL)
+#define HOST_FAMILIES(X) X(0, 0) X(0, 1) X(0, 2) X(0, 3) X(0, 4) X(2, 0) X(2, 2)
+
+template <class Kern>
+static int lml_impl(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                    const double* theta, int nthr, double* lml, double* grad) {
   std::vector<double> smem(gp_smem_doubles(n));
   GpCurveView cv{n, xs, band, y, al, lam};
   int okout = 0;
   const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
     GpSmem s = gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
-    double l, g[4];
+    double l, g[Kern::P];
     bool ok;
-    gp_eval_lml_grad(c, cv, theta, s, l, g, ok);
+    gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
     if (c.tid == 0) { *lml = l; std::memcpy(grad, g, sizeof(g)); okout = ok; }
   });
   return okout;
 }
 
-extern "C" int host_gp_predict(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
-                               const double* theta, const double* stats, int m, int n_obs, double t_min, double t_max,
-                               const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
+extern "C" int host_gp_lml(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                           const double* theta, int nthr, double* lml, double* grad) {
+#define X(F1, EX) if (family == ((F1) | ((EX) << 4))) return lml_impl<GpKern<F1, EX>>(n, xs, band, y, al, lam, theta, nthr, lml, grad);
+  HOST_FAMILIES(X)
+#undef X
+  return -1;
+}
+
+template <class Kern>
+static int predict_impl(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                        const double* theta, const double* stats, int m, int n_obs, double t_min, double t_max,
+                        const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
   std::vector<double> smem(gp_smem_doubles(n));
   std::vector<double> V((size_t)gp_pad(n) * GP_QC);
   GpCurveView cv{n, xs, band, y, al, lam};
@@ -106,10 +119,21 @@ extern "C" int host_gp_predict(int n, const double* xs, const int32_t* band, con
   run_block(nthr, [&](HostCtx& c) {
     GpSmem s = gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
     double l;
-    int st = gp_predict_curve(c, cv, theta, stats, qd, s, V.data(), mean, stdv, l);
+    int st = gp_predict_curve<Kern>(c, cv, theta, stats, qd, s, V.data(), mean, stdv, l);
     if (c.tid == 0) { status = st; *lml = l; }
   });
   return status;
+}
+
+extern "C" int host_gp_predict(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                               const double* theta, const double* stats, int m, int n_obs, double t_min, double t_max,
+                               const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
+#define X(F1, EX) \
+  if (family == ((F1) | ((EX) << 4))) \
+    return predict_impl<GpKern<F1, EX>>(n, xs, band, y, al, lam, theta, stats, m, n_obs, t_min, t_max, qt, qband, nthr, mean, stdv, lml);
+  HOST_FAMILIES(X)
+#undef X
+  return -1;
 }
 
 extern "C" void host_gp_exp_neg(int n, const double* x, double* out) {

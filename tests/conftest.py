@@ -15,8 +15,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def golden_names():
+    """Fixtures of the default kernel (fulu/gp_aug.py:29)."""
+    return [n for n in _all_golden() if not n.startswith("fam_")]
+
+
+def family_golden_names():
+    """Fixtures of the non-default kernels (tests/golden/make_golden.py --families); theta / grad in the kernel object's order."""
+    return [n for n in _all_golden() if n.startswith("fam_")]
+
+
+def family_kernel(name):
+    """The sklearn kernel object a fam_* fixture was generated with (same table as make_golden.family_kernels)."""
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, Matern, RationalQuadratic, WhiteKernel
+
+    return {
+        "rbf_matern": lambda: C(1.0) * RBF([1, 1]) + Matern() + WhiteKernel(),
+        "notebook": lambda: C(1.0) * Matern() * RBF([1, 1]) + Matern() + WhiteKernel(),
+        "rbf_rq": lambda: C(1.0) * RBF([1, 1]) + RationalQuadratic() + WhiteKernel(),
+        "matern_rbf": lambda: C(1.0) * Matern() * RBF([1.0, 1.0]) + WhiteKernel(),
+        "rbf_matern05": lambda: C(1.0) * RBF([1, 1]) + Matern(nu=0.5) + WhiteKernel(),
+        "permuted_matern25": lambda: WhiteKernel(0.5) + Matern(length_scale=2.0, nu=2.5) + RBF([2.0, 0.5]) * C(4.0),
+    }[str(name)]()
 
 
 def load_golden(name):

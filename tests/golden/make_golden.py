@@ -38,7 +38,24 @@ def load_reference():
     return gp_aug.GaussianProcessesAugmentation
 
 
-def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=None, t_max=None):
+def family_kernels():
+    """The non-default kernels of the fam_* fixtures, by name (tests/conftest.py builds the same objects from the name).
+    rbf_matern: the reference's docstring / test kernel (fulu/gp_aug.py:24, tests/test_aug.py:37); notebook: plotting.ipynb:33;
+    rbf_rq: the RationalQuadratic the reference imports (gp_aug.py:5); the others exercise Matern nu = 1/2, 5/2 and a different
+    ordering of the same sum/product (theta permutation)."""
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, Matern, RationalQuadratic, WhiteKernel
+
+    return {
+        "rbf_matern": lambda: C(1.0) * RBF([1, 1]) + Matern() + WhiteKernel(),
+        "notebook": lambda: C(1.0) * Matern() * RBF([1, 1]) + Matern() + WhiteKernel(),
+        "rbf_rq": lambda: C(1.0) * RBF([1, 1]) + RationalQuadratic() + WhiteKernel(),
+        "matern_rbf": lambda: C(1.0) * Matern() * RBF([1.0, 1.0]) + WhiteKernel(),
+        "rbf_matern05": lambda: C(1.0) * RBF([1, 1]) + Matern(nu=0.5) + WhiteKernel(),
+        "permuted_matern25": lambda: WhiteKernel(0.5) + Matern(length_scale=2.0, nu=2.5) + RBF([2.0, 0.5]) * C(4.0),
+    }
+
+
+def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=None, t_max=None, kernel=None):
     import sklearn.gaussian_process._gpr as gpr_mod
 
     keys = list(p2l)
@@ -54,7 +71,7 @@ def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=
 
     gpr_mod.GaussianProcessRegressor.log_marginal_likelihood = counted
     try:
-        aug = cls(p2l, use_err=use_err)
+        aug = cls(p2l, use_err=use_err) if kernel is None else cls(p2l, kernel=family_kernels()[kernel](), use_err=use_err)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             assert aug.fit(t, flux, flux_err, passband) is aug
@@ -64,7 +81,8 @@ def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=
     theta_star = reg.kernel_.theta.copy()
     rng = np.random.RandomState(42)
     b = reg.kernel_.bounds
-    thetas = [np.zeros(len(theta_star))] + [rng.uniform(b[:, 0], b[:, 1]) for _ in range(5)] + [theta_star]
+    theta0 = np.zeros(len(theta_star)) if kernel is None else family_kernels()[kernel]().theta
+    thetas = [theta0] + [rng.uniform(b[:, 0], b[:, 1]) for _ in range(5)] + [theta_star]
     lmls, grads = [], []
     for th in thetas:
         l, g = reg.log_marginal_likelihood(th, eval_gradient=True, clone_kernel=True)
@@ -76,8 +94,10 @@ def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         t_aug, f_aug, e_aug, pb_aug = aug.augmentation(t_min, t_max, n_obs)
-        # prediction at fixed (non-optimised) hyperparameters: start point #5 is a well conditioned one
-        reg2 = gpr_mod.GaussianProcessRegressor(kernel=reg.kernel_.clone_with_theta(thetas[5]), optimizer=None, normalize_y=True,
+        # prediction at fixed (non-optimised) hyperparameters: start point #5 is a well conditioned one for the default kernel;
+        # for the other kernels the restart point with the best LML is used (key k_fix; the arrays keep the "theta5" name)
+        k_fix = 5 if kernel is None else 1 + int(np.argmax(lmls[1:6]))
+        reg2 = gpr_mod.GaussianProcessRegressor(kernel=reg.kernel_.clone_with_theta(thetas[k_fix]), optimizer=None, normalize_y=True,
                                                 alpha=reg.alpha)
         reg2.fit(aug.ss.transform(np.c_[t, loglam[band]]), np.asarray(flux, np.float64))
         Xq = aug.ss.transform(np.c_[t_aug, np.repeat(loglam, n_obs)])
@@ -90,7 +110,8 @@ def run_case(cls, name, p2l, t, flux, flux_err, passband, use_err, n_obs, t_min=
         theta_star=theta_star, lml_star=np.array(reg.log_marginal_likelihood_value_), n_eval=np.array(n_eval[0]),
         thetas=np.array(thetas), lml=np.array(lmls), grad=np.array(grads),
         t_aug=t_aug, flux_aug=f_aug, flux_err_aug=e_aug, band_aug=np.repeat(np.arange(len(keys), dtype=np.int32), n_obs),
-        flux_aug_theta5=f5, flux_err_aug_theta5=e5,
+        flux_aug_theta5=f5, flux_err_aug_theta5=e5, kernel=np.array("" if kernel is None else kernel),
+        k_fix=np.array(k_fix),
     )
     print(f"{name}: N={len(t)} use_err={use_err} E={n_eval[0]} lml*={reg.log_marginal_likelihood_value_:.10f} theta*={theta_star}")
 
@@ -101,6 +122,29 @@ def main():
     from fulu_b200 import datasets
 
     cls = load_reference()
+    if "--families" in sys.argv or "--families-only" in sys.argv:
+        # non-default kernels: theta / grad are stored in the kernel object's own (sklearn) order
+        p2l, *lc = datasets.reference_test_fixture()
+        run_case(cls, "fam_rbf_matern_testfixture", p2l, *lc, use_err=False, n_obs=100, kernel="rbf_matern")   # tests/test_aug.py:37
+        run_case(cls, "fam_permuted_matern25_testfixture", p2l, *lc, use_err=True, n_obs=50, kernel="permuted_matern25")
+        df = pd.read_csv(os.path.join(REF, "notebook_examples", "object_34299.csv"))
+        p2l = {i: float(np.log10(v)) for i, v in enumerate(datasets.LSST_LAMBDA)}
+        lc = (df.mjd.values, df.flux.values, df.flux_err.values, df.passband.values)
+        run_case(cls, "fam_notebook_csv34299", p2l, *lc, use_err=False, n_obs=128, kernel="notebook")           # plotting.ipynb:33
+        run_case(cls, "fam_rbf_matern_csv34299", p2l, *lc, use_err=False, n_obs=128, kernel="rbf_matern")
+        run_case(cls, "fam_rbf_rq_csv34299_err", p2l, *lc, use_err=True, n_obs=64, kernel="rbf_rq")
+        run_case(cls, "fam_matern_rbf_csv34299", p2l, *lc, use_err=False, n_obs=64, kernel="matern_rbf")
+        b = datasets.plasticc_like(2)
+        for i, kn in enumerate(("rbf_matern", "rbf_rq")):
+            t, f, e, bd = b.curve(i)
+            run_case(cls, f"fam_{kn}_plasticc_{i}", p2l, t, f, e, bd, use_err=False, n_obs=128, kernel=kn)
+        z = datasets.ztf_like(2)
+        p2z = {i: float(np.log10(v)) for i, v in enumerate(datasets.ZTF_LAMBDA)}
+        for i, kn in enumerate(("rbf_matern05", "notebook")):
+            t, f, e, bd = z.curve(i)
+            run_case(cls, f"fam_{kn}_ztf_{i}", p2z, t, f, e, bd, use_err=False, n_obs=128, kernel=kn)
+        if "--families-only" in sys.argv:
+            return
     p2l, *lc = datasets.readme_example()
     run_case(cls, "readme", p2l, *lc, use_err=False, n_obs=100)
     run_case(cls, "readme_err", p2l, *lc, use_err=True, n_obs=100)

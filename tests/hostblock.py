@@ -39,27 +39,27 @@ def prepare(t, flux, flux_err, band, loglam, use_err, alpha0=1e-10, nthr=32):
     return p
 
 
-def lml_grad(p, theta, nthr=32):
+def lml_grad(p, theta, nthr=32, family=0):
     lib = _lib()
     theta = np.ascontiguousarray(theta, np.float64)
     lml = ctypes.c_double()
-    grad = np.zeros(4)
-    ok = lib.host_gp_lml(p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), nthr, ctypes.byref(lml), _dp(grad))
+    grad = np.zeros(len(theta))
+    ok = lib.host_gp_lml(family, p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), nthr, ctypes.byref(lml), _dp(grad))
     return lml.value, grad, bool(ok)
 
 
-def predict_grid(p, theta, n_bands, n_obs, t_min, t_max, nthr=32):
+def predict_grid(p, theta, n_bands, n_obs, t_min, t_max, nthr=32, family=0):
     lib = _lib()
     theta = np.ascontiguousarray(theta, np.float64)
     m = n_bands * n_obs
     mean, std = np.zeros(m), np.zeros(m)
     lml = ctypes.c_double()
-    st = lib.host_gp_predict(p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), _dp(p.stats), m, n_obs,
+    st = lib.host_gp_predict(family, p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), _dp(p.stats), m, n_obs,
                              ctypes.c_double(t_min), ctypes.c_double(t_max), None, None, nthr, _dp(mean), _dp(std), ctypes.byref(lml))
     return mean, std, lml.value, st
 
 
-def predict_points(p, theta, qt, qband, nthr=32):
+def predict_points(p, theta, qt, qband, nthr=32, family=0):
     lib = _lib()
     theta = np.ascontiguousarray(theta, np.float64)
     qt = np.ascontiguousarray(qt, np.float64)
@@ -67,7 +67,7 @@ def predict_points(p, theta, qt, qband, nthr=32):
     m = len(qt)
     mean, std = np.zeros(m), np.zeros(m)
     lml = ctypes.c_double()
-    st = lib.host_gp_predict(p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), _dp(p.stats), m, 0,
+    st = lib.host_gp_predict(family, p.n, _dp(p.xs), _ip(p.band), _dp(p.y), _dp(p.al), _dp(p.lam), _dp(theta), _dp(p.stats), m, 0,
                              ctypes.c_double(0), ctypes.c_double(0), _dp(qt), _ip(qband), nthr, _dp(mean), _dp(std), ctypes.byref(lml))
     return mean, std, lml.value, st
 

@@ -28,7 +28,7 @@ def test_binding_loads_and_reports_version(lib_path):
     from fulu_b200 import _capi
 
     lib = _capi.load()
-    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 2
+    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 3
     assert b"workspace" in lib.fulu_gp_strerror(-2)
     assert set(_capi.EXPORTS) <= {n for n in dir(lib)} | set(_capi.EXPORTS)
 
@@ -36,9 +36,9 @@ def test_binding_loads_and_reports_version(lib_path):
 def test_struct_layout_matches_header():
     from fulu_b200 import _capi
 
-    # fulu_gp_batch: 2*i64 + 2*i32 + 6 pointers + 2*i32 + f64 + pointer + i64 = 104 bytes; fit options: 8*i32 + 2*f64 + 12*f64 + pointer = 152
+    # fulu_gp_batch: 2*i64 + 2*i32 + 6 pointers + 2*i32 + f64 + pointer + i64 = 104 bytes; fit options: 10*i32 + 2*f64 + 12*f64 + pointer = 160
     assert ctypes.sizeof(_capi.Batch) == 104
-    assert ctypes.sizeof(_capi.FitOptions) == 152
+    assert ctypes.sizeof(_capi.FitOptions) == 160
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -71,6 +71,9 @@ def test_unsupported_kernel_is_refused():
 
     import fulu_b200
 
+    from sklearn.gaussian_process.kernels import ExpSineSquared
+
     fulu_b200.GaussianProcessesAugmentation({0: 3.5}, kernel=ConstantKernel(1.0) * RBF([1.0, 1.0]) + WhiteKernel())
+    fulu_b200.GaussianProcessesAugmentation({0: 3.5}, kernel=ConstantKernel(1.0) * RBF([1, 1]) + Matern() + WhiteKernel())
     with pytest.raises(NotImplementedError):
-        fulu_b200.GaussianProcessesAugmentation({0: 3.5}, kernel=ConstantKernel(1.0) * RBF([1, 1]) + Matern() + WhiteKernel())
+        fulu_b200.GaussianProcessesAugmentation({0: 3.5}, kernel=ConstantKernel(1.0) * RBF([1, 1]) + ExpSineSquared() + WhiteKernel())
