@@ -31,9 +31,24 @@ N_POINTS, N_OBS, N_BANDS = 100, 128, 6
 METRIC = "light curves/sec GP fit+augment (6 bands, N=100)"
 
 
+# kernels of the --kernel option: the reference's default (fulu/gp_aug.py:29) and the others its users pass
+def make_kernel(name):
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, Matern, RationalQuadratic, WhiteKernel
+
+    return {
+        "default": lambda: None,
+        "rbf_matern": lambda: C(1.0) * RBF([1, 1]) + Matern() + WhiteKernel(),                  # fulu/gp_aug.py:24, tests/test_aug.py:37
+        "notebook": lambda: C(1.0) * Matern() * RBF([1, 1]) + Matern() + WhiteKernel(),         # notebook_examples/plotting.ipynb:33
+        "rbf_rq": lambda: C(1.0) * RBF([1, 1]) + RationalQuadratic() + WhiteKernel(),           # fulu/gp_aug.py:5
+    }[name]()
+
+
+KERNEL = "default"
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def _cpu_worker(args):
-    first, count, n_points, n_obs = args
+    first, count, n_points, n_obs, kernel = args
     import warnings
 
     import numpy as np
@@ -46,7 +61,7 @@ def _cpu_worker(args):
     out = []
     for i in range(hb.n_curves):
         t, f, e, b = hb.curve(i)
-        aug = SklearnGPAugmentation(p2l)
+        aug = SklearnGPAugmentation(p2l, kernel=make_kernel(kernel))
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             aug.fit(t, f, e, b)
@@ -63,9 +78,9 @@ def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4):
     cores = cores or os.cpu_count() or 1
     for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = "1"  # 8 procs x 1 BLAS thread beat 1 x 8 by 6x
-    tasks = [(first + i, min(chunk, n_curves - i), N_POINTS, N_OBS) for i in range(0, n_curves, chunk)]
+    tasks = [(first + i, min(chunk, n_curves - i), N_POINTS, N_OBS, KERNEL) for i in range(0, n_curves, chunk)]
     with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
-        list(ex.map(_cpu_worker, [(10_000_000 + w, 1, N_POINTS, N_OBS) for w in range(cores)]))  # warm-up: imports + first fit
+        list(ex.map(_cpu_worker, [(10_000_000 + w, 1, N_POINTS, N_OBS, KERNEL) for w in range(cores)]))  # warm-up: imports + first fit
         t0 = time.perf_counter()
         lml = [v for part in ex.map(_cpu_worker, tasks) for v in part]
         dt = time.perf_counter() - t0
@@ -86,12 +101,13 @@ def run_reference(args):
             times.append(dt)
     value = per_step * len(times) / sum(times)
     sample = f"{per_step} curves of config #3 per step (N={N_POINTS}, 6 bands, M={N_BANDS * N_OBS}), {cores} processes x 1 BLAS thread"
+    metric = METRIC if args.kernel == "default" else f"light curves/sec GP fit+augment (plasticc workload, {args.kernel} kernel)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "curves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric, "value": value, "unit": "curves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands)", "curves_per_step": per_step,
-                   "n_points": N_POINTS, "n_bands": N_BANDS, "n_obs": N_OBS},
+                   "n_points": N_POINTS, "n_bands": N_BANDS, "n_obs": N_OBS, "kernel": args.kernel},
         "cpu_baseline": {"value": value, "unit": "curves/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,7 +223,7 @@ def run_gpu(args):
     import torch
 
     import fulu_b200
-    from fulu_b200.engine import DeviceBatch, fit_augment_device, pin_batch, pin_results
+    from fulu_b200.engine import DeviceBatch, fit_augment_device, kernel_spec_from_sklearn, pin_batch, pin_results
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -228,10 +244,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     desc, default_b, n_obs = WORKLOADS[args.workload]
-    headline = args.workload == "plasticc"
+    headline = args.workload == "plasticc" and args.kernel == "default"
     # CPU baseline first (rank 0, N=1 only), before this process's CUDA context is busy
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and headline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "plasticc":
         cores = os.cpu_count() or 1
         sample_n = max(2 * cores, min(args.ref_curves, 24 * cores))
         v, dt, cores, _ = cpu_reference_throughput(sample_n, cores)
@@ -240,23 +256,24 @@ def run_gpu(args):
                               "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"}
 
     engine = fulu_b200.GPEngine(torch.device("cuda", local))
+    spec = kernel_spec_from_sklearn(make_kernel(args.kernel))
     B = args.curves or default_b
     host = make_workload(args.workload, B, rank)
     lengths = host.lengths()
     nb = host.n_bands
     pinned = pin_batch(host)
-    pinned_out = pin_results(B, nb, n_obs)
-    dev = DeviceBatch.from_host(host, engine.device, pinned=pinned)
+    pinned_out = pin_results(B, nb, n_obs, spec.n_params)
+    dev = DeviceBatch.from_host(host, engine.device, pinned=pinned, family=spec.family)
     in_bytes = dev.h2d_bytes()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=engine.device)   # > 126 MB L2
 
     def step_resident(profile=False):
         flush.zero_()   # L2 flush between timed iterations (the headline inputs are 28 MB, smaller than L2)
-        return fit_augment_device(engine, dev, lengths, n_obs, profile=profile)
+        return fit_augment_device(engine, dev, lengths, n_obs, spec=spec, profile=profile)
 
     def step_e2e():
         flush.zero_()
-        return fulu_b200.fit_augment_batch(host, n_obs=n_obs, engine=engine, pinned=pinned, out=pinned_out)
+        return fulu_b200.fit_augment_batch(host, n_obs=n_obs, engine=engine, pinned=pinned, out=pinned_out, spec=spec)
 
     for _ in range(args.warmup):
         step_resident()
@@ -336,10 +353,10 @@ def run_gpu(args):
     mean_in = in_bytes / B
     out_bytes = 16 * nb * n_obs + 8 * 4 + 16
     cfg = {"workload": desc, "curves_per_gpu_per_step": B, "n_points": N_POINTS if headline else f"{int(lengths.min())}..{int(lengths.max())} (mean {lengths.mean():.0f})",
-           "n_bands": nb, "n_obs": n_obs, "n_starts": 6,
+           "n_bands": nb, "n_obs": n_obs, "n_starts": 6, "kernel": args.kernel, "n_params": spec.n_params,
            "l2": f"flushed between steps (256 MiB memset); inputs {in_bytes / 1e6:.0f} MB", "parallelism": f"curve-sharded x{world}, no collective"}
     line = {
-        "metric": METRIC if headline else f"light curves/sec GP fit+augment ({args.workload} workload)", "value": value, "unit": "curves/s",
+        "metric": METRIC if headline else f"light curves/sec GP fit+augment ({args.workload} workload, {args.kernel} kernel)", "value": value, "unit": "curves/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
@@ -351,7 +368,7 @@ def run_gpu(args):
                      "frac": achieved / peak_dfma if peak_dfma else None, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": (mean_in + 8 * 4 + 8 * 5) * (evals_all / world) / max(rounds, 1),
                      "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",
-                     "peak_dmma": peak_dmma, "flops_per_eval": (N_POINTS ** 3 + 12 * N_POINTS ** 2) if headline else flops_all / max(evals_all, 1),
+                     "peak_dmma": peak_dmma, "flops_per_eval": (N_POINTS ** 3 + 12 * N_POINTS ** 2) if args.workload == "plasticc" else flops_all / max(evals_all, 1),
                      "evals_per_curve": evals_all / (world * B * args.steps),
                      "eval_kernel_ms_per_step": eval_ms_all / args.steps, "eval_kernel_share_of_step": eval_ms_all / ms_max,
                      "timing": "kernel durations from CUDA events on the launching stream in a separate pass of the same K steps; "
@@ -377,10 +394,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--curves", type=int, default=0, help="curves per GPU per step (default: the workload's own, 10,000 for config #3)")
     ap.add_argument("--workload", default="plasticc", choices=sorted(WORKLOADS), help="plasticc = the headline config #3 (default); ztf = config #4 sample; ddf = config #5")
+    ap.add_argument("--kernel", default="default", choices=["default", "rbf_matern", "notebook", "rbf_rq"],
+                    help="covariance: the reference's default C*RBF+White (headline) or another kernel its users pass (SURVEY 8f-1)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-curves", type=int, default=256, help="CPU sample size per step (bounded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global KERNEL
+    KERNEL = args.kernel
     if args.impl == "reference":
         run_reference(args)
     else:
