@@ -19,11 +19,14 @@
 // produces the block's inverse X_D = L_D^-1 in the same sweep; X_D is what gets stored on the diagonal, so the panel solve is a
 // DMMA product P X_D^T, the triangular inverse finds its diagonal blocks done, and no thread ever holds a whole 8x8 block.
 //
-// Storage (v3).  Only the lower triangle exists: tile (I, J), J <= I < T (T = np / 8, np = N padded to a multiple of 8 with an
-// identity block) lives at 64 (I (I + 1) / 2 + J) doubles, followed by one border tile-row I = T (tiles (T, 0..T-1)) whose row 0
-// carries y^T.  The bordered matrix M = [[L, 0], [z^T, 1]] is what the algorithms act on:
-//   * the panel solves and trailing updates of the Cholesky turn the border row into z^T = (L^-1 y)^T for free,
-//   * the triangular inverse of M has -a^T = -(X^T z)^T in its border row, so alpha = K^-1 y costs nothing extra either.
+// Storage (v5).  Only the lower triangle exists: tile (I, J), J <= I < T lives at 64 (I (I + 1) / 2 + J) doubles, followed by a
+// scratch column of T tiles (the triangular inverse's W).  The matrix that is factored is the BORDERED one, of order N + 1,
+// padded with an identity block to np = 8 T >= N + 1: row N carries y^T (and, in the last diagonal tile, column N carries y),
+// its diagonal entry acts as 1.  So M = [[L, 0], [z^T, 1]] and
+//   * the panel solves and trailing updates of the Cholesky turn row N into z^T = (L^-1 y)^T for free,
+//   * the triangular inverse of M has -a^T = -(X^T z)^T in row N, so alpha = K^-1 y costs nothing extra either,
+// and the border costs no tiles of its own unless N is a multiple of 8 (v3/v4 kept it as a 14th tile-row at N = 100: 12 % of
+// all tile operations for one useful row in eight).
 // K itself is not kept: the gradient pass recomputes K_ij (one exp) where it meets K^-1_ij.  That halves the footprint
 // (N = 100: 55 KB instead of 100 KB), which is what lets four curves be resident per SM instead of two - the evaluation is
 // latency bound (serial 8x8 diagonal factorisations, barriers), so residency is throughput.
@@ -61,7 +64,7 @@ struct alignas(16) GpPair {
 };
 
 struct GpSmem {
-  double* A;      // packed tiles: T (T + 1) / 2 lower tiles, then T border tiles
+  double* A;      // packed tiles: T (T + 1) / 2 lower tiles, then T scratch tiles
   double* u;      // np   x_i0 / l_t
   double* v;      // np   x_i1 / l_lambda
   double* red;    // reduction scratch, GP_RED doubles (32 warps x 6 values)
@@ -69,7 +72,7 @@ struct GpSmem {
   int np, T;
 };
 
-GP_HD int gp_pad(int n) { return (n + GP_NB - 1) / GP_NB * GP_NB; }
+GP_HD int gp_pad(int n) { return (n + GP_NB) / GP_NB * GP_NB; }   // order of the bordered matrix (n + 1), padded to a multiple of 8
 GP_HD size_t gp_mat_doubles(int np) { const size_t T = (size_t)np / GP_NB; return 64 * (T * (T + 1) / 2 + T); }
 GP_HD size_t gp_vec_doubles(int np) { return 2 * (size_t)np + GP_RED + 2; }
 // doubles of shared memory needed for a curve of n observations (matrix + vectors)
@@ -95,7 +98,7 @@ GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
 // ---------------------------------------------------------------------------------------------- tile addressing
 GP_HD int gp_swz(int c) { return ((c & 2) ? 6 : 0) ^ (c & 4); }
 GP_HD int gp_el(int r, int c) { return c * 8 + (r ^ gp_swz(c)); }           // element (r, c) inside a tile
-GP_HD int gp_tile(int I, int J) { return 64 * (I * (I + 1) / 2 + J); }      // tile (I, J), J <= I; border row: I = T
+GP_HD int gp_tile(int I, int J) { return 64 * (I * (I + 1) / 2 + J); }      // tile (I, J), J <= I; scratch column: I = T
 GP_HD int gp_at(int i, int j) { return gp_tile(i >> 3, j >> 3) + gp_el(i & 7, j & 7); }   // matrix element (i, j), j <= i
 // column permutation of the accumulator fragment: register c0 of lane (g, t) holds tile column t, c1 holds column 4 + t
 // (instead of 2t, 2t+1), so that accumulator loads/stores are conflict free too.  B-fragment lane g must then supply
@@ -311,32 +314,35 @@ struct GpKern {
 };
 using GpKernDefault = GpKern<GP_F_NONE, GP_F_NONE>;   // C * RBF([l_t, l_lambda]) + White  (fulu/gp_aug.py:29)
 
-// K into the lower tiles, y^T into row 0 of the border tile-row.  One warp per tile; lane (g, t) writes (g, t) and (g, 4 + t).
+// K into the lower tiles, y^T into row n (and y into column n of the last diagonal tile).  One warp per tile; lane (g, t) writes
+// (g, t) and (g, 4 + t).
 template <class Ctx, class Kern>
 GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Kern& kn) {
-  const int T = s.T, n = cv.n, ntile = T * (T + 1) / 2 + T, g = c.lane >> 2, t = c.lane & 3;
+  const int T = s.T, n = cv.n, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const GpFrag f = gp_frag(c.lane);
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
     double* tp = s.A + 64 * q;
-    const int j0 = 8 * J + t, j1 = j0 + 4;
-    double v0, v1;
-    if (I == T) {            // border: y^T then seven zero rows
-      v0 = (g == 0 && j0 < n) ? cv.y[j0] : 0.0;
-      v1 = (g == 0 && j1 < n) ? cv.y[j1] : 0.0;
-    } else {
-      const int i = 8 * I + g;
-      const double ui = s.u[i], vi = s.v[i];
-      // diagonal tiles are assembled in full (both triangles): the warp-level factorisation keeps them symmetric
-      const double du0 = ui - s.u[j0], dv0 = vi - s.v[j0], du1 = ui - s.u[j1], dv1 = vi - s.v[j1];
-      v0 = kn.value(du0 * du0, dv0 * dv0);
-      v1 = kn.value(du1 * du1, dv1 * dv1);
-      if (i >= n || j0 >= n) v0 = 0.0;
-      if (i >= n || j1 >= n) v1 = 0.0;
-      // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding
-      if (i == j0) v0 = (i < n) ? kn.diag() + cv.al[i] : 1.0;
-      if (i == j1) v1 = (i < n) ? kn.diag() + cv.al[i] : 1.0;
+    const int i = 8 * I + g, j0 = 8 * J + t, j1 = j0 + 4;
+    const double ui = s.u[i], vi = s.v[i];
+    // diagonal tiles are assembled in full (both triangles): the warp-level factorisation keeps them symmetric
+    const double du0 = ui - s.u[j0], dv0 = vi - s.v[j0], du1 = ui - s.u[j1], dv1 = vi - s.v[j1];
+    double v0 = kn.value(du0 * du0, dv0 * dv0);
+    double v1 = kn.value(du1 * du1, dv1 * dv1);
+    if (i >= n || j0 >= n) v0 = 0.0;
+    if (i >= n || j1 >= n) v1 = 0.0;
+    // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding; the border's own diagonal entry
+    // starts at 0 and collects -z.z during the factorisation (its pivot is taken as 1)
+    if (i == j0) v0 = (i < n) ? kn.diag() + cv.al[i] : (i == n ? 0.0 : 1.0);
+    if (i == j1) v1 = (i < n) ? kn.diag() + cv.al[i] : (i == n ? 0.0 : 1.0);
+    // the border: row n = y^T, and its mirror image in the last diagonal tile
+    if (i == n) {
+      if (j0 < n) v0 = cv.y[j0];
+      if (j1 < n) v1 = cv.y[j1];
+    } else if (i < n) {
+      if (j0 == n) v0 = cv.y[i];
+      if (j1 == n) v1 = cv.y[i];
     }
     tp[f.a0] = v0;
     tp[f.a1] = v1;
@@ -387,8 +393,10 @@ GP_DEV void gp_logprod_mul(GpLogProd& lp, double x) {   // x in (1e-300, 1e300)
 }
 GP_DEV double gp_logprod_value(const GpLogProd& lp) { return log(lp.m) + (double)lp.e * 0.6931471805599453; }
 
+// jb: local index of the border row when this block holds it, 8 otherwise.  The border's pivot is taken as 1; what has
+// accumulated in its diagonal entry by then is -z.z (it starts at 0), returned in bq.
 template <class Ctx>
-GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, GpLogProd& rdet) {
+GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, GpLogProd& rdet, int jb, double& bq) {
   const int g = c.lane >> 2, t = c.lane & 3;
   z0 = (g == t) ? 1.0 : 0.0;
   z1 = (g == 4 + t) ? 1.0 : 0.0;
@@ -398,7 +406,9 @@ GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, 
   for (int j = 0; j < 8; ++j) {
     const int jt = j & 3;
     const double aj = (j < 4) ? a0 : a1;           // this lane's entry of block column (j & 3) / (4 + (j & 3))
-    const double d = c.shfl(aj, 4 * j + jt);        // A[j][j]
+    const double dj = c.shfl(aj, 4 * j + jt);       // A[j][j]
+    const double d = (j == jb) ? 1.0 : dj;
+    if (j == jb) bq = dj;
     const double cg = c.shfl(aj, 4 * g + jt);       // A[g][j]
     const double c0 = c.shfl(aj, 4 * t + jt);       // A[t][j]
     const double c1 = c.shfl(aj, 4 * (4 + t) + jt); // A[4 + t][j]
@@ -427,15 +437,15 @@ GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, 
   return ok;
 }
 
-// rows below the diagonal tile kb (border tile included): P_I <- P_I X_D^T, the panel solve x L_D^T = p as a DMMA product
+// rows below the diagonal tile kb: P_I <- P_I X_D^T, the panel solve x L_D^T = p as a DMMA product
 // with the inverted diagonal block.  One tile per warp at a time.
 template <class Ctx>
 GP_DEV void gp_panel_mult(Ctx& c, const GpSmem& s, const GpFrag& f, int kb) {
   const int T = s.T;
-  if (kb + 1 + c.warp > T) return;
+  if (kb + 1 + c.warp >= T) return;
   const double* D = s.A + gp_tile(kb, kb);
   const double b0 = D[f.b0], b1 = D[f.b1];   // B[k][n] = X_D[n][k]
-  for (int I = kb + 1 + c.warp; I <= T; I += c.nwarp) {
+  for (int I = kb + 1 + c.warp; I < T; I += c.nwarp) {
     double* tp = s.A + gp_tile(I, kb);
     double w0 = 0.0, w1 = 0.0;
     c.mma(w0, w1, tp[f.a0], b0);
@@ -480,13 +490,13 @@ GP_DEV void gp_chol_accumulate(Ctx& c, const GpSmem& s, const GpFrag& f, int k, 
   acc[0][0] += d10; acc[0][1] += d11;
 }
 
-// rows I = first, first + stride, ... <= T of block column k: apply the terms [J0, J1) and store (two rows per pass)
+// rows I = first, first + stride, ... < T of block column k: apply the terms [J0, J1) and store (two rows per pass)
 template <class Ctx>
 GP_DEV void gp_chol_update_rows(Ctx& c, const GpSmem& s, const GpFrag& f, int k, int first, int stride, int J0, int J1) {
   const int T = s.T;
   double acc[2][2];
-  for (int I = first; I <= T; I += 2 * stride) {
-    const int I2 = (I + stride <= T) ? I + stride : -1;
+  for (int I = first; I < T; I += 2 * stride) {
+    const int I2 = (I + stride < T) ? I + stride : -1;
     gp_chol_accumulate(c, s, f, k, I, I2, J0, J1, acc);
     double* C1 = s.A + gp_tile(I, k);
     C1[f.a0] = acc[0][0];
@@ -507,11 +517,12 @@ GP_DEV void gp_chol_update_rows(Ctx& c, const GpSmem& s, const GpFrag& f, int k,
 //   barrier; the rows of block column kb are multiplied by the inverted diagonal block; barrier.
 // So the critical path of a step is one tile update + the 8x8 factorisation, as in a right-looking sweep, while each tile of
 // the matrix is loaded and stored twice instead of once per step.  Sets flag on breakdown.  On exit the strictly-lower tiles
-// hold L, the diagonal tiles hold the INVERSES of L's diagonal blocks, row 0 of the border tile-row holds z^T = (L^-1 y)^T,
-// and logdet (valid in thread 0, zero elsewhere) = sum_i log L_ii.
+// hold L, the diagonal tiles hold the INVERSES of L's diagonal blocks, row n holds z^T = (L^-1 y)^T (left of the last diagonal
+// tile), and logdet = sum_i log L_ii, quad = z.z = y^T K^-1 y (both valid in thread 0, zero elsewhere).
 template <class Ctx>
-GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, double& logdet) {
+GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, int n, double& logdet, double& quad) {
   const int T = s.T;
+  double bq = 0.0;
   const GpFrag f = gp_frag(c.lane);
   GpLogProd rdet;
   rdet.m = 1.0;
@@ -525,7 +536,7 @@ GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, double& logdet) {
       double acc[2][2], z0, z1;
       const long long t0 = c.clock();
       gp_chol_accumulate(c, s, f, kb, kb, -1, Jlast, kb, acc);
-      if (!gp_chol8_warp(c, acc[0][0], acc[0][1], z0, z1, rdet) && c.lane == 0) s.flag[0] = 1;
+      if (!gp_chol8_warp(c, acc[0][0], acc[0][1], z0, z1, rdet, kb == T - 1 ? (n & 7) : 8, bq) && c.lane == 0) s.flag[0] = 1;
       double* D = s.A + gp_tile(kb, kb);
       D[f.a0] = z0;
       D[f.a1] = z1;
@@ -541,72 +552,53 @@ GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, double& logdet) {
   }
   c.mark_value(9, tdiag);   // diagnostics: cycles warp 0 spent on the diagonal tiles
   logdet = (c.tid == 0) ? -gp_logprod_value(rdet) : 0.0;
-}
-
-// After gp_cholesky: this thread's share of z.z (= y^T K^-1 y).
-template <class Ctx>
-GP_DEV double gp_collect(Ctx& c, const GpSmem& s) {
-  const int np = s.np, T = s.T;
-  double quad = 0.0;
-  for (int i = c.tid; i < np; i += c.nthr) {
-    const double zi = s.A[gp_tile(T, i >> 3) + gp_el(0, i & 7)];
-    quad += zi * zi;
-  }
-  return quad;
+  quad = (c.tid == 0) ? -bq : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------- triangular inverse
-// In place: M = [[L, 0], [z^T, 1]] -> M^-1 = [[X, 0], [-a^T, 1]], block columns from the last to the first.  For block column
-// kb with rows I in (kb, T]:   W_I = -M_I,kb X_kb,kb (in place), then X_I,kb = sum_{kb < K <= I} X_I,K W_K, written over W_I.
-// Row I only reads W_K with K <= I, so rows are finished from the bottom up in waves of one row per warp, with one barrier
-// between a wave's reads and its stores; no scratch is needed.
+// M = [[L, 0], [z^T, 1]] -> M^-1 = [[X, 0], [-a^T, 1]], block columns from the last to the first.  For block column kb with
+// rows I in (kb, T):   W_I = -M_I,kb X_kb,kb goes to the scratch column, then X_I,kb = sum_{kb < K <= I} X_I,K W_K replaces
+// M_I,kb.  Reading W from scratch instead of in place removes every hazard between rows: two barriers per block column
+// (v4 finished the rows in waves of one per warp with a barrier each - 58 barriers at T = 13 instead of 26).
 template <class Ctx>
 GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
   const int T = s.T;
   double* A = s.A;
+  double* W = A + gp_tile(T, 0);   // scratch column: W_I at 64 I
   const GpFrag f = gp_frag(c.lane);
   // (the diagonal tiles already hold the inverted diagonal blocks: gp_cholesky)
-  for (int kb = T - 1; kb >= 0; --kb) {
+  for (int kb = T - 2; kb >= 0; --kb) {
     // (1) W_I = -(M_I,kb X11)
     {
       const double* X11 = A + gp_tile(kb, kb);
       const double b0 = X11[f.p0], b1 = X11[f.p1];
-      for (int I = kb + 1 + c.warp; I <= T; I += c.nwarp) {
-        double* tp = A + gp_tile(I, kb);
+      for (int I = kb + 1 + c.warp; I < T; I += c.nwarp) {
+        const double* tp = A + gp_tile(I, kb);
         double w0 = 0.0, w1 = 0.0;
         c.mma(w0, w1, -tp[f.a0], b0);
         c.mma(w0, w1, -tp[f.a1], b1);
-        tp[f.a0] = w0;
-        tp[f.a1] = w1;
+        W[64 * I + f.a0] = w0;
+        W[64 * I + f.a1] = w1;
       }
     }
     c.sync();
-    // (2) waves of rows, bottom up
-    for (int Itop = T; Itop > kb; Itop -= c.nwarp) {
-      const int I = Itop - c.warp;
+    // (2) the rows, longest first (row I costs I - kb tile products)
+    for (int I = T - 1 - c.warp; I > kb; I -= c.nwarp) {
       double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-      if (I > kb) {
-        const double* Xr = A + gp_tile(I, kb + 1);   // X_I,K for K = kb + 1 ..
-        const double* Wk = A + gp_tile(kb + 1, kb);  // W_K: next K is (K + 1) tiles further
-        int K = kb + 1;
-        const int Kend = (I == T) ? T : I + 1;       // the border's own diagonal tile is the identity
-        for (; K < Kend; ++K) {
-          c.mma(p0, p1, Xr[f.a0], Wk[f.p0]);
-          c.mma(q0, q1, Xr[f.a1], Wk[f.p1]);
-          Xr += 64;
-          Wk += 64 * (K + 1);
-        }
-        if (I == T) { p0 += Wk[f.a0]; p1 += Wk[f.a1]; }   // Wk now points at W_T
+      const double* Xr = A + gp_tile(I, kb + 1);   // X_I,K for K = kb + 1 .. I
+      const double* Wk = W + 64 * (kb + 1);
+      for (int K = kb + 1; K <= I; ++K) {
+        c.mma(p0, p1, Xr[f.a0], Wk[f.p0]);
+        c.mma(q0, q1, Xr[f.a1], Wk[f.p1]);
+        Xr += 64;
+        Wk += 64;
       }
-      c.sync();
-      if (I > kb) {
-        double* O = A + gp_tile(I, kb);
-        O[f.a0] = p0 + q0;
-        O[f.a1] = p1 + q1;
-      }
+      double* O = A + gp_tile(I, kb);
+      O[f.a0] = p0 + q0;
+      O[f.a1] = p1 + q1;
     }
+    c.sync();
   }
-  c.sync();
 }
 
 // Fused K^-1 = X^T X (8x8 DMMA tiles), recomputed K and gradient traces.  tr[k] = sum_{i>j} W_ij dK_ij/dtheta_k for the
@@ -614,11 +606,12 @@ GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
 // scaled time / wavelength differences), trd = sum_i W_ii  (W = alpha alpha^T - K^-1).
 template <class Ctx, class Kern>
 GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, double (&tr)[Kern::NTR], double& trd) {
-  const int T = s.T, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
+  const int T = s.T, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3, rb = n & 7;
   const double* A = s.A;
   const GpFrag f = gp_frag(c.lane);
-  const double* bord = A + gp_tile(T, 0);
-  const int ob_g = gp_el(0, g), ob_0 = gp_el(0, 2 * t), ob_1 = gp_el(0, 2 * t + 1);
+  const double* bord = A + gp_tile(T - 1, 0);   // row n of M^-1 holds -alpha
+  const int ob_g = gp_el(rb, g), ob_0 = gp_el(rb, 2 * t), ob_1 = gp_el(rb, 2 * t + 1);
+  const bool brow0 = (t == rb), brow1 = (4 + t == rb);   // this lane's k-rows of a tile that are the border row
 #pragma unroll
   for (int k = 0; k < Kern::NTR; ++k) tr[k] = 0.0;
   trd = 0.0;
@@ -626,16 +619,18 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
   while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-    // K^-1[i][j] = sum_{k >= i} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
-    // the diagonal tiles of X carry explicit zeros above the diagonal
+    // K^-1[i][j] = sum_{k >= i, k != n} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
+    // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
     const double* Xi = A + gp_tile(I, I);
     const double* Xj = A + gp_tile(I, J);
-    for (int K = I; K < T; ++K) {
+    for (int K = I; K < T - 1; ++K) {
       c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
       c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
       Xi += 64 * (K + 1);
       Xj += 64 * (K + 1);
     }
+    c.mma(p0, p1, brow0 ? 0.0 : Xi[f.t0], Xj[f.t0]);
+    c.mma(q0, q1, brow1 ? 0.0 : Xi[f.t1], Xj[f.t1]);
     // epilogue: lane (g, t) owns (i, j) = (i0 + g, j0 + 2t) and (i0 + g, j0 + 2t + 1)
     const int i = 8 * I + g, j = 8 * J + 2 * t;
     const double ai = bord[64 * I + ob_g], ui = s.u[i], vi = s.v[i];                 // (the border row holds -alpha)
@@ -665,12 +660,17 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
   gp_load_curve(c, cv, s, kn.lt, kn.ll);
   c.sync();
   c.mark(1);
-  gp_assemble(c, cv, s, kn);
+  // GP_WHATIF (profiling builds only, scripts/gpu_whatif.sh): bit k set = phase k left out, to measure its marginal cost under load
+#ifndef GP_WHATIF
+#define GP_WHATIF 0
+#endif
+  if (!(GP_WHATIF & 1)) gp_assemble(c, cv, s, kn);
   c.sync();
   c.mark(2);
   constexpr int NT = Kern::NTR;
   double v[NT + 3];   // traces, trd, quadratic form, log-determinant
-  gp_cholesky(c, s, v[NT + 2]);
+  if (!(GP_WHATIF & 2)) gp_cholesky(c, s, cv.n, v[NT + 2], v[NT + 1]);
+  else { v[NT + 2] = 0.0; v[NT + 1] = 0.0; }
   c.mark(3);
   ok = (s.flag[0] == 0);
   if (!ok) {
@@ -679,14 +679,14 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
     c.sync();
     return;
   }
-  v[NT + 1] = gp_collect(c, s);   // the border row is next written after the inverse's first barrier
   c.mark(4);
-  gp_trtri(c, s);
+  if (!(GP_WHATIF & 4)) gp_trtri(c, s);
   c.mark(5);
   c.mark(6);
   {
     double tr[NT];
-    gp_inverse_traces(c, s, cv.n, kn, tr, v[NT]);
+    if (!(GP_WHATIF & 8)) gp_inverse_traces(c, s, cv.n, kn, tr, v[NT]);
+    else { for (int k = 0; k < NT; ++k) tr[k] = 0.0; v[NT] = 0.0; }
 #pragma unroll
     for (int k = 0; k < NT; ++k) v[k] = tr[k];
   }
@@ -707,20 +707,19 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const Kern& kn, const GpSme
   gp_assemble(c, cv, s, kn);
   c.sync();
   double v[2];
-  gp_cholesky(c, s, v[1]);
+  gp_cholesky(c, s, cv.n, v[1], v[0]);
   ok = (s.flag[0] == 0);
   if (!ok) { lml = -INFINITY; c.sync(); return; }
-  v[0] = gp_collect(c, s);
   gp_block_sum(c, v, s.red);
   lml = -0.5 * v[0] - v[1] - 0.5 * (double)cv.n * GP_LOG_2PI;
 }
 
 // ---------------------------------------------------------------------------------------------- prediction
-// Query points against a factored curve (lower tiles = L, border row = z^T), one query point per thread:
+// Query points against a factored curve (lower tiles = L, row n = z^T), one query point per thread:
 //   k*_i = c exp(-1/2 |x*/l - x_i/l|^2)          (kernels.py:1569-1570; White contributes 0 off the training set)
 //   v    = L^-1 k*  by forward substitution       (_gpr.py:460-462: solve_triangular, NOT an explicit inverse - at noise
 //                                                  levels of 1e-5 the explicit-inverse product loses ~40x in the variance)
-//   mean* = k*.alpha = v.z                        (_gpr.py:446-447)
+//   mean* = k*.alpha = v.z                        (_gpr.py:446-447; falls out of the border row of the substitution)
 //   |v|^2 -> var = (c + s2) - |v|^2               (_gpr.py:480-481)
 // Each thread owns column q of V (V[i * ldv + q]).  Block substitution over the 8x8 tiles: v_I = X_II (k*_I - sum_{J<I} L_IJ v_J)
 // with X_II = L_II^-1 from gp_cholesky (explicit inverses only of the 8x8 diagonal blocks; between blocks it is substitution).
@@ -729,9 +728,8 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const Kern& kn, const GpSme
 template <class Kern>
 GP_DEV void gp_predict_column(const GpSmem& s, int n, const Kern& kn, double uq, double vq, double* V, int ldv, double& mean, double& v2) {
   const double* A = s.A;
-  const double* bord = A + gp_tile(s.T, 0);
   double m = 0.0, q2 = 0.0;
-  for (int I = 0; 8 * I < n; ++I) {
+  for (int I = 0; I < s.T; ++I) {
     double acc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -751,15 +749,21 @@ GP_DEV void gp_predict_column(const GpSmem& s, int n, const Kern& kn, double uq,
       row += 64;
       vp += 8 * ldv;
     }
-    // `row` is the diagonal tile now: X_II, lower triangular
+    // `row` is the diagonal tile now: X_II, lower triangular.  The border row of the bordered system M [v; mu] = [k*; 0]
+    // solves to mu = -z.v = -mean, so the mean needs no pass of its own; rows past the border are padding.
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       double a = 0.0;
 #pragma unroll
       for (int k = 0; k <= r; ++k) a += row[gp_el(r, k)] * acc[k];
-      vp[r * ldv] = a;
-      m += a * bord[64 * I + gp_el(0, r)];
-      q2 += a * a;
+      const int i = 8 * I + r;
+      if (i < n) {
+        vp[r * ldv] = a;
+        q2 += a * a;
+      } else {
+        vp[r * ldv] = 0.0;
+        if (i == n) m = -a;
+      }
     }
   }
   mean = m;

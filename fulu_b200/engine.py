@@ -414,7 +414,9 @@ class GPEngine:
 # ------------------------------------------------------------------------------------------------ batched entry point
 # upper bounds of the length classes one launch covers: the class bound (not the batch's own maximum) fixes the launch geometry
 # (shared memory, CTAs per SM, threads per CTA), so a curve's result does not depend on what else is in the batch
-N_BUCKETS = (32, 64, 104, 128, 160, 216, 304, 512, 1024, 2048, 4096)
+# (bounds are 8k - 1: the factored matrix is the bordered one of order N + 1, padded to a multiple of 8; N <= 223 lives in shared
+# memory; 1031 / 1543 / 2055 keep config #5's N = 1024 / 1536 / 2048 in tight classes)
+N_BUCKETS = (31, 63, 103, 127, 159, 223, 303, 511, 1031, 1543, 2055, 4095)
 
 
 @dataclass

@@ -153,9 +153,9 @@ def test_fixed_theta_prediction_against_live_sklearn(engine):
         assert abs(float(out["lml"][i]) - ref.reg.log_marginal_likelihood_value_) < 1e-9 * max(1, abs(ref.reg.log_marginal_likelihood_value_))
 
 
-@pytest.mark.parametrize("n", [164, 216, 217, 300])
+@pytest.mark.parametrize("n", [164, 216, 223, 224, 300])
 def test_long_curves_use_the_global_memory_path(engine, n):
-    """Around and above the shared-memory limit (N = 216): K lives in an L2-resident slab; same numbers as the oracle."""
+    """Around and above the shared-memory limit (N = 223): K lives in an L2-resident slab; same numbers as the oracle."""
     from fulu_b200 import DeviceBatch, datasets
     from oracle import gp_oracle as O
 
