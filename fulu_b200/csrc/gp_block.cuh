@@ -68,13 +68,14 @@ struct GpSmem {
   double* u;      // np   x_i0 / l_t
   double* v;      // np   x_i1 / l_lambda
   double* red;    // reduction scratch, GP_RED doubles (32 warps x 6 values)
+  double* tab;    // [0..15] c 2^(j/16), [16..31] 2^(j/16): the exponential's table (gp_exp_tab), rebuilt per evaluation
   int* flag;      // [0] = Cholesky breakdown
   int np, T;
 };
 
 GP_HD int gp_pad(int n) { return (n + GP_NB) / GP_NB * GP_NB; }   // order of the bordered matrix (n + 1), padded to a multiple of 8
 GP_HD size_t gp_mat_doubles(int np) { const size_t T = (size_t)np / GP_NB; return 64 * (T * (T + 1) / 2 + T); }
-GP_HD size_t gp_vec_doubles(int np) { return 2 * (size_t)np + GP_RED + 2; }
+GP_HD size_t gp_vec_doubles(int np) { return 2 * (size_t)np + GP_RED + 32 + 2; }
 // doubles of shared memory needed for a curve of n observations (matrix + vectors)
 GP_HD size_t gp_smem_doubles(int n) {
   const int np = gp_pad(n);
@@ -91,6 +92,7 @@ GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
   s.u = p; p += s.np;
   s.v = p; p += s.np;
   s.red = p; p += GP_RED;
+  s.tab = p; p += 32;
   s.flag = (int*)p;
   return s;
 }
@@ -146,22 +148,14 @@ GP_DEV void gp_block_sum(Ctx& c, double (&v)[K], double* red) {
 }
 
 // ---------------------------------------------------------------------------------------------- load + assemble
-template <class Ctx>
-GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, double lt, double ll) {
-  for (int i = c.tid; i < s.np; i += c.nthr) {
-    if (i < cv.n) {
-      s.u[i] = cv.xs[i] / lt;              // X / length_scale  (kernels.py:1561)
-      s.v[i] = cv.lam[cv.band[i]] / ll;
-    } else {
-      s.u[i] = 0.0; s.v[i] = 0.0;
-    }
-  }
-  if (c.tid == 0) s.flag[0] = 0;
-}
-
-// exp(x) for x <= 0, branch free so that several evaluations interleave: k = rint(x log2 e), r = x - k ln 2 (two-part
-// constant), degree-13 Taylor polynomial on |r| <= 0.347, 2^k by exponent arithmetic; results below 2^-1021 flush to zero.
-// Maximum error 0.63 ulp over [-708, 0] (tests/test_block_host.py::test_exp_neg_accuracy); the library exp is 0.5 ulp.
+// exp(x) for x <= 0, branch free so that several evaluations interleave.  x = (16 k + j) ln2/16 + r, |r| <= ln2/32:
+//   exp(x) = 2^k * 2^(j/16) * exp(r),  n = 16 k + j = rint(x 16/ln2) read from the low word of x 16/ln2 + 1.5 2^52,
+//   r = x - n ln2/16 with a two-part constant, exp(r) a degree-7 Taylor polynomial (remainder 1.2e-18), 2^k by exponent arithmetic.
+// The 16-entry table sits in shared memory (128 bytes = every bank once: any 32 lookups are conflict free) and may carry a
+// constant factor (the kernel amplitude c), which saves the multiplication by it; arguments below xmin give 0 (xmin keeps
+// 2^k * tab[j] clear of the subnormal range).  12 FP64 operations where the table-free degree-13 version needed 18 - the
+// exponential is a quarter of the FP64 pipe's time in an evaluation.  Error <= 1.6 ulp over [-690, 0]
+// (tests/test_block_host.py::test_exp_accuracy; the library exp is 0.5 ulp).
 #if defined(__CUDACC__)
 #define GP_CONST __constant__
 #else
@@ -169,33 +163,39 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, double
 #endif
 // constants live in constant memory on the device: FP64 instructions take constant-bank operands directly, while immediates
 // would each cost two register moves
-GP_CONST double gp_exp_c[18] = {
-    1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
-    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
-    2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664,
-    0.16666666666666666, 0.5, 1.0, -708.0};
+GP_CONST double gp_exp2_tab[16] = {1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484,
+                                   1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407,
+                                   1.6104903319492543, 1.681792830507429, 1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+GP_CONST double gp_exp_c[11] = {23.083120654223414, 6755399441055744.0, -0.04332169877307024, -1.1926343307941173e-11,
+                                0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664,
+                                0.16666666666666666, 0.5, 1.0};
+#define GP_EXP_XMIN (-690.0)
 
-GP_DEV double gp_exp_neg(double x) {
-  const double t = fma(x, gp_exp_c[0], gp_exp_c[1]);   // low word of t = k
+GP_DEV double gp_exp_tab(double x, const double* tab, double xmin) {
+  const double t = fma(x, gp_exp_c[0], gp_exp_c[1]);   // low word of t = n
   const double kf = t - gp_exp_c[1];
   double r = fma(kf, gp_exp_c[2], x);
   r = fma(kf, gp_exp_c[3], r);
   double p = gp_exp_c[4];
 #pragma unroll
-  for (int i = 5; i <= 15; ++i) p = fma(p, r, gp_exp_c[i]);
-  p = fma(p, r, gp_exp_c[16]);
-  p = fma(p, r, gp_exp_c[16]);
+  for (int i = 5; i <= 9; ++i) p = fma(p, r, gp_exp_c[i]);
+  p = fma(p, r, gp_exp_c[10]);
+  p = fma(p, r, gp_exp_c[10]);
 #if defined(__CUDA_ARCH__)
-  const double res = __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+  const int n = __double2loint(t);
+  p *= tab[n & 15];
+  const double res = __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
 #else
   int64_t tb, pb;
   memcpy(&tb, &t, 8);
+  const int32_t n = (int32_t)(tb & 0xffffffff);
+  p *= tab[n & 15];
   memcpy(&pb, &p, 8);
-  pb += (int64_t)(int32_t)(tb & 0xffffffff) << 52;
+  pb += (int64_t)(n >> 4) << 52;
   double res;
   memcpy(&res, &pb, 8);
 #endif
-  return x < gp_exp_c[17] ? 0.0 : res;
+  return x < xmin ? 0.0 : res;
 }
 
 // ---------------------------------------------------------------------------------------------- covariance families
@@ -218,6 +218,7 @@ template <int KIND>
 struct GpIso {
   double au, av;   // r^2 = au du^2 + av dv^2
   double alpha;    // RationalQuadratic scale mixture
+  const double* tab;   // 2^(j/16) (GpSmem::tab + 16)
   GP_DEV void init(double lt, double ll, double l, double al) {
     const double ru = lt / l, rv = ll / l;
     au = ru * ru; av = rv * rv; alpha = al;
@@ -229,19 +230,19 @@ struct GpIso {
     gl = 0.0; ga = 0.0;
     if constexpr (KIND == GP_F_MAT05) {
       const double r = gp_sqrt_pos(s);
-      k = gp_exp_neg(-r);
+      k = gp_exp_tab(-r, tab, GP_EXP_XMIN);
       if (GRAD) gl = k * r;
     } else if constexpr (KIND == GP_F_MAT15) {
-      const double a = gp_sqrt_pos(3.0 * s), e = gp_exp_neg(-a);
+      const double a = gp_sqrt_pos(3.0 * s), e = gp_exp_tab(-a, tab, GP_EXP_XMIN);
       k = (1.0 + a) * e;
       if (GRAD) gl = 3.0 * s * e;
     } else if constexpr (KIND == GP_F_MAT25) {
-      const double a = gp_sqrt_pos(5.0 * s), e = gp_exp_neg(-a);
+      const double a = gp_sqrt_pos(5.0 * s), e = gp_exp_tab(-a, tab, GP_EXP_XMIN);
       k = (1.0 + a + a * a / 3.0) * e;
       if (GRAD) gl = (5.0 / 3.0) * s * (a + 1.0) * e;
     } else if constexpr (KIND == GP_F_RQ) {
       const double base = 1.0 + s / (2.0 * alpha), lb = log(base);
-      k = gp_exp_neg(-alpha * lb);
+      k = gp_exp_tab(-alpha * lb, tab, GP_EXP_XMIN);
       if (GRAD) {
         gl = s * k / base;
         ga = k * (s / (2.0 * base) - alpha * lb);
@@ -260,6 +261,8 @@ struct GpKern {
   static constexpr int P = 4 + NF1 + NEX;   // hyperparameters
   static constexpr int NTR = P - 1;         // traces over the strictly-lower pairs: every parameter but the noise level
   double cst, s2, lt, ll;
+  double xminc;        // arguments of the amplitude-scaled exponential below this give 0
+  const double* tabc;  // c 2^(j/16) (GpSmem::tab)
   GpIso<F1> f1;
   GpIso<EX> ex;
 
@@ -268,13 +271,14 @@ struct GpKern {
     lt = exp(theta[1 + NF1]);
     ll = exp(theta[2 + NF1]);
     s2 = exp(theta[P - 1]);
+    xminc = GP_EXP_XMIN + fmax(0.0, -theta[0]);
     if constexpr (NF1 > 0) f1.init(lt, ll, exp(theta[1]), 0.0);
     if constexpr (EX == GP_F_RQ) ex.init(lt, ll, exp(theta[4 + NF1]), exp(theta[3 + NF1]));   // sklearn orders alpha before length_scale
     else if constexpr (NEX > 0) ex.init(lt, ll, exp(theta[3 + NF1]), 0.0);
   }
   // K_ij, i != j, from the squared scaled differences
   GP_DEV double value(double du2, double dv2) const {
-    double k = cst * gp_exp_neg(-0.5 * (du2 + dv2));
+    double k = gp_exp_tab(-0.5 * (du2 + dv2), tabc, xminc);   // c exp(.)
     double f, g0, g1;
     if constexpr (NF1 > 0) { f1.template eval<false>(du2, dv2, f, g0, g1); k *= f; }
     if constexpr (NEX > 0) { ex.template eval<false>(du2, dv2, f, g0, g1); k += f; }
@@ -284,7 +288,7 @@ struct GpKern {
   GP_DEV double diag() const { return NEX ? (cst + 1.0) + s2 : cst + s2; }
   // tr[k] += w dK_ij / dtheta_k for the NTR parameters that act off the diagonal
   GP_DEV void accumulate(double w, double du2, double dv2, double (&tr)[NTR]) const {
-    const double e = cst * gp_exp_neg(-0.5 * (du2 + dv2));
+    const double e = gp_exp_tab(-0.5 * (du2 + dv2), tabc, xminc);   // c exp(.)
     double f, gl, ga;
     if constexpr (NF1 > 0) {
       f1.template eval<true>(du2, dv2, f, gl, ga);
@@ -313,6 +317,25 @@ struct GpKern {
   }
 };
 using GpKernDefault = GpKern<GP_F_NONE, GP_F_NONE>;   // C * RBF([l_t, l_lambda]) + White  (fulu/gp_aug.py:29)
+
+// Scaled coordinates and the exponential's tables into shared memory; binds the kernel to the tables.
+template <class Ctx, class Kern>
+GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, Kern& kn) {
+  const double lt = kn.lt, ll = kn.ll;
+  kn.tabc = s.tab;
+  kn.f1.tab = s.tab + 16;
+  kn.ex.tab = s.tab + 16;
+  if (c.tid < 32) s.tab[c.tid] = (c.tid < 16 ? kn.cst : 1.0) * gp_exp2_tab[c.tid & 15];
+  for (int i = c.tid; i < s.np; i += c.nthr) {
+    if (i < cv.n) {
+      s.u[i] = cv.xs[i] / lt;              // X / length_scale  (kernels.py:1561)
+      s.v[i] = cv.lam[cv.band[i]] / ll;
+    } else {
+      s.u[i] = 0.0; s.v[i] = 0.0;
+    }
+  }
+  if (c.tid == 0) s.flag[0] = 0;
+}
 
 // K into the lower tiles, y^T into row n (and y into column n of the last diagonal tile).  One warp per tile; lane (g, t) writes
 // (g, t) and (g, 4 + t).
@@ -657,7 +680,7 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
   Kern kn;
   kn.init(theta);
   c.mark(0);
-  gp_load_curve(c, cv, s, kn.lt, kn.ll);
+  gp_load_curve(c, cv, s, kn);
   c.sync();
   c.mark(1);
   // GP_WHATIF (profiling builds only, scripts/gpu_whatif.sh): bit k set = phase k left out, to measure its marginal cost under load
@@ -701,8 +724,8 @@ GP_DEV void gp_eval_lml_grad(Ctx& c, const GpCurveView& cv, const double* theta,
 // L_ = chol(K(theta)) and z = L^-1 y (_gpr.py:349-367; alpha_ = L^-T z is never needed: mean* = v.z with v = L^-1 k*).
 // Returns LML as a by-product.
 template <class Ctx, class Kern>
-GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, const Kern& kn, const GpSmem& s, double& lml, bool& ok) {
-  gp_load_curve(c, cv, s, kn.lt, kn.ll);
+GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, Kern& kn, const GpSmem& s, double& lml, bool& ok) {
+  gp_load_curve(c, cv, s, kn);
   c.sync();
   gp_assemble(c, cv, s, kn);
   c.sync();

@@ -137,5 +137,5 @@ extern "C" int host_gp_predict(int family, int n, const double* xs, const int32_
 }
 
 extern "C" void host_gp_exp_neg(int n, const double* x, double* out) {
-  for (int i = 0; i < n; ++i) out[i] = gp_exp_neg(x[i]);
+  for (int i = 0; i < n; ++i) out[i] = gp_exp_tab(x[i], gp_exp2_tab, GP_EXP_XMIN);
 }
