@@ -344,9 +344,9 @@ def run_gpu(args):
     traffic, traffic_src = None, None
     if headline:
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_eval_kernel_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v5_eval_kernel_traffic.json")))
             traffic = tj["dram_bytes_per_evaluation"] * (evals_all / world) / max(rounds, 1)
-            traffic_src = ("profiles/r01_v4_eval_kernel_traffic.json (dram__bytes_read+write per evaluation, ncu --set full) x evaluations "
+            traffic_src = ("profiles/r01_v5_eval_kernel_traffic.json (dram__bytes_read+write per evaluation, ncu --set full) x evaluations "
                            "per launch of this run")
         except (OSError, KeyError, ValueError):
             pass
