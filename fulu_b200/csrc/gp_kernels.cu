@@ -251,6 +251,143 @@ __global__ void export_stats_kernel(int64_t B, const int32_t* order, const doubl
   if (ynorm) { ynorm[cu * 2] = stats[cu * 6 + 4]; ynorm[cu * 2 + 1] = stats[cu * 6 + 5]; }
 }
 
+// ------------------------------------------------------------------------------------------------ downstream consumer: band sum + peak
+// One warp per curve: the augmented curve summed over the passbands at each grid time (bands added in table order, as pandas'
+// groupby("time").sum() meets them in the band-major frame), and its first maximum (Series.argmax; NaNs are skipped).
+struct PeakArgs {
+  int64_t B;
+  const int32_t* order;
+  const int64_t* offsets;
+  const double* t_raw;
+  const double *mean, *t_min, *t_max;
+  int n_bands, n_obs;
+  double *sum_flux, *peak_t, *peak_flux;
+  int32_t* peak_index;
+};
+
+__global__ void __launch_bounds__(256) peak_kernel(PeakArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (k >= a.B) return;
+  const int64_t cu = a.order ? (int64_t)a.order[k] : k;
+  const double* m = a.mean + cu * (int64_t)a.n_bands * a.n_obs;
+  double best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int q = lane; q < a.n_obs; q += 32) {
+    double sum = m[q];
+    for (int b = 1; b < a.n_bands; ++b) sum += m[(int64_t)b * a.n_obs + q];
+    if (a.sum_flux) a.sum_flux[cu * a.n_obs + q] = sum;
+    if (sum > best) { best = sum; bi = q; }   // strictly greater: the first maximum of this lane's points (they ascend)
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) {
+    double lo, hi;
+    if (a.t_min && a.t_max) { lo = a.t_min[cu]; hi = a.t_max[cu]; }
+    else {
+      const double* tr = a.t_raw + a.offsets[cu];
+      const int n = (int)(a.offsets[cu + 1] - a.offsets[cu]);
+      lo = hi = n > 0 ? tr[0] : 0.0;
+      for (int i = 1; i < n; ++i) { lo = fmin(lo, tr[i]); hi = fmax(hi, tr[i]); }
+    }
+    const bool found = bi != 0x7fffffff;
+    a.peak_index[cu] = found ? bi : -1;
+    a.peak_flux[cu] = found ? best : NAN;
+    a.peak_t[cu] = found ? gp_linspace(lo, hi, a.n_obs, bi) : NAN;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ingest: object-grouped table -> CSR
+// Rows of one object are contiguous (PLAsTiCC / ZTF tables, notebook_examples/object_34299.csv).  A row is a head when its object
+// id differs from the previous row's; offsets = positions of the heads.  Three passes over the id column (12 bytes read and 4
+// written per row in all, HBM bound): heads per 1024-row chunk, an exclusive scan of the chunk counts by one block, the write.
+constexpr int kIngestThreads = 256, kIngestRows = 1024;
+
+__device__ __forceinline__ bool is_head(const int64_t* id, int64_t i) { return i == 0 || id[i] != id[i - 1]; }
+
+__global__ void __launch_bounds__(kIngestThreads) ingest_count_kernel(int64_t n_rows, const int64_t* id, int64_t* chunk_count) {
+  __shared__ int wsum[kIngestThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kIngestRows;
+  int c = 0;
+  for (int r = threadIdx.x; r < kIngestRows; r += kIngestThreads) {
+    const int64_t i = base + r;
+    if (i < n_rows && is_head(id, i)) ++c;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kIngestThreads / 32; ++w) t += wsum[w];
+    chunk_count[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) ingest_scan_kernel(int64_t n_chunks, int64_t* chunk_count, int64_t* n_objects) {
+  // in place: chunk_count[b] <- number of heads before chunk b; one block, 1024 chunks per sweep
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < n_chunks; b0 += 1024) {
+    const int64_t b = b0 + threadIdx.x;
+    const int64_t v = b < n_chunks ? chunk_count[b] : 0;
+    int64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int64_t before = carry;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += wsum[w];
+    if (b < n_chunks) chunk_count[b] = before + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_objects = carry;
+}
+
+__global__ void __launch_bounds__(kIngestThreads) ingest_write_kernel(int64_t n_rows, const int64_t* id, const int64_t* chunk_base, int64_t max_objects,
+                                                                      int64_t* offsets, const int64_t* n_objects, const int32_t* passband,
+                                                                      const int32_t* lut, int lut_size, int32_t* band, int32_t* unknown) {
+  __shared__ int wsum[kIngestThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kIngestRows;
+  int64_t rank0 = chunk_base[blockIdx.x];
+  int bad = 0;
+  for (int r0 = 0; r0 < kIngestRows; r0 += kIngestThreads) {
+    const int64_t i = base + r0 + threadIdx.x;
+    const bool h = i < n_rows && is_head(id, i);
+    const unsigned bal = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kIngestThreads / 32; ++w) { if (w < warp) before += wsum[w]; total += wsum[w]; }
+    if (h) {
+      const int64_t pos = rank0 + before + __popc(bal & ((1u << lane) - 1u));
+      if (pos < max_objects) offsets[pos] = i;
+    }
+    if (band && i < n_rows) {   // add_log_lam as a table lookup (fulu/_base_aug.py:9-11); unknown passband -> -1, counted
+      const int32_t p = passband[i];
+      const int32_t bidx = (p >= 0 && p < lut_size) ? lut[p] : -1;
+      band[i] = bidx;
+      bad += bidx < 0;
+    }
+    rank0 += total;
+    __syncthreads();
+  }
+  if (unknown && bad) atomicAdd(unknown, bad);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t no = *n_objects;
+    if (no <= max_objects) offsets[no] = n_rows;
+  }
+}
+
 __global__ void copy_status_kernel(int64_t B, const int32_t* order, const int32_t* src, int32_t* dst) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= B) return;
@@ -540,6 +677,51 @@ int fulu_gp_predict_points_batch(const fulu_gp_batch* batch, int32_t n_params, c
   PredictArgs a = {};
   a.theta = theta; a.n_obs = 0; a.q_offsets = q_offsets; a.q_t = q_t; a.q_band = q_band; a.mean = mean; a.stdv = std; a.status = status;
   return predict_common(batch, n_params, a, workspace, workspace_bytes, stream);
+}
+
+int fulu_gp_peak_batch(const fulu_gp_batch* batch, const double* mean, const double* t_min, const double* t_max, int32_t n_obs, double* sum_flux,
+                       double* peak_t, double* peak_flux, int32_t* peak_index, void* stream) {
+  if (!batch || batch->n_curves < 0 || batch->n_bands < 1 || n_obs < 1) return FULU_GP_E_BADARG;
+  if (batch->order && (batch->n_order < 0 || batch->n_order > batch->n_curves)) return FULU_GP_E_BADARG;
+  const int64_t B = n_active(*batch);
+  if (B == 0) return 0;
+  if (!mean || !peak_t || !peak_flux || !peak_index || (t_min == nullptr) != (t_max == nullptr)) return FULU_GP_E_BADARG;
+  if (!t_min && (!batch->offsets || !batch->t)) return FULU_GP_E_BADARG;
+  PeakArgs a;
+  a.B = B; a.order = batch->order; a.offsets = batch->offsets; a.t_raw = batch->t; a.mean = mean; a.t_min = t_min; a.t_max = t_max;
+  a.n_bands = batch->n_bands; a.n_obs = n_obs; a.sum_flux = sum_flux; a.peak_t = peak_t; a.peak_flux = peak_flux; a.peak_index = peak_index;
+  peak_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int fulu_gp_ingest_workspace_bytes(int64_t n_rows, size_t* bytes) {
+  if (n_rows < 0 || !bytes) return FULU_GP_E_BADARG;
+  *bytes = align_up((size_t)((n_rows + kIngestRows - 1) / kIngestRows + 1) * 8);
+  return 0;
+}
+
+int fulu_gp_ingest_table(int64_t n_rows, const int64_t* object_id, const int32_t* passband, const int32_t* lut, int32_t lut_size,
+                         int64_t max_objects, int64_t* offsets, int64_t* n_objects, int32_t* band, int32_t* unknown_bands, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (n_rows < 0 || max_objects < 0 || !offsets || !n_objects) return FULU_GP_E_BADARG;
+  if (n_rows > 0 && !object_id) return FULU_GP_E_BADARG;
+  if (band && (!passband || !lut || lut_size < 1)) return FULU_GP_E_BADARG;
+  size_t need = 0;
+  fulu_gp_ingest_workspace_bytes(n_rows, &need);
+  if (!workspace || workspace_bytes < need) return FULU_GP_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (unknown_bands) CU_TRY(cudaMemsetAsync(unknown_bands, 0, 4, st));
+  const int64_t n_chunks = (n_rows + kIngestRows - 1) / kIngestRows;
+  int64_t* chunk = reinterpret_cast<int64_t*>(workspace);
+  if (n_chunks > 0) ingest_count_kernel<<<(unsigned)n_chunks, kIngestThreads, 0, st>>>(n_rows, object_id, chunk);
+  ingest_scan_kernel<<<1, 1024, 0, st>>>(n_chunks, chunk, n_objects);
+  if (n_chunks > 0)
+    ingest_write_kernel<<<(unsigned)n_chunks, kIngestThreads, 0, st>>>(n_rows, object_id, chunk, max_objects, offsets, n_objects, passband, lut,
+                                                                      lut_size, band, unknown_bands);
+  else CU_TRY(cudaMemsetAsync(offsets, 0, 8, st));
+  CU_TRY(cudaGetLastError());
+  return 0;
 }
 
 int fulu_gp_fp64_peak(int32_t mode, int32_t iters, double* tflops, void* stream) {

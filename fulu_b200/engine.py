@@ -403,6 +403,67 @@ class GPEngine:
                                                               self._p(out["status"]), self._p(ws), ws.numel(), self._stream()))
             return out
 
+    # ---- 8f-3: downstream consumer and upstream ingest on the device
+    def peak(self, batch: DeviceBatch, mean, t_min=None, t_max=None, want_sum=False):
+        """Band-summed augmented curve and its first maximum per curve (LcPlotter.plot_sum_passbands / plot_peak,
+        fulu/plotting.py:93,114-115), computed where the curves lie.  mean [B,n_bands,n_obs] (device) ->
+        dict(peak_t [B], peak_flux [B], peak_index [B] (+ sum_flux [B,n_obs]))."""
+        with torch.cuda.device(self.device):
+            B, n_obs = batch.n_curves, int(mean.shape[2])
+            if (t_min is None) != (t_max is None):
+                raise ValueError("give both t_min and t_max or neither")
+            if t_min is not None:
+                t_min = torch.as_tensor(t_min, dtype=torch.float64).to(self.device).contiguous().reshape(B)
+                t_max = torch.as_tensor(t_max, dtype=torch.float64).to(self.device).contiguous().reshape(B)
+            mean = mean.contiguous()
+            out = dict(peak_t=self._new(B), peak_flux=self._new(B), peak_index=self._new(B, dtype=torch.int32))
+            if want_sum:
+                out["sum_flux"] = self._new(B, n_obs)
+            _capi.check(self.lib.fulu_gp_peak_batch(ctypes.byref(batch.c), self._p(mean), self._p(t_min), self._p(t_max), n_obs,
+                                                    self._p(out.get("sum_flux")), self._p(out["peak_t"]), self._p(out["peak_flux"]),
+                                                    self._p(out["peak_index"]), self._stream()))
+            return out
+
+    def ingest_table(self, object_id, t, flux, flux_err, passband, passband2lam, use_err=False, family=KERNEL_RBF_WHITE):
+        """A survey table grouped by object (columns as in notebook_examples/object_34299.csv plus an object id) -> a DeviceBatch,
+        built on the device: CSR offsets from the id column, band indices through a lookup table of the (integer) passband ids
+        (fulu/_base_aug.py:9-11).  The t / flux / flux_err columns are used where they lie.  Returns (batch, lengths, object_ids):
+        lengths (host int64 [B]) for the length-class launches, object_ids (host) = the id of each curve.
+        Raises KeyError for a passband that is not in passband2lam, like the reference."""
+        with torch.cuda.device(self.device):
+            dev = self.device
+            oid = torch.as_tensor(object_id, dtype=torch.int64).to(dev).contiguous()
+            cols = [torch.as_tensor(c, dtype=torch.float64).to(dev).contiguous() for c in (t, flux, flux_err)]
+            pb = torch.as_tensor(passband, dtype=torch.int32).to(dev).contiguous()
+            n_rows = int(oid.numel())
+            keys = list(passband2lam)
+            if not all(isinstance(k, (int, np.integer)) and k >= 0 for k in keys):
+                raise TypeError("ingest_table needs non-negative integer passband ids (map string keys on the host first)")
+            lut_h = np.full(max(keys) + 1, -1, np.int32)
+            lut_h[np.asarray(keys, np.int64)] = np.arange(len(keys), dtype=np.int32)
+            lut = torch.from_numpy(lut_h).to(dev)
+            loglam = torch.tensor([float(passband2lam[k]) for k in keys], dtype=torch.float64, device=dev)
+            need = ctypes.c_size_t()
+            _capi.check(self.lib.fulu_gp_ingest_workspace_bytes(n_rows, ctypes.byref(need)))
+            ws = torch.empty(max(int(need.value), 8), dtype=torch.uint8, device=dev)
+            offsets = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)   # at most one object per row
+            n_obj = torch.zeros(1, dtype=torch.int64, device=dev)
+            band = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            unknown = torch.zeros(1, dtype=torch.int32, device=dev)
+            _capi.check(self.lib.fulu_gp_ingest_table(n_rows, self._p(oid), self._p(pb), self._p(lut), int(lut.numel()), n_rows,
+                                                      self._p(offsets), self._p(n_obj), self._p(band), self._p(unknown), self._p(ws),
+                                                      ws.numel(), self._stream()))
+            B = int(n_obj.cpu()[0])
+            if int(unknown.cpu()[0]):
+                bad = pb[band < 0][0].item()
+                raise KeyError(bad)
+            offsets = offsets[: B + 1].contiguous()
+            off_h = offsets.cpu().numpy()
+            lengths = np.diff(off_h)
+            ids = oid[offsets[:-1]].cpu().numpy() if B else np.zeros(0, np.int64)
+            batch = DeviceBatch(offsets, cols[0], cols[1], cols[2], band, loglam, int(lengths.max()) if B else 0, use_err, family=family)
+            return batch, lengths, ids
+
     def fp64_peak(self, mode=0, iters=20000):
         """Measured FP64 TFLOP/s of a register-resident DFMA (mode 0) or DMMA (mode 1) loop on this GPU."""
         with torch.cuda.device(self.device):
@@ -429,6 +490,9 @@ class AugmentResult:
     status: np.ndarray  # [B]
     h2d_bytes: int = 0
     d2h_bytes: int = 0
+    peak_t: np.ndarray = None  # [B] grid time of the band-summed curve's maximum (reduce="peak")
+    peak_flux: np.ndarray = None  # [B]
+    peak_index: np.ndarray = None  # [B]
 
 
 def bucket_curves(lengths, buckets=N_BUCKETS):
@@ -477,7 +541,7 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
 
 
 def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use_err=False, spec: KernelSpec = None, engine: GPEngine = None,
-                      device=None, window=0, pinned=None, out=None):
+                      device=None, window=0, pinned=None, out=None, reduce=None):
     """The batched ragged entry point: GP fit + augmentation for every curve of `curves` (host arrays in, host arrays out).
 
     Equivalent to, for each curve i:  aug = fulu.GaussianProcessesAugmentation(passband2lam, use_err=use_err).fit(t, flux, flux_err, band);
@@ -487,7 +551,9 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     of its curves, longest class first, and every pass writes its rows of the same device result tensors, which come back in one
     copy.  `pinned`: pinned staging of the inputs (pin_batch); `out`: pinned result buffers (pin_results) - the returned arrays
     are then views of them.  `spec`: the covariance family (KernelSpec / kernel_spec_from_sklearn); `theta` comes back in the
-    order of the sklearn kernel the spec was built from (KernelSpec.perm).
+    order of the sklearn kernel the spec was built from (KernelSpec.perm).  `reduce="peak"`: the augmented curves stay on the
+    device; the band-summed curve's peak (time, flux, grid index; LcPlotter.plot_peak, fulu/plotting.py:114-115) comes back instead
+    (flux_aug / flux_err_aug are None, 20 bytes per curve instead of 16 n_bands n_obs).
     """
     engine = engine or GPEngine(device)
     spec = spec or KernelSpec()
@@ -499,6 +565,13 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
         tmn = None if t_min is None else torch.as_tensor(np.asarray(t_min, np.float64)).to(engine.device)
         tmx = None if t_max is None else torch.as_tensor(np.asarray(t_max, np.float64)).to(engine.device)
         dev = fit_augment_device(engine, db, curves.lengths(), n_obs, tmn, tmx, spec, window)
+        if reduce == "peak":
+            pk = engine.peak(db, dev["mean"], tmn, tmx)
+            dev = {k: v for k, v in dev.items() if k not in ("mean", "std")}
+            dev.update(pk)
+            out = None
+        elif reduce is not None:
+            raise ValueError("reduce must be None or 'peak'")
         if out is None:
             host = {k: v.cpu() for k, v in dev.items()}
         else:
@@ -509,7 +582,44 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     theta = host["theta"].numpy()
     if not np.array_equal(spec.perm, np.arange(P)):
         theta = spec.to_sklearn(theta)
-    res = AugmentResult(host["mean"].numpy(), host["std"].numpy(), theta, host["lml"].numpy(), host["n_eval"].numpy(), host["status"].numpy())
+    res = AugmentResult(host["mean"].numpy() if "mean" in host else None, host["std"].numpy() if "std" in host else None, theta,
+                        host["lml"].numpy(), host["n_eval"].numpy(), host["status"].numpy())
+    if reduce == "peak":
+        res.peak_t, res.peak_flux, res.peak_index = host["peak_t"].numpy(), host["peak_flux"].numpy(), host["peak_index"].numpy()
     res.h2d_bytes = db.h2d_bytes()
     res.d2h_bytes = sum(int(v.numel() * v.element_size()) for v in dev.values())
     return res
+
+
+def fit_augment_table(object_id, t, flux, flux_err, passband, passband2lam, n_obs=128, use_err=False, spec: KernelSpec = None,
+                      engine: GPEngine = None, device=None, reduce=None):
+    """GP fit + augmentation of every object of a survey table grouped by object (one row per observation: object id, time, flux,
+    flux error, integer passband id).  The table is uploaded as it is and turned into the ragged batch on the device
+    (GPEngine.ingest_table); grids span each object's own observations.  Returns (AugmentResult, object_ids)."""
+    engine = engine or GPEngine(device)
+    spec = spec or KernelSpec()
+    with torch.cuda.device(engine.device):
+        db, lengths, ids = engine.ingest_table(object_id, t, flux, flux_err, passband, passband2lam, use_err=use_err, family=spec.family)
+        B, P = db.n_curves, spec.n_params
+        if B == 0:
+            nb = db.n_bands
+            return AugmentResult(np.empty((0, nb, n_obs)), np.empty((0, nb, n_obs)), np.empty((0, P)), np.empty(0), np.zeros(0, np.int32),
+                                 np.zeros(0, np.int32)), ids
+        dev = fit_augment_device(engine, db, lengths, n_obs, None, None, spec)
+        if reduce == "peak":
+            pk = engine.peak(db, dev["mean"])
+            dev = {k: v for k, v in dev.items() if k not in ("mean", "std")}
+            dev.update(pk)
+        elif reduce is not None:
+            raise ValueError("reduce must be None or 'peak'")
+        host = {k: v.cpu() for k, v in dev.items()}
+    theta = host["theta"].numpy()
+    if not np.array_equal(spec.perm, np.arange(P)):
+        theta = spec.to_sklearn(theta)
+    res = AugmentResult(host["mean"].numpy() if "mean" in host else None, host["std"].numpy() if "std" in host else None, theta,
+                        host["lml"].numpy(), host["n_eval"].numpy(), host["status"].numpy())
+    if reduce == "peak":
+        res.peak_t, res.peak_flux, res.peak_index = host["peak_t"].numpy(), host["peak_flux"].numpy(), host["peak_index"].numpy()
+    res.h2d_bytes = db.h2d_bytes() + 12 * db.n_obs_total
+    res.d2h_bytes = sum(int(v.numel() * v.element_size()) for v in dev.values())
+    return res, ids

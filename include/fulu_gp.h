@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FULU_GP_ABI_VERSION 3
+#define FULU_GP_ABI_VERSION 4
 #define FULU_GP_MAX_PARAMS 6
 #define FULU_GP_MAX_BANDS 16
 
@@ -142,6 +142,27 @@ int fulu_gp_predict_grid_batch(const fulu_gp_batch* batch, int32_t n_params, con
 int fulu_gp_predict_points_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const int64_t* q_offsets,
                                  const double* q_t, const int32_t* q_band, int32_t q_max, double* mean, double* std,
                                  int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Downstream consumer on the device (reference: LcPlotter.plot_sum_passbands / plot_peak, fulu/plotting.py:78-115):
+ * the augmented curve summed over the passbands at each grid time (groupby("time").sum() of the band-major frame, :93,114) and the
+ * grid time of its first maximum (curve["time"][curve["flux"].argmax()], :115).  A pipeline that only needs the peak leaves the
+ * [B, n_bands, n_obs] curves on the device and reads back 20 bytes per curve.
+ * mean [B, n_bands, n_obs] in (as written by fulu_gp_predict_grid_batch); t_min / t_max [B] in (both NULL = the curve's own span, taken
+ * from batch->t); sum_flux [B, n_obs] out (may be NULL); peak_t [B], peak_flux [B], peak_index [B] out (NaN / -1 when every sum is
+ * NaN).  Of `batch` only n_curves, n_bands, offsets, t and the optional index list are used. */
+int fulu_gp_peak_batch(const fulu_gp_batch* batch, const double* mean, const double* t_min, const double* t_max, int32_t n_obs,
+                       double* sum_flux, double* peak_t, double* peak_flux, int32_t* peak_index, void* stream);
+
+/* Upstream ingest on the device: a survey table whose rows are grouped by object (PLAsTiCC / ZTF tables,
+ * notebook_examples/object_34299.csv) -> the ragged CSR layout of fulu_gp_batch.  object_id [n_rows] in; offsets [max_objects + 1]
+ * and n_objects (one int64 on the device) out: offsets[k] = first row of the k-th object, offsets[n_objects] = n_rows (objects beyond
+ * max_objects are counted in n_objects but not written).  If band != NULL: band[i] = lut[passband[i]] (the reference's add_log_lam
+ * dict lookup, fulu/_base_aug.py:9-11, as a table: lut[id] = index into loglam or -1), rows with an unknown passband get -1 and are
+ * counted in *unknown_bands (the reference raises KeyError).  t / flux / flux_err are used where they lie: no column is copied. */
+int fulu_gp_ingest_workspace_bytes(int64_t n_rows, size_t* bytes);
+int fulu_gp_ingest_table(int64_t n_rows, const int64_t* object_id, const int32_t* passband, const int32_t* lut, int32_t lut_size,
+                         int64_t max_objects, int64_t* offsets, int64_t* n_objects, int32_t* band, int32_t* unknown_bands,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* FP64 roofline probe: runs a register-resident DFMA (mode 0) or DMMA m8n8k4 (mode 1) loop on every SM and returns the
  * achieved TFLOP/s in *tflops (CUDA-event timed on `stream`).  Used by bench.py for the roofline denominator because

@@ -409,3 +409,27 @@ class ClosedFormGP:
         t_aug, pb_aug = create_aug_data(t_min, t_max, tuple(self.passband2lam), n_obs)
         m, s = self.predict(t_aug, pb_aug)
         return t_aug, m, s, pb_aug
+
+
+# --------------------------------------------------------------------------------------------------
+# 8f-3: the steps either side of the path (checkers for fulu_gp_ingest_table / fulu_gp_peak_batch)
+# --------------------------------------------------------------------------------------------------
+def table_to_csr(object_id):
+    """Rows grouped by object -> (offsets, ids): what a pandas groupby(sort=False) on the id column yields for such a table."""
+    object_id = np.asarray(object_id, np.int64)
+    n = len(object_id)
+    if n == 0:
+        return np.zeros(1, np.int64), np.zeros(0, np.int64)
+    heads = np.flatnonzero(np.r_[True, object_id[1:] != object_id[:-1]])
+    return np.r_[heads, n].astype(np.int64), object_id[heads]
+
+
+def band_sum_peak(t_aug, flux_aug, passband_aug):
+    """LcPlotter.plot_sum_passbands / plot_peak (fulu/plotting.py:90-94, 111-115): the augmented curve summed over the
+    passbands per time, and the time of its maximum.  Executes the same pandas calls."""
+    import pandas as pd
+
+    frame = pd.DataFrame({"time": np.asarray(t_aug), "flux": np.asarray(flux_aug), "passband": np.asarray(passband_aug)})  # plotting.py:14-23
+    curve = frame[["time", "flux"]].groupby("time", as_index=False).sum()  # plotting.py:114
+    peak = curve["time"][curve["flux"].argmax()]  # plotting.py:115
+    return curve["time"].values, curve["flux"].values, float(peak)

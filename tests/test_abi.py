@@ -28,7 +28,7 @@ def test_binding_loads_and_reports_version(lib_path):
     from fulu_b200 import _capi
 
     lib = _capi.load()
-    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 3
+    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 4
     assert b"workspace" in lib.fulu_gp_strerror(-2)
     assert set(_capi.EXPORTS) <= {n for n in dir(lib)} | set(_capi.EXPORTS)
 

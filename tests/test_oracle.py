@@ -84,3 +84,13 @@ def test_start_points_match_survey():
     assert s.shape == (6, 4)
     np.testing.assert_allclose(s[1], [-2.88882052, 10.37808043, 5.34185792, 2.27169555], atol=1e-8)
     np.testing.assert_allclose(s[5], [-4.50748893, 0.5700379, -1.56702386, -4.8071267], atol=1e-8)
+
+
+def test_pipeline_checkers():
+    """The restatements that check the device-side ingest and peak consumer."""
+    off, ids = O.table_to_csr([5, 5, 5, 2, 2, 9])
+    assert off.tolist() == [0, 3, 5, 6] and ids.tolist() == [5, 2, 9]
+    assert O.table_to_csr([])[0].tolist() == [0]
+    t = np.tile(np.linspace(0.0, 3.0, 4), 2)
+    tt, ss, peak = O.band_sum_peak(t, np.array([0.0, 1.0, 5.0, 2.0, 1.0, 1.0, -3.0, 4.0]), np.repeat([0, 1], 4))
+    assert ss.tolist() == [1.0, 2.0, 2.0, 6.0] and peak == 3.0
