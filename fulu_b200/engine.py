@@ -495,11 +495,24 @@ class AugmentResult:
     peak_index: np.ndarray = None  # [B]
 
 
+MERGE_ABOVE = 511     # classes above this bound share one launch geometry (one 512-thread CTA per SM, matrix in a global slab)
+MERGE_BELOW_CURVES = 50   # ... and are merged upwards while they hold fewer curves than this (6 starts x 50 = two waves of 148 CTAs)
+
+
 def bucket_curves(lengths, buckets=N_BUCKETS):
-    """Group curve indices by padded length so one kernel launch sees similar N (cost ~ N^3)."""
+    """Group curve indices by padded length so one kernel launch sees similar N (cost ~ N^3).  The long-curve classes
+    (bound > MERGE_ABOVE) all run with the same geometry, so a class too small to fill the GPU is merged into the next larger
+    one instead of running alone (results do not depend on the class there: only the slab stride does)."""
     lengths = np.asarray(lengths)
     which = np.searchsorted(np.asarray(buckets), lengths, side="left")
-    return [(int(buckets[min(k, len(buckets) - 1)]), np.nonzero(which == k)[0]) for k in np.unique(which)]
+    groups = [[int(buckets[min(k, len(buckets) - 1)]), np.nonzero(which == k)[0]] for k in np.unique(which)]
+    out = []
+    for bound, idx in groups:   # ascending bounds
+        if out and out[-1][0] > MERGE_ABOVE and len(out[-1][1]) < MERGE_BELOW_CURVES:
+            prev = out.pop()
+            idx = np.sort(np.concatenate([prev[1], idx]))
+        out.append([bound, idx])
+    return [(b, i) for b, i in out]
 
 
 def pin_results(n_curves, n_bands, n_obs, n_params=4):  # n_params: KernelSpec.n_params of the family that will be fitted
@@ -526,7 +539,7 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
     profiles = []
     for bound, idx in reversed(groups):   # longest curves first
         order = None
-        if not single:
+        if not single or lengths.min() != lengths.max():
             # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
             order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
         sub = db.select(order, n_max=bound)
