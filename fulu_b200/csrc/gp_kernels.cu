@@ -165,13 +165,28 @@ __global__ void fit_init_kernel(FitDev d) {
   }
 }
 
-// One optimiser state per thread, advanced in place.  (Staging the 1.5 KB states through shared memory - warp-cooperative
-// coalesced copy in, advance there, copy out - was measured slower on B200: 19.3 ms instead of 14.1 ms per 188 rounds.)
+// One optimiser state per thread.  The advance is ~5.5k dependent, branchy instructions per slot (a third of them the replay of the
+// stored BFGS pairs into the dense B) at one warp per scheduler: 75-84 us per launch whatever the layout - ncu: 31 % long-scoreboard,
+// 30 % instruction-fetch, 25 % fixed-latency stalls, issue slots 7.6 % used (profiles/r01_v5_step_kernel_ncu.md).  Measured on the
+// 10,000-curve fit (188 launches): state advanced in place in global memory, 128-thread blocks 14.2 ms; on a thread-local copy
+// 14.0 ms, with 64-thread blocks 13.5 ms (kept), 32-thread blocks 13.1 ms; staged through shared memory 19.3 ms; slots spread over
+// 2-32x more warps 14.0-28 ms.
+#ifndef GP_STEP_LOCAL
+#define GP_STEP_LOCAL 1
+#endif
+#ifndef GP_STEP_THREADS
+#define GP_STEP_THREADS 64
+#endif
 __global__ void fit_step_kernel(FitDev d, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.counts[round]) return;
   const int slot = d.list[(size_t)(round & 1) * d.window + i];
+#if GP_STEP_LOCAL
+  // thread-local copy of the 1.5 KB state (local memory is interleaved per thread and L1-resident): one pipelined copy in, one out
+  FgState st = d.slots[slot];
+#else
   FgState& st = d.slots[slot];
+#endif
   lbfgsb_advance(st, d.opt, d.f_out[slot], d.g_out + slot * FG_MAXP);
   d.slot_nev[slot] += 1;
   bool live = true;
@@ -183,6 +198,9 @@ __global__ void fit_step_kernel(FitDev d, int round) {
     d.run_end[task] = st.task;
     live = acquire_task(d, slot, st);
   }
+#if GP_STEP_LOCAL
+  d.slots[slot] = st;
+#endif
   if (live) {
     const int pos = atomicAdd(&d.counts[round + 1], 1);
     d.list[(size_t)((round + 1) & 1) * d.window + pos] = slot;
@@ -585,7 +603,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   rc = ops->eval_prepare(w.globalA, w.smem_eval);
   if (rc) return rc;
 
-  const unsigned step_grid = (unsigned)((w.window + 127) / 128);
+  const unsigned step_grid = (unsigned)((w.window + GP_STEP_THREADS - 1) / GP_STEP_THREADS);
   constexpr int kMaxGroup = 16;
   const bool prof = opt->profile != nullptr;
   std::vector<cudaEvent_t> ev;   // 3 per round when profiling; read back only after the loop so timing does not perturb it
@@ -601,7 +619,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
       }
       ops->eval(w.globalA, w.grid_eval, w.threads_eval, w.smem_eval, st, d, round);
       if (prof) cudaEventRecord(ev[3 * round + 1], st);
-      fit_step_kernel<<<step_grid, 128, 0, st>>>(d, round);
+      fit_step_kernel<<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round);
       if (prof) cudaEventRecord(ev[3 * round + 2], st);
     }
     CU_TRY(cudaGetLastError());

@@ -13,6 +13,6 @@ eng.fit(db); torch.cuda.synchronize()
 for _ in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); f = eng.fit(db, profile=True); e1.record(); torch.cuda.synchronize()
-    print("fit ms", round(e0.elapsed_time(e1), 2), {k: f["profile"][k] for k in ("eval_ms", "threads_eval", "ctas_per_sm")})
+    print("fit ms", round(e0.elapsed_time(e1), 2), {k: round(f["profile"][k], 2) for k in ("eval_ms", "step_ms", "threads_eval", "ctas_per_sm")}, "lml sum", float(f["lml"].sum()))
 PY
 done 2>&1 | tee gpurun_out/ab.log

@@ -34,8 +34,8 @@ for r in rows:
     a = agg[key]
     a["samples"] += s
     a["inst"] += float(d["Instructions Executed"] or 0)
-    a["excess"] += float(d["L1 Wavefronts Shared Excessive"] or 0)
-    a["wave"] += float(d["L1 Wavefronts Shared"] or 0)
+    a["excess"] += float(d.get("L1 Wavefronts Shared Excessive") or 0)
+    a["wave"] += float(d.get("L1 Wavefronts Shared") or 0)
     for k in STALLS:
         a[k] += float(d.get(k) or 0)
     tot += s
