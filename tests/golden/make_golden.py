@@ -122,6 +122,22 @@ def main():
     from fulu_b200 import datasets
 
     cls = load_reference()
+    if "--notebook" in sys.argv or "--notebook-only" in sys.argv:
+        # BASELINE config #2 (ii): the reference notebook's own run (notebook_examples/plotting.ipynb cell 0) - fit on the 47 rows of
+        # train_test_split(test_size=0.5, random_state=11), augmentation over the whole object's span with n_obs = 1000, for its three
+        # GP models ('GP', 'GP C*RBF+Matern()+White', 'GP C*Matern()*RBF+Matern()+White')
+        from sklearn.model_selection import train_test_split
+
+        df = pd.read_csv(os.path.join(REF, "notebook_examples", "object_34299.csv"))
+        p2l = {i: float(np.log10(v)) for i, v in enumerate(datasets.LSST_LAMBDA)}
+        train, _ = train_test_split(df, test_size=0.5, random_state=11)
+        lc = (train["mjd"].values, train["flux"].values, train["flux_err"].values, train["passband"].values)
+        span = dict(t_min=float(df["mjd"].min()), t_max=float(df["mjd"].max()))
+        run_case(cls, "csv34299_split47", p2l, *lc, use_err=False, n_obs=1000, **span)
+        run_case(cls, "fam_rbf_matern_split47", p2l, *lc, use_err=False, n_obs=1000, kernel="rbf_matern", **span)
+        run_case(cls, "fam_notebook_split47", p2l, *lc, use_err=False, n_obs=1000, kernel="notebook", **span)
+        if "--notebook-only" in sys.argv:
+            return
     if "--families" in sys.argv or "--families-only" in sys.argv:
         # non-default kernels: theta / grad are stored in the kernel object's own (sklearn) order
         p2l, *lc = datasets.reference_test_fixture()
