@@ -77,3 +77,32 @@ def gather_rows(local_rows, local_index, n_total, dst=0, device=None):
         k = int(counts[r].item())
         out[idxs[r][:k].cpu()] = rows[r][:k].cpu()
     return out
+
+
+def fit_augment_sharded(curves, n_obs=128, dst=0, fit_fn=None, **kw):
+    """GP fit + augmentation of a ragged batch over all ranks of the default process group (one process per GPU).
+
+    Every rank calls this with the same host batch (or a batch whose curves it can index): the curves are split by the LPT
+    partition on the cubic cost model (`lpt_partition`), every rank runs `fit_augment_batch` on its own curves on its own GPU - no
+    collective on the data path - and the results are gathered ONCE at the end onto rank `dst`, in the original curve order.
+    Returns an AugmentResult on `dst`, None elsewhere.  `fit_fn` (tests) replaces `fit_augment_batch`.
+    """
+    import torch.distributed as dist
+
+    from .engine import AugmentResult, fit_augment_batch
+
+    fit_fn = fit_fn or fit_augment_batch
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lengths = curves.lengths()
+    mine = lpt_partition(lengths, world, m=curves.n_bands * n_obs)[rank]
+    res = fit_fn(curves.take(mine), n_obs=n_obs, **kw)
+    backend = dist.get_backend() if world > 1 else None
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    fields = {}
+    for name in ("flux_aug", "flux_err_aug", "theta", "lml", "n_eval", "status"):
+        fields[name] = gather_rows(torch.as_tensor(getattr(res, name)), mine, curves.n_curves, dst=dst, device=dev)
+    if rank != dst:
+        return None
+    out = {k: v.numpy() for k, v in fields.items()}
+    return AugmentResult(out["flux_aug"], out["flux_err_aug"], out["theta"], out["lml"], out["n_eval"], out["status"])
