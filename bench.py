@@ -13,6 +13,9 @@ GPU) every rank owns its own 10,000 curves (weak scaling); there is no collectiv
                 algorithmic flops N^3+12N^2 per evaluation / CUDA-event time of its launches (library-side events on
                 the launching stream); peak = DFMA rate measured in this run by fulu_gp_fp64_peak (MEASURED_PEAKS.json has no FP64)
   cpu_baseline  the reference path (fulu adapter on scikit-learn, oracle/fulu_sklearn_port.py) on all host cores, bounded sample
+  parity        curves with a status other than "theta on a bound"; vs_cpu_pass: the CPU sample is the first curves of the GPU batch, so
+                the final LMLs are compared curve by curve (max deficit against sklearn, fraction within 1e-6) together with both
+                evaluation counts; roofline.frac_at_sklearn_evals rescales the roofline fraction to sklearn's count
 """
 from __future__ import annotations
 
@@ -54,7 +57,7 @@ def _cpu_worker(args):
     import numpy as np
 
     from fulu_b200 import datasets
-    from oracle.fulu_sklearn_port import SklearnGPAugmentation
+    from oracle.fulu_sklearn_port import SklearnGPAugmentation, count_evals
 
     hb = datasets.plasticc_like(count, n_points=n_points, first=first)
     p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
@@ -64,9 +67,9 @@ def _cpu_worker(args):
         aug = SklearnGPAugmentation(p2l, kernel=make_kernel(kernel))
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            aug.fit(t, f, e, b)
+            n_eval = count_evals(aug, t, f, e, b)   # aug.fit(...) with the LML+gradient evaluations counted (E of SURVEY 8d)
             aug.augmentation(t.min(), t.max(), n_obs)
-        out.append(float(aug.reg.log_marginal_likelihood_value_))
+        out.append((float(aug.reg.log_marginal_likelihood_value_), n_eval))
     return out
 
 
@@ -84,7 +87,7 @@ def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4):
         t0 = time.perf_counter()
         lml = [v for part in ex.map(_cpu_worker, tasks) for v in part]
         dt = time.perf_counter() - t0
-    return n_curves / dt, dt, cores, lml
+    return n_curves / dt, dt, cores, lml   # lml: [(final LML, evaluations)] per curve, in curve order
 
 
 def run_reference(args):
@@ -246,11 +249,11 @@ def run_gpu(args):
     desc, default_b, n_obs = WORKLOADS[args.workload]
     headline = args.workload == "plasticc" and args.kernel == "default"
     # CPU baseline first (rank 0, N=1 only), before this process's CUDA context is busy
-    cpu_base = None
+    cpu_base, cpu_curves = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "plasticc":
         cores = os.cpu_count() or 1
         sample_n = max(2 * cores, min(args.ref_curves, 24 * cores))
-        v, dt, cores, _ = cpu_reference_throughput(sample_n, cores)
+        v, dt, cores, cpu_curves = cpu_reference_throughput(sample_n, cores)
         cpu_base = {"value": v, "unit": "curves/s", "cores": cores, "kind": "port",
                     "sample": f"{sample_n} curves of config #3 (N={N_POINTS}, 6 bands, M={N_BANDS * N_OBS}) in {dt:.1f} s, {cores} processes x 1 BLAS thread, "
                               "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"}
@@ -350,6 +353,17 @@ def run_gpu(args):
                            "per launch of this run")
         except (OSError, KeyError, ValueError):
             pass
+    # parity next to the CPU pass: the CPU sample is the first curves of rank 0's batch, so the final LMLs compare curve by
+    # curve, and the roofline gets a second figure normalised to sklearn's evaluation count (extra evaluations earn no credit)
+    parity_cpu = None
+    if cpu_curves:
+        k = min(len(cpu_curves), B)
+        ref_lml = np.array([c[0] for c in cpu_curves[:k]])
+        ref_ev = np.array([c[1] for c in cpu_curves[:k]], np.float64)
+        deficit = ref_lml - res.lml[:k]
+        parity_cpu = {"curves": int(k), "max_lml_deficit_vs_sklearn": float(np.max(deficit)), "median_abs_lml_difference": float(np.median(np.abs(deficit))),
+                      "fraction_within_1e-6": float(np.mean(deficit <= 1e-6)), "fraction_better_or_equal": float(np.mean(deficit <= 0.0)),
+                      "sklearn_evals_per_curve": float(ref_ev.mean()), "gpu_evals_per_curve_same_curves": float(res.n_eval[:k].mean())}
     mean_in = in_bytes / B
     out_bytes = 16 * nb * n_obs + 8 * 4 + 16
     cfg = {"workload": desc, "curves_per_gpu_per_step": B, "n_points": N_POINTS if headline else f"{int(lengths.min())}..{int(lengths.max())} (mean {lengths.mean():.0f})",
@@ -370,6 +384,8 @@ def run_gpu(args):
                      "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",
                      "peak_dmma": peak_dmma, "flops_per_eval": (N_POINTS ** 3 + 12 * N_POINTS ** 2) if args.workload == "plasticc" else flops_all / max(evals_all, 1),
                      "evals_per_curve": evals_all / (world * B * args.steps),
+                     "frac_at_sklearn_evals": (achieved / peak_dfma * parity_cpu["sklearn_evals_per_curve"] / parity_cpu["gpu_evals_per_curve_same_curves"])
+                     if (parity_cpu and peak_dfma) else None,
                      "eval_kernel_ms_per_step": eval_ms_all / args.steps, "eval_kernel_share_of_step": eval_ms_all / ms_max,
                      "timing": "kernel durations from CUDA events on the launching stream in a separate pass of the same K steps; "
                                "the timed region itself runs without them",
@@ -380,7 +396,7 @@ def run_gpu(args):
                                          "eval_ms": c["eval_ms"]} for c in classes],
                      "grid": int(classes[0]["grid_eval"]), "smem_per_cta": int(classes[0]["smem_eval"])},
         "cpu_baseline": cpu_base,
-        "parity": {"curves_flagged": int(stats[2]), "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)]))},
+        "parity": {"curves_flagged": int(stats[2]), "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)])), "vs_cpu_pass": parity_cpu},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
