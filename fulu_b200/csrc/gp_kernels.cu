@@ -24,7 +24,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 struct WsLayout {
   size_t xs, y, al, lam, stats, pstatus;                                      // prepared curves
   size_t slots, slot_task, slot_nev, f_out, g_out, list, counts, next_task;   // optimiser window
-  size_t run_f, run_x, run_nev, run_end, starts;                              // per (curve, start) results
+  size_t run_f, run_x, run_nev, run_end;                                      // per (curve, start) results
   size_t gA, gV;                                                              // per-CTA global scratch
   size_t total;
   int window, max_rounds, grid_eval, grid_predict, threads_eval, occ_eval;
@@ -95,7 +95,6 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.run_x = take(tasks * (size_t)FG_MAXP * 8);
   w.run_nev = take(tasks * 4);
   w.run_end = take(tasks * 4);
-  w.starts = take((size_t)(S > 0 ? S : 1) * FG_MAXP * 8);
   w.gA_stride = w.globalA ? gp_mat_doubles((int)np) : 0;
   w.gA = take((size_t)w.grid_eval * w.gA_stride * 8);
   w.gV_stride = np * GP_QC;
