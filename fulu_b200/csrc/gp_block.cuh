@@ -738,59 +738,125 @@ GP_DEV void gp_factor(Ctx& c, const GpCurveView& cv, Kern& kn, const GpSmem& s, 
 }
 
 // ---------------------------------------------------------------------------------------------- prediction
-// Query points against a factored curve (lower tiles = L, row n = z^T), one query point per thread:
+// Query points against a factored curve (strictly-lower tiles = L, diagonal tiles = inverted diagonal blocks, row n = z^T), eight
+// query points per warp at a time, as a blocked triangular solve on the FP64 tensor-core instruction:
 //   k*_i = c exp(-1/2 |x*/l - x_i/l|^2)          (kernels.py:1569-1570; White contributes 0 off the training set)
-//   v    = L^-1 k*  by forward substitution       (_gpr.py:460-462: solve_triangular, NOT an explicit inverse - at noise
+//   V    = L^-1 K*^T  by block forward substitution  (_gpr.py:460-462: solve_triangular, NOT an explicit inverse - at noise
 //                                                  levels of 1e-5 the explicit-inverse product loses ~40x in the variance)
-//   mean* = k*.alpha = v.z                        (_gpr.py:446-447; falls out of the border row of the substitution)
+//        V_I = X_II (K*_I - sum_{J<I} L_IJ V_J),  X_II = L_II^-1 from gp_cholesky (only the 8x8 diagonal blocks are inverted)
+//   mean* = k*.alpha = v.z                        (_gpr.py:446-447): the border row of the bordered system M [v; mu] = [k*; 0]
+//                                                  solves to mu = -z.v, so the mean needs no pass of its own
 //   |v|^2 -> var = (c + s2) - |v|^2               (_gpr.py:480-481)
-// Each thread owns column q of V (V[i * ldv + q]).  Block substitution over the 8x8 tiles: v_I = X_II (k*_I - sum_{J<I} L_IJ v_J)
-// with X_II = L_II^-1 from gp_cholesky (explicit inverses only of the 8x8 diagonal blocks; between blocks it is substitution).
-#define GP_QC 128   // query columns per pass (= threads that own a column)
+// A warp keeps its eight columns of V as T tiles of [row][query] doubles (`Vw`: shared memory, or the warp's global slab for
+// long curves); nothing of V goes to DRAM for curves that fit shared memory (v4 wrote 223 KB per curve).
+// DMMA operands: A = a tile of the matrix (lane (g, t): [g][t], [g][4 + t]), B = a tile of V (lane (g, t): [t][g], [4 + t][g]),
+// C = rows g, queries 2t and 2t + 1.
+struct GpQuery {
+  int m;                 // number of query points of this curve
+  int n_obs;             // grid mode: points per band (m = n_bands * n_obs); 0 = explicit points
+  double t_min, t_max;   // grid mode
+  const double* qt;      // explicit mode [m]
+  const int32_t* qband;  // explicit mode [m]
+};
 
-template <class Kern>
-GP_DEV void gp_predict_column(const GpSmem& s, int n, const Kern& kn, double uq, double vq, double* V, int ldv, double& mean, double& v2) {
+// np.linspace(t_min, t_max, n_obs)[k]: arange * step + start with the end point forced (numpy/_core/function_base.py)
+GP_DEV double gp_linspace(double t_min, double t_max, int n_obs, int k) {
+  if (n_obs <= 1) return t_min;
+  if (k == n_obs - 1) return t_max;
+  const double step = (t_max - t_min) / (double)(n_obs - 1);
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(__dmul_rn((double)k, step), t_min);   // no FMA contraction: numpy rounds the product first
+#else
+  volatile double prod = (double)k * step;
+  return prod + t_min;
+#endif
+}
+
+// Eight query points q0 .. q0 + 7 (those >= qd.m are padding) by one warp.  Returns 1.0 if a negative variance was clamped.
+template <class Ctx, class Kern>
+GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, const double* stats, const GpQuery& qd, const GpSmem& s,
+                              double* Vw, int q0, double* mean, double* stdv) {
+  const int n = cv.n, T = s.T, g = c.lane >> 2, t = c.lane & 3, rb = n & 7;
+  const GpFrag f = gp_frag(c.lane);
   const double* A = s.A;
-  double m = 0.0, q2 = 0.0;
-  for (int I = 0; I < s.T; ++I) {
-    double acc[8];
+  // this lane's two queries (columns 2t, 2t + 1 of the tile): scaled coordinates
+  double uq[2], vq[2];
+  bool valid[2];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int i = 8 * I + r;
-      const double du = uq - s.u[i], dv = vq - s.v[i];
-      acc[r] = (i < n) ? kn.value(du * du, dv * dv) : 0.0;
+  for (int e = 0; e < 2; ++e) {
+    const int q = q0 + 2 * t + e;
+    valid[e] = q < qd.m;
+    double tq = 0.0;
+    int bq = 0;
+    if (valid[e]) {
+      if (qd.n_obs > 0) { bq = q / qd.n_obs; tq = gp_linspace(qd.t_min, qd.t_max, qd.n_obs, q - bq * qd.n_obs); }
+      else { tq = qd.qt[q]; bq = qd.qband[q]; }
     }
-    const double* row = A + gp_tile(I, 0);
-    double* vp = V;
+    uq[e] = ((tq - stats[0]) / stats[1]) / kn.lt;   // ss.transform then X / length_scale
+    vq[e] = cv.lam[bq] / kn.ll;
+  }
+  const int oc = g * 8 + 2 * t;                    // C layout in a V tile: [row g][queries 2t, 2t + 1]
+  const int ob0 = t * 8 + g, ob1 = (4 + t) * 8 + g;   // B layout: [k = t][n = g], [k = 4 + t][n = g]
+  double sq0 = 0.0, sq1 = 0.0, m0 = 0.0, m1 = 0.0;
+  for (int I = 0; I < T; ++I) {
+    const int i = 8 * I + g;
+    const double ui = s.u[i], vi = s.v[i];
+    const double du0 = uq[0] - ui, dv0 = vq[0] - vi, du1 = uq[1] - ui, dv1 = vq[1] - vi;
+    double p0 = (i < n && valid[0]) ? kn.value(du0 * du0, dv0 * dv0) : 0.0;
+    double p1 = (i < n && valid[1]) ? kn.value(du1 * du1, dv1 * dv1) : 0.0;
+    double r0 = 0.0, r1 = 0.0;
+    const double* L = A + gp_tile(I, 0);
+    const double* Vj = Vw;
     for (int J = 0; J < I; ++J) {
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const double vj = vp[cc * ldv];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] -= row[gp_el(r, cc)] * vj;
-      }
-      row += 64;
-      vp += 8 * ldv;
+      c.mma(p0, p1, -L[f.a0], Vj[ob0]);
+      c.mma(r0, r1, -L[f.a1], Vj[ob1]);
+      L += 64;
+      Vj += 64;
     }
-    // `row` is the diagonal tile now: X_II, lower triangular.  The border row of the bordered system M [v; mu] = [k*; 0]
-    // solves to mu = -z.v = -mean, so the mean needs no pass of its own; rows past the border are padding.
+    // right-hand side through the warp's own tile I (accumulator layout -> B layout), then V_I = X_II rhs
+    double* Vi = Vw + 64 * I;
+    Vi[oc] = p0 + r0;
+    Vi[oc + 1] = p1 + r1;
+    c.warp_sync();
+    const double b0 = Vi[ob0], b1 = Vi[ob1];
+    double v0 = 0.0, v1 = 0.0;
+    c.mma(v0, v1, L[f.a0], b0);   // L points at the diagonal tile now: X_II, lower triangular with explicit zeros above
+    c.mma(v0, v1, L[f.a1], b1);
+    c.warp_sync();
+    if (i < n) {
+      sq0 += v0 * v0;
+      sq1 += v1 * v1;
+    } else {
+      if (i == n) { m0 = -v0; m1 = -v1; }   // the border row: -z.v
+      v0 = 0.0; v1 = 0.0;                   // rows past the curve never feed later rows (there are none), keep V clean
+    }
+    Vi[oc] = v0;
+    Vi[oc + 1] = v1;
+    c.warp_sync();
+  }
+  // column sums over the rows (lanes with the same t), the mean from the lanes that held the border row
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      double a = 0.0;
+  for (int o = 4; o < 32; o <<= 1) {
+    sq0 += c.shfl_xor(sq0, o);
+    sq1 += c.shfl_xor(sq1, o);
+  }
+  m0 = c.shfl(m0, 4 * rb + t);
+  m1 = c.shfl(m1, 4 * rb + t);
+  double neg = 0.0;
+  if (g == 0) {
+    const double kss = kn.diag();   // kernel_.diag(X*) (kernels.py:490,1315-1319,1438-1440)
+    const double ymean = stats[4], ystd = stats[5];
 #pragma unroll
-      for (int k = 0; k <= r; ++k) a += row[gp_el(r, k)] * acc[k];
-      const int i = 8 * I + r;
-      if (i < n) {
-        vp[r * ldv] = a;
-        q2 += a * a;
-      } else {
-        vp[r * ldv] = 0.0;
-        if (i == n) m = -a;
-      }
+    for (int e = 0; e < 2; ++e) {
+      if (!valid[e]) continue;
+      const int q = q0 + 2 * t + e;
+      double var = kss - (e ? sq1 : sq0);
+      if (var < 0.0) { var = 0.0; neg = 1.0; }            // _gpr.py:485-491
+      mean[q] = ystd * (e ? m1 : m0) + ymean;             // _gpr.py:450
+      stdv[q] = sqrt(var * (ystd * ystd));                // _gpr.py:494,500
     }
   }
-  mean = m;
-  v2 = q2;
+  return neg;
 }
 
 // ---------------------------------------------------------------------------------------------- per-curve preparation (a1-a3)
@@ -853,33 +919,12 @@ GP_DEV int gp_prepare_curve(Ctx& c, int n, const double* t, const double* flux, 
 }
 
 // ---------------------------------------------------------------------------------------------- whole-curve prediction
-struct GpQuery {
-  int m;                 // number of query points of this curve
-  int n_obs;             // grid mode: points per band (m = n_bands * n_obs); 0 = explicit points
-  double t_min, t_max;   // grid mode
-  const double* qt;      // explicit mode [m]
-  const int32_t* qband;  // explicit mode [m]
-};
-
-// np.linspace(t_min, t_max, n_obs)[k]: arange * step + start with the end point forced (numpy/_core/function_base.py)
-GP_DEV double gp_linspace(double t_min, double t_max, int n_obs, int k) {
-  if (n_obs <= 1) return t_min;
-  if (k == n_obs - 1) return t_max;
-  const double step = (t_max - t_min) / (double)(n_obs - 1);
-#if defined(__CUDA_ARCH__)
-  return __dadd_rn(__dmul_rn((double)k, step), t_min);   // no FMA contraction: numpy rounds the product first
-#else
-  volatile double prod = (double)k * step;
-  return prod + t_min;
-#endif
-}
-
 // mean/std [m] of one curve at hyperparameters theta.  stats = per-curve (t mean, t scale, ., ., flux mean, flux std).
-// V: scratch of gp_pad(n) * GP_QC doubles (column q of thread q).  Threads >= GP_QC only help with the factorisation.
+// Vw: nwarp x T tiles of scratch (64 doubles each), one slab of T tiles per warp.
 // Returns status bits (valid in all threads): 2 = not PD, 16 = a negative variance was clamped.
 template <class Kern, class Ctx>
 GP_DEV int gp_predict_curve(Ctx& c, const GpCurveView& cv, const double* theta, const double* stats, const GpQuery& qd,
-                            const GpSmem& s, double* V, double* mean, double* stdv, double& lml) {
+                            const GpSmem& s, double* Vw, double* mean, double* stdv, double& lml) {
   bool ok;
   Kern kn;
   kn.init(theta);
@@ -888,26 +933,10 @@ GP_DEV int gp_predict_curve(Ctx& c, const GpCurveView& cv, const double* theta, 
     for (int q = c.tid; q < qd.m; q += c.nthr) { mean[q] = NAN; stdv[q] = NAN; }
     return 2;
   }
-  const double lt = kn.lt, ll = kn.ll;
-  const double kss = kn.diag();                      // kernel_.diag(X*) (kernels.py:490,1315-1319,1438-1440)
-  const double ymean = stats[4], ystd = stats[5];
+  c.sync();   // the factor is complete for every warp
   double neg[1] = {0.0};
-  const int ncol = c.nthr < GP_QC ? c.nthr : GP_QC;
-  if (c.tid < ncol) {
-    for (int q = c.tid; q < qd.m; q += ncol) {
-      double tq; int bq;
-      if (qd.n_obs > 0) { bq = q / qd.n_obs; tq = gp_linspace(qd.t_min, qd.t_max, qd.n_obs, q - bq * qd.n_obs); }
-      else { tq = qd.qt[q]; bq = qd.qband[q]; }
-      const double uq = ((tq - stats[0]) / stats[1]) / lt;   // ss.transform then X / length_scale
-      const double vq = cv.lam[bq] / ll;
-      double m, v2;
-      gp_predict_column(s, cv.n, kn, uq, vq, V + c.tid, GP_QC, m, v2);
-      double var = kss - v2;
-      if (var < 0.0) { var = 0.0; neg[0] = 1.0; }      // _gpr.py:485-491
-      mean[q] = ystd * m + ymean;                      // _gpr.py:450
-      stdv[q] = sqrt(var * (ystd * ystd));             // _gpr.py:494,500
-    }
-  }
+  double* mine = Vw + (size_t)c.warp * s.T * 64;
+  for (int q0 = 8 * c.warp; q0 < qd.m; q0 += 8 * c.nwarp) neg[0] += gp_predict_tile(c, cv, kn, stats, qd, s, mine, q0, mean, stdv);
   gp_block_sum(c, neg, s.red);
   return neg[0] > 0.0 ? 16 : 0;
 }

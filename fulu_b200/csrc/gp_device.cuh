@@ -45,7 +45,7 @@ struct DevCtx {
 #define GP_EVAL_MAX_THREADS 512
 #endif
 constexpr int kEvalMaxThreads = GP_EVAL_MAX_THREADS;
-constexpr int kPredictThreads = 128;
+constexpr int kPredictThreads = 256;   // eight warps: each takes eight query points at a time (gp_predict_tile)
 constexpr int kPrepThreads = 128;
 constexpr size_t kMaxSmem = 227 * 1024;
 
@@ -161,11 +161,12 @@ struct PredictArgs {
 };
 
 template <class Kern, bool kGlobalA>
-__global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs a) {
+__global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double tlim[2];
   DevCtx c;
-  double* V = a.gV + (size_t)blockIdx.x * a.gV_stride;
+  // the warps' V tiles: behind the matrix and vectors in shared memory, or this CTA's global slab for long curves
+  double* Vglobal = a.gV + (size_t)blockIdx.x * a.gV_stride;
   for (int64_t kk = blockIdx.x; kk < a.B; kk += gridDim.x) {
     const int64_t cu = curve_of(a.tab, kk);
     GpCurveView cv = curve_view(a.tab, cu);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kPredictThreads, 4) predict_kernel(PredictArgs
       for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }
     } else {
       GpSmem s = carve<kGlobalA>(smem, a.gA, a.gA_stride, cv.n);
+      double* V = a.gV_stride ? Vglobal : smem + gp_smem_doubles(cv.n);   // (classes near the shared-memory limit keep V in the slab too)
       st = gp_predict_curve<Kern>(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, s, V, a.mean + out0, a.stdv + out0, l);
     }
     if (threadIdx.x == 0) {

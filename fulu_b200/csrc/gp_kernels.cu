@@ -57,7 +57,10 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   const size_t full = gp_mat_doubles((int)np) * sizeof(double) + vec;
   w.globalA = full > kMaxSmem;
   w.smem_eval = w.globalA ? vec : full;
-  w.smem_predict = w.smem_eval;
+  // prediction: eight warps, each with its eight columns of V as T tiles (shared memory, or the CTA's global slab for long curves)
+  const size_t vtiles = (size_t)(kPredictThreads / 32) * (np / GP_NB) * 64 * sizeof(double);
+  const bool globalV = w.globalA || w.smem_eval + vtiles > kMaxSmem;
+  w.smem_predict = globalV ? w.smem_eval : w.smem_eval + vtiles;
   // residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation is latency bound, so as many curves per
   // SM as fit, and the 512 threads the register file allows are split between them
   // (matrix in global memory: one 512-thread CTA per SM above np = 512 - two 256-thread CTAs per SM were measured 37 % slower at
@@ -70,7 +73,9 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.occ_eval = occ;
   w.threads_eval = threads;
   w.grid_eval = sms * occ;
-  int occ_p = occ > 4 ? 4 : occ;   // 128-thread prediction CTAs
+  int occ_p = (int)((228 * 1024) / (w.smem_predict + 1024));   // 256-thread prediction CTAs, at most two per SM (registers)
+  if (occ_p > 2) occ_p = 2;
+  if (occ_p < 1) occ_p = 1;
   w.grid_predict = sms * occ_p;
   if (window <= 0) window = kDefaultWindow;
   size_t tasks = (size_t)(b.order ? b.n_order : b.n_curves) * (size_t)(S > 0 ? S : 1);
@@ -97,7 +102,7 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.run_end = take(tasks * 4);
   w.gA_stride = w.globalA ? gp_mat_doubles((int)np) : 0;
   w.gA = take((size_t)w.grid_eval * w.gA_stride * 8);
-  w.gV_stride = np * GP_QC;
+  w.gV_stride = globalV ? vtiles / sizeof(double) : 0;
   w.gV = take((size_t)w.grid_predict * w.gV_stride * 8);
   w.total = o;
 }

@@ -111,7 +111,7 @@ static int predict_impl(int n, const double* xs, const int32_t* band, const doub
                         const double* theta, const double* stats, int m, int n_obs, double t_min, double t_max,
                         const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
   std::vector<double> smem(gp_smem_doubles(n));
-  std::vector<double> V((size_t)gp_pad(n) * GP_QC);
+  std::vector<double> V((size_t)(nthr / 32) * (gp_pad(n) / 8) * 64);
   GpCurveView cv{n, xs, band, y, al, lam};
   GpQuery qd{m, n_obs, t_min, t_max, qt, qband};
   int status = 0;
