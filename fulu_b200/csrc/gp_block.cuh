@@ -795,8 +795,11 @@ GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, con
     uq[e] = ((tq - stats[0]) / stats[1]) / kn.lt;   // ss.transform then X / length_scale
     vq[e] = cv.lam[bq] / kn.ll;
   }
-  const int oc = g * 8 + 2 * t;                    // C layout in a V tile: [row g][queries 2t, 2t + 1]
-  const int ob0 = t * 8 + g, ob1 = (4 + t) * 8 + g;   // B layout: [k = t][n = g], [k = 4 + t][n = g]
+  // a V tile holds element (row k, query n) at 8 k + (n ^ (k & 2 ? 4 : 0)): the 16-byte stores in accumulator layout
+  // ([row g][queries 2t, 2t + 1]) and the 8-byte loads in B-operand layout ([k = t][n = g], [k = 4 + t][n = g]) are then both
+  // free of bank conflicts (plain 8 k + n made rows k and k + 2 collide: 31 % conflicting wavefronts in the first version)
+  const int oc = g * 8 + ((2 * t) ^ ((g & 2) ? 4 : 0));
+  const int ob0 = t * 8 + (g ^ ((t & 2) ? 4 : 0)), ob1 = ob0 + 32;
   double sq0 = 0.0, sq1 = 0.0, m0 = 0.0, m1 = 0.0;
   for (int I = 0; I < T; ++I) {
     const int i = 8 * I + g;
@@ -815,8 +818,7 @@ GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, con
     }
     // right-hand side through the warp's own tile I (accumulator layout -> B layout), then V_I = X_II rhs
     double* Vi = Vw + 64 * I;
-    Vi[oc] = p0 + r0;
-    Vi[oc + 1] = p1 + r1;
+    *reinterpret_cast<GpPair*>(Vi + oc) = GpPair{p0 + r0, p1 + r1};   // (one 16-byte store: oc is even)
     c.warp_sync();
     const double b0 = Vi[ob0], b1 = Vi[ob1];
     double v0 = 0.0, v1 = 0.0;
@@ -830,8 +832,7 @@ GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, con
       if (i == n) { m0 = -v0; m1 = -v1; }   // the border row: -z.v
       v0 = 0.0; v1 = 0.0;                   // rows past the curve never feed later rows (there are none), keep V clean
     }
-    Vi[oc] = v0;
-    Vi[oc + 1] = v1;
+    *reinterpret_cast<GpPair*>(Vi + oc) = GpPair{v0, v1};
     c.warp_sync();
   }
   // column sums over the rows (lanes with the same t), the mean from the lanes that held the border row
