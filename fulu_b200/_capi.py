@@ -25,7 +25,7 @@ class FitOptions(ctypes.Structure):
     _fields_ = [
         ("n_params", ctypes.c_int32), ("n_starts", ctypes.c_int32), ("m", ctypes.c_int32), ("maxiter", ctypes.c_int32),
         ("maxfun", ctypes.c_int32), ("maxls", ctypes.c_int32), ("window", ctypes.c_int32), ("max_rounds", ctypes.c_int32),
-        ("starts_per_curve", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("starts_per_curve", ctypes.c_int32), ("profile_counts_only", ctypes.c_int32),
         ("factr", ctypes.c_double), ("pgtol", ctypes.c_double),
         ("lower", ctypes.c_double * MAX_PARAMS), ("upper", ctypes.c_double * MAX_PARAMS),
         ("profile", ctypes.POINTER(ctypes.c_double)),

@@ -121,6 +121,58 @@ struct FitDev {
   size_t gA_stride;
 };
 
+// pulls the next runnable task into `slot` (whose optimiser state is `state`); returns false when the queue is empty
+__device__ __forceinline__ bool acquire_task(const FitDev& d, int slot, FgState& state) {
+  for (;;) {
+    unsigned long long nt = atomicAdd(d.next_task, 1ULL);
+    if (nt >= (unsigned long long)d.n_tasks) { d.slot_task[slot] = -1; state.task = FG_TASK_IDLE; return false; }
+    const int64_t cu = curve_of(d.tab, (int64_t)(nt / d.S));
+    const int st = (int)(nt % d.S);
+    // start points: [S, P] shared by all curves, or [B, S, P] by curve id
+    const double* x0 = d.starts + ((d.starts_per_curve ? cu * d.S : 0) + st) * d.P;
+    if (d.tab.pstatus[cu] != 0) {   // unusable curve: record and move on
+      d.run_f[nt] = INFINITY;
+      for (int k = 0; k < d.P; ++k) d.run_x[nt * FG_MAXP + k] = x0[k];
+      d.run_nev[nt] = 0;
+      d.run_end[nt] = FG_TASK_ABNORMAL;
+      continue;
+    }
+    lbfgsb_init(state, d.opt, x0);
+    d.slot_task[slot] = (int64_t)nt;
+    d.slot_nev[slot] = 0;
+    return true;
+  }
+}
+
+// One optimiser step of `slot` after its objective evaluation (f, g): advances the L-BFGS-B state machine on a thread-local copy of
+// the 1.5 KB state (local memory is interleaved per thread and L1-resident: one pipelined copy in, one out); a finished run records
+// its result and pulls the next task into the slot.  Returns false when the slot has nothing left to do.
+#ifndef GP_STEP_LOCAL
+#define GP_STEP_LOCAL 1
+#endif
+__device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f, const double* g) {
+#if GP_STEP_LOCAL
+  FgState st = d.slots[slot];
+#else
+  FgState& st = d.slots[slot];
+#endif
+  lbfgsb_advance(st, d.opt, f, g);
+  d.slot_nev[slot] += 1;
+  bool live = true;
+  if (fg_task_done(st.task)) {
+    const int64_t task = d.slot_task[slot];
+    d.run_f[task] = st.f;
+    for (int k = 0; k < FG_MAXP; ++k) d.run_x[task * FG_MAXP + k] = st.x[k];
+    d.run_nev[task] = d.slot_nev[slot];
+    d.run_end[task] = st.task;
+    live = acquire_task(d, slot, st);
+  }
+#if GP_STEP_LOCAL
+  d.slots[slot] = st;
+#endif
+  return live;
+}
+
 template <class Kern, bool kGlobalA>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
@@ -140,6 +192,36 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
       for (int k = 0; k < Kern::P; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
     }
     __syncthreads();
+  }
+}
+
+
+// The tail of a fit - fewer live slots than CTAs - and every small fit (a single curve through the drop-in class is six tasks): one
+// launch in which CTA b owns slot list[b] and alternates evaluation (all warps) and optimiser step (thread 0) until the slot runs
+// dry.  No rounds, no host round trips: a tail round costs an evaluation plus a step latency instead of two launches and two
+// under-filled kernels.  Same block geometry as fit_eval_kernel, so a run's numbers do not depend on which kernel finished it.
+template <class Kern, bool kGlobalA>
+__global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, int round) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int go;
+  DevCtx c;
+  if ((int)blockIdx.x >= d.counts[round]) return;
+  const int slot = d.list[(size_t)(round & 1) * d.window + blockIdx.x];
+  for (;;) {
+    const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
+    GpCurveView cv = curve_view(d.tab, cu);
+    GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
+    double l, g[FG_MAXP];
+    bool ok;
+    gp_eval_lml_grad<Kern>(c, cv, d.slots[slot].x, s, l, g, ok);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
+      for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
+      go = advance_slot(d, slot, -l, g) ? 1 : 0;
+      __threadfence_block();
+    }
+    __syncthreads();
+    if (!go) break;   // (thread 0 next writes `go` after the barriers of a whole evaluation: no second barrier needed here)
   }
 }
 
@@ -217,6 +299,7 @@ struct GpFamilyOps {
              double* lml, double* grad, double* gA, size_t gA_stride, long long* marks);
   int (*eval_prepare)(bool globalA, size_t smem);
   int (*eval)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
+  int (*tail)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
   int (*predict)(bool globalA, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a);
 };
 
@@ -241,11 +324,18 @@ struct GpFamilyLaunch {
     return (int)cudaGetLastError();
   }
   static int eval_prepare(bool globalA, size_t smem) {
-    return globalA ? gp_set_smem(fit_eval_kernel<Kern, true>, smem) : gp_set_smem(fit_eval_kernel<Kern, false>, smem);
+    int rc = globalA ? gp_set_smem(fit_eval_kernel<Kern, true>, smem) : gp_set_smem(fit_eval_kernel<Kern, false>, smem);
+    if (rc) return rc;
+    return globalA ? gp_set_smem(fit_tail_kernel<Kern, true>, smem) : gp_set_smem(fit_tail_kernel<Kern, false>, smem);
   }
   static int eval(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
     if (globalA) fit_eval_kernel<Kern, true><<<grid, threads, smem, st>>>(d, round);
     else fit_eval_kernel<Kern, false><<<grid, threads, smem, st>>>(d, round);
+    return 0;
+  }
+  static int tail(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
+    if (globalA) fit_tail_kernel<Kern, true><<<grid, threads, smem, st>>>(d, round);
+    else fit_tail_kernel<Kern, false><<<grid, threads, smem, st>>>(d, round);
     return 0;
   }
   static int predict(bool globalA, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a) {
@@ -260,7 +350,7 @@ struct GpFamilyLaunch {
     return (int)cudaGetLastError();
   }
   static const GpFamilyOps* ops() {
-    static const GpFamilyOps o = {Kern::P, &lml, &eval_prepare, &eval, &predict};
+    static const GpFamilyOps o = {Kern::P, &lml, &eval_prepare, &eval, &tail, &predict};
     return &o;
   }
 };

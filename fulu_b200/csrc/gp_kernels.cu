@@ -7,10 +7,13 @@
 //                    factors it and returns -LML and its gradient                                   (a4, a5)
 //   step kernel      one thread per active slot: advances its L-BFGS-B state machine, and when a run finishes pulls the
 //                    next (curve, start) task into the freed slot ("continuous batching")            (a6)
+//   tail kernel      once fewer slots are live than CTAs (and for every small fit): one launch, CTA b owns slot b and
+//                    alternates evaluation and optimiser step until the slot runs dry                 (a4-a6)
 //   select kernel    best of the S runs per curve                                                    (a6)
 //   predict kernel   one CTA per curve: final factorisation + augmentation grid / query points       (a7-a9)
 // There is no collective anywhere: curves are independent, multi-GPU runs shard the batch.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -137,29 +140,6 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
   }
 }
 
-// pulls the next runnable task into `slot` (whose optimiser state is `state`); returns false when the queue is empty
-__device__ bool acquire_task(const FitDev& d, int slot, FgState& state) {
-  for (;;) {
-    unsigned long long nt = atomicAdd(d.next_task, 1ULL);
-    if (nt >= (unsigned long long)d.n_tasks) { d.slot_task[slot] = -1; state.task = FG_TASK_IDLE; return false; }
-    const int64_t cu = curve_of(d.tab, (int64_t)(nt / d.S));
-    const int st = (int)(nt % d.S);
-    // start points: [S, P] shared by all curves, or [B, S, P] by curve id
-    const double* x0 = d.starts + ((d.starts_per_curve ? cu * d.S : 0) + st) * d.P;
-    if (d.tab.pstatus[cu] != 0) {   // unusable curve: record and move on
-      d.run_f[nt] = INFINITY;
-      for (int k = 0; k < d.P; ++k) d.run_x[nt * FG_MAXP + k] = x0[k];
-      d.run_nev[nt] = 0;
-      d.run_end[nt] = FG_TASK_ABNORMAL;
-      continue;
-    }
-    lbfgsb_init(state, d.opt, x0);
-    d.slot_task[slot] = (int64_t)nt;
-    d.slot_nev[slot] = 0;
-    return true;
-  }
-}
-
 __global__ void fit_init_kernel(FitDev d) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= d.window) return;
@@ -175,9 +155,6 @@ __global__ void fit_init_kernel(FitDev d) {
 // 10,000-curve fit (188 launches): state advanced in place in global memory, 128-thread blocks 14.2 ms; on a thread-local copy
 // 14.0 ms, with 64-thread blocks 13.5 ms (kept), 32-thread blocks 13.1 ms; staged through shared memory 19.3 ms; slots spread over
 // 2-32x more warps 14.0-28 ms.
-#ifndef GP_STEP_LOCAL
-#define GP_STEP_LOCAL 1
-#endif
 #ifndef GP_STEP_THREADS
 #define GP_STEP_THREADS 64
 #endif
@@ -185,27 +162,7 @@ __global__ void fit_step_kernel(FitDev d, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.counts[round]) return;
   const int slot = d.list[(size_t)(round & 1) * d.window + i];
-#if GP_STEP_LOCAL
-  // thread-local copy of the 1.5 KB state (local memory is interleaved per thread and L1-resident): one pipelined copy in, one out
-  FgState st = d.slots[slot];
-#else
-  FgState& st = d.slots[slot];
-#endif
-  lbfgsb_advance(st, d.opt, d.f_out[slot], d.g_out + slot * FG_MAXP);
-  d.slot_nev[slot] += 1;
-  bool live = true;
-  if (fg_task_done(st.task)) {
-    const int64_t task = d.slot_task[slot];
-    d.run_f[task] = st.f;
-    for (int k = 0; k < FG_MAXP; ++k) d.run_x[task * FG_MAXP + k] = st.x[k];
-    d.run_nev[task] = d.slot_nev[slot];
-    d.run_end[task] = st.task;
-    live = acquire_task(d, slot, st);
-  }
-#if GP_STEP_LOCAL
-  d.slots[slot] = st;
-#endif
-  if (live) {
+  if (advance_slot(d, slot, d.f_out[slot], d.g_out + slot * FG_MAXP)) {
     const int pos = atomicAdd(&d.counts[round + 1], 1);
     d.list[(size_t)((round + 1) & 1) * d.window + pos] = slot;
   }
@@ -609,11 +566,20 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
 
   const unsigned step_grid = (unsigned)((w.window + GP_STEP_THREADS - 1) / GP_STEP_THREADS);
   constexpr int kMaxGroup = 16;
-  const bool prof = opt->profile != nullptr;
+  const bool prof = opt->profile != nullptr && opt->profile_counts_only == 0;   // per-launch CUDA events
+  int launches = 3;   // prep, init, select
   std::vector<cudaEvent_t> ev;   // 3 per round when profiling; read back only after the loop so timing does not perturb it
   int round = 0, group = 4;
   bool finished = false;
-  while (round < w.max_rounds) {
+  // the tail (and every small fit): once the live slots fit one wave of CTAs, one fused launch finishes them (fit_tail_kernel)
+  const bool use_tail = !prof && getenv("FULU_GP_NO_TAIL") == nullptr;
+  if (use_tail && d.n_tasks <= (int64_t)w.grid_eval) {
+    ops->tail(w.globalA, (unsigned)d.n_tasks, w.threads_eval, w.smem_eval, st, d, 0);
+    CU_TRY(cudaGetLastError());
+    finished = true;
+    ++launches;
+  }
+  while (!finished && round < w.max_rounds) {
     int upto = round + group;
     if (upto > w.max_rounds) upto = w.max_rounds;
     for (; round < upto; ++round) {
@@ -625,26 +591,37 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
       if (prof) cudaEventRecord(ev[3 * round + 1], st);
       fit_step_kernel<<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round);
       if (prof) cudaEventRecord(ev[3 * round + 2], st);
+      launches += 2;
     }
     CU_TRY(cudaGetLastError());
     int32_t remaining = 0;
     CU_TRY(cudaMemcpyAsync(&remaining, d.counts + round, 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     if (remaining == 0) { finished = true; break; }
-    if (group < kMaxGroup) group *= 2;
-  }
-  if (prof) {
-    double eval_ms = 0.0, step_ms = 0.0;
-    for (int r = 0; r < round; ++r) {
-      float a = 0.f, b = 0.f;
-      cudaEventElapsedTime(&a, ev[3 * r], ev[3 * r + 1]);
-      cudaEventElapsedTime(&b, ev[3 * r + 1], ev[3 * r + 2]);
-      eval_ms += a;
-      step_ms += b;
+    if (use_tail && remaining <= w.grid_eval) {
+      ops->tail(w.globalA, (unsigned)remaining, w.threads_eval, w.smem_eval, st, d, round);
+      CU_TRY(cudaGetLastError());
+      finished = true;
+      ++launches;
+      break;
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (remaining < 8 * w.grid_eval) group = 4;   // close to the tail: look more often
+    else if (group < kMaxGroup) group *= 2;
+  }
+  if (opt->profile != nullptr) {
+    double eval_ms = 0.0, step_ms = 0.0;
+    if (prof) {
+      for (int r = 0; r < round; ++r) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[3 * r], ev[3 * r + 1]);
+        cudaEventElapsedTime(&b, ev[3 * r + 1], ev[3 * r + 2]);
+        eval_ms += a;
+        step_ms += b;
+      }
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
     double* pr = opt->profile;
-    pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = 2.0 * round + 4.0; pr[4] = w.window; pr[5] = w.grid_eval;
+    pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = launches + (finished ? 0 : 1); pr[4] = w.window; pr[5] = w.grid_eval;
     pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0; pr[8] = w.threads_eval; pr[9] = w.occ_eval;
   }
   if (!finished) {

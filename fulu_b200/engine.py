@@ -341,8 +341,9 @@ class GPEngine:
                 out["run_lml"] = self._new(B, S)
                 out["run_theta"] = self._new(B, S, P)
             prof = (ctypes.c_double * 10)() if profile else None
-            if profile:
+            if profile:   # True: per-launch CUDA events (eval_ms, step_ms); "counts": only rounds / launches / geometry, no events
                 o.profile = ctypes.cast(prof, ctypes.POINTER(ctypes.c_double))
+                o.profile_counts_only = 1 if profile == "counts" else 0
             ws = self._workspace(batch, P, S, window)
             _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts), self._p(out["theta"]),
                                                    self._p(out["lml"]), self._p(out["n_eval"]), self._p(out["status"]),
@@ -353,7 +354,7 @@ class GPEngine:
                 out["profile"] = {k: float(prof[i]) for i, k in enumerate(keys)}
             for _ in range(spec.polish if polish is None else polish):
                 # rows the batch does not select hold copies of the current values, so they compare equal and stay
-                o.n_starts, o.starts_per_curve, o.profile = 1, 1, None
+                o.n_starts, o.starts_per_curve, o.profile, o.profile_counts_only = 1, 1, None, 0
                 cont = dict(theta=out["theta"].clone(), lml=out["lml"].clone(), n_eval=torch.zeros_like(out["n_eval"]), status=out["status"].clone())
                 starts2 = out["theta"].contiguous()
                 _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts2), self._p(cont["theta"]),

@@ -96,13 +96,14 @@ typedef struct fulu_gp_fit_options {
   int32_t max_rounds;        /* hard cap on evaluation rounds (0 = default) */
   int32_t starts_per_curve;  /* 0: theta_starts is [S,P], shared by all curves (sklearn's restarts); 1: [B,S,P], indexed by curve id
                                 (e.g. S = 1 continuation runs from each curve's current optimum) */
-  int32_t reserved;
+  int32_t profile_counts_only; /* with `profile`: fill only the counts ([0], [3]..[9]) - no per-launch events, same launches as an
+                                unprofiled call (per-launch timing makes every round two separately timed kernels) */
   double factr;              /* 1e7  (ftol = factr * eps) */
   double pgtol;              /* 1e-5 */
   double lower[FULU_GP_MAX_PARAMS];   /* log-bounds, ln(1e-5) */
   double upper[FULU_GP_MAX_PARAMS];   /* ln(1e5) */
   double* profile;           /* optional HOST pointer to 10 doubles, filled on return: [0] evaluation rounds, [1] ms spent in the
-                                evaluation kernel (CUDA events on `stream`), [2] ms in the optimiser-step kernel, [3] kernels launched,
+                                evaluation kernel (CUDA events on `stream`), [2] ms in the optimiser-step kernel, [3] kernels this call launched,
                                 [4] window, [5] evaluation grid (CTAs), [6] dynamic shared memory per CTA (bytes), [7] 1 if K lives in
                                 global memory, [8] threads per evaluation CTA, [9] evaluation CTAs per SM.  NULL = no per-launch timing. */
 } fulu_gp_fit_options;
