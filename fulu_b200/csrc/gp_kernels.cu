@@ -579,7 +579,17 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     finished = true;
     ++launches;
   }
-  while (!finished && round < w.max_rounds) {
+  // Rounds are launched in groups, and one group is always queued ahead of the one whose live-slot count the host is waiting for
+  // (the count is read on a second stream behind an event), so the GPU never waits for the host between groups: a late host
+  // thread costs nothing, an early finish costs at most one group of empty launches.
+  cudaStream_t cs = nullptr;
+  cudaEvent_t mark[2] = {nullptr, nullptr};
+  int mark_round[2] = {0, 0};
+  if (!finished) {
+    CU_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreateWithFlags(&mark[i], cudaEventDisableTiming));
+  }
+  auto launch_group = [&](int which) -> int {
     int upto = round + group;
     if (upto > w.max_rounds) upto = w.max_rounds;
     for (; round < upto; ++round) {
@@ -594,19 +604,35 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
       launches += 2;
     }
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(mark[which], st));
+    mark_round[which] = round;
+    return 0;
+  };
+  int cur = 0;
+  if (!finished && (rc = launch_group(cur))) return rc;
+  while (!finished) {
+    const bool more = round < w.max_rounds;
+    if (more && (rc = launch_group(cur ^ 1))) return rc;   // the next group is queued before the host waits
     int32_t remaining = 0;
-    CU_TRY(cudaMemcpyAsync(&remaining, d.counts + round, 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaStreamWaitEvent(cs, mark[cur], 0));
+    CU_TRY(cudaMemcpyAsync(&remaining, d.counts + mark_round[cur], 4, cudaMemcpyDeviceToHost, cs));
+    CU_TRY(cudaStreamSynchronize(cs));
     if (remaining == 0) { finished = true; break; }
-    if (use_tail && remaining <= w.grid_eval) {
+    if (use_tail && remaining <= w.grid_eval) {   // (the count can only have gone down since: an upper bound on the CTAs needed)
       ops->tail(w.globalA, (unsigned)remaining, w.threads_eval, w.smem_eval, st, d, round);
       CU_TRY(cudaGetLastError());
       finished = true;
       ++launches;
       break;
     }
+    if (!more) break;   // round cap reached with live slots: flushed below
     if (remaining < 8 * w.grid_eval) group = 4;   // close to the tail: look more often
     else if (group < kMaxGroup) group *= 2;
+    cur ^= 1;
+  }
+  if (cs) {
+    cudaStreamDestroy(cs);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(mark[i]);
   }
   if (opt->profile != nullptr) {
     double eval_ms = 0.0, step_ms = 0.0;
