@@ -130,11 +130,15 @@ class ClockSampler:
     def __init__(self, gpu_index, period_s=0.1):
         self.gpu, self.period, self.proc, self.path = gpu_index, period_s, None, f"/tmp/fulu_clocks_{os.getpid()}.csv"
         self.thread, self.stop_flag, self.sm, self.mx, self.reasons, self.how = None, False, [], [], set(), None
+        self.active = False   # the thread exists from prepare() on (NVML initialised outside the timed region) and samples only while active
 
     def _nvml_loop(self, nv, h):
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
         while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.005)
+                continue
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
@@ -146,7 +150,16 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation and thread start, to be called well before the timed region: nvmlInit takes tens of milliseconds and
+        driver locks, and doing it at the start of the timed region stalled the launching thread on some runs."""
+        self.start(active=False)
+
+    def start(self, active=True):
+        if self.thread is not None or self.proc is not None:
+            self.active = active
+            return
+        self.active = active
         try:
             import threading
 
@@ -259,6 +272,9 @@ def run_gpu(args):
                               "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"}
 
     engine = fulu_b200.GPEngine(torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
     spec = kernel_spec_from_sklearn(make_kernel(args.kernel))
     B = args.curves or default_b
     host = make_workload(args.workload, B, rank)
@@ -284,7 +300,6 @@ def run_gpu(args):
     peak_dmma = engine.fp64_peak(1)
 
     # ---- timed: resident inputs
-    sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
