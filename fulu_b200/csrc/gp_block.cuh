@@ -69,6 +69,8 @@ struct GpSmem {
   double* v;      // np   x_i1 / l_lambda
   double* red;    // reduction scratch, GP_RED doubles (32 warps x 6 values)
   double* tab;    // [0..15] c 2^(j/16), [16..31] 2^(j/16): the exponential's table (gp_exp_tab), rebuilt per evaluation
+  double* kslab;  // optional: this CTA's slab in global memory (L2) that keeps the assembled K tiles, row-major 8x8, for the gradient
+                  // pass (null: K_ij is recomputed there)
   int* flag;      // [0] = Cholesky breakdown
   int np, T;
 };
@@ -93,6 +95,7 @@ GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
   s.v = p; p += s.np;
   s.red = p; p += GP_RED;
   s.tab = p; p += 32;
+  s.kslab = nullptr;
   s.flag = (int*)p;
   return s;
 }
@@ -260,6 +263,7 @@ struct GpKern {
   static constexpr int NEX = (EX == GP_F_NONE) ? 0 : (EX == GP_F_RQ ? 2 : 1);
   static constexpr int P = 4 + NF1 + NEX;   // hyperparameters
   static constexpr int NTR = P - 1;         // traces over the strictly-lower pairs: every parameter but the noise level
+  static constexpr bool kKeepK = (F1 == GP_F_NONE && EX == GP_F_NONE);   // every off-diagonal derivative is K_ij times a weight
   double cst, s2, lt, ll;
   double xminc;        // arguments of the amplitude-scaled exponential below this give 0
   const double* tabc;  // c 2^(j/16) (GpSmem::tab)
@@ -308,6 +312,13 @@ struct GpKern {
       if constexpr (EX == GP_F_RQ) { tr[3 + NF1] += w * ga; tr[NTR - 1] += w * gl; }
       else tr[3 + NF1] += w * gl;
     }
+  }
+  // the same with K_ij given (default family only: dK/dlog c = K, dK/dlog l_d = K d_d^2)
+  GP_DEV void accumulate_stored(double w, double k, double du2, double dv2, double (&tr)[NTR]) const {
+    const double wk = w * k;
+    tr[0] += wk;
+    tr[1] += wk * du2;
+    tr[2] += wk * dv2;
   }
   // gradient of the LML from the pair traces and trd = sum_i W_ii (the 1/2 of Eq. 5.9 cancels against the two triangles)
   GP_DEV void gradient(const double* tr, double trd, double* grad) const {
@@ -369,6 +380,10 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Ke
     }
     tp[f.a0] = v0;
     tp[f.a1] = v1;
+    if (Kern::kKeepK && s.kslab != nullptr) {   // a copy of the tile for the gradient pass, which then needs no second exponential
+      s.kslab[64 * q + 8 * g + t] = v0;
+      s.kslab[64 * q + 8 * g + 4 + t] = v1;
+    }
     J += c.nwarp;
     while (J > I) { J -= I + 1; ++I; }
   }
@@ -640,8 +655,11 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
   trd = 0.0;
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
+  const bool stored = Kern::kKeepK && s.kslab != nullptr;
   for (int q = c.warp; q < ntile; q += c.nwarp) {
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+    GpPair kst = {0.0, 0.0};
+    if (stored) kst = *reinterpret_cast<const GpPair*>(s.kslab + 64 * q + 8 * g + 2 * t);   // K[i][j], K[i][j + 1]: in flight during the products
     // K^-1[i][j] = sum_{k >= i, k != n} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
     // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
     const double* Xi = A + gp_tile(I, I);
@@ -664,8 +682,13 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     // strictly-lower entries inside the curve count (K_ij and its derivatives are recomputed, not stored); on a diagonal tile
     // the diagonal feeds trd
     const bool in = i < n;
-    kn.accumulate((in && i > j) ? w0 : 0.0, du0s, dv0s, tr);
-    kn.accumulate((in && i > j + 1) ? w1 : 0.0, du1s, dv1s, tr);
+    if (stored) {
+      kn.accumulate_stored((in && i > j) ? w0 : 0.0, kst.x, du0s, dv0s, tr);
+      kn.accumulate_stored((in && i > j + 1) ? w1 : 0.0, kst.y, du1s, dv1s, tr);
+    } else {
+      kn.accumulate((in && i > j) ? w0 : 0.0, du0s, dv0s, tr);
+      kn.accumulate((in && i > j + 1) ? w1 : 0.0, du1s, dv1s, tr);
+    }
     if (I == J) trd += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
     J += c.nwarp;
     while (J > I) { J -= I + 1; ++I; }

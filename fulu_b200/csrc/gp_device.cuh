@@ -78,6 +78,12 @@ __device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stri
   return gp_carve(gA + (size_t)blockIdx.x * gA_stride, smem, n);
 }
 
+// shared-memory classes: the same per-CTA slab region keeps a copy of the assembled K tiles for the gradient pass (GpSmem::kslab)
+template <bool kGlobalA>
+__device__ __forceinline__ void attach_kslab(GpSmem& s, double* gA, size_t gA_stride) {
+  if (!kGlobalA && gA != nullptr && gA_stride > 0) s.kslab = gA + (size_t)blockIdx.x * gA_stride;
+}
+
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
 template <class Kern, bool kGlobalA>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
@@ -93,6 +99,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab,
     }
     GpCurveView cv = curve_view(tab, cu);
     GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
+    attach_kslab<kGlobalA>(s, gA, gA_stride);
     double l, g[Kern::P];
     bool ok;
     gp_eval_lml_grad<Kern>(c, cv, theta + cu * P, s, l, g, ok);
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
     GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
+    attach_kslab<kGlobalA>(s, d.gA, d.gA_stride);
     double l, g[Kern::P];
     bool ok;
     gp_eval_lml_grad<Kern>(c, cv, d.slots[slot].x, s, l, g, ok);
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, 
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
     GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
+    attach_kslab<kGlobalA>(s, d.gA, d.gA_stride);
     double l, g[FG_MAXP];
     bool ok;
     gp_eval_lml_grad<Kern>(c, cv, d.slots[slot].x, s, l, g, ok);
@@ -319,7 +328,7 @@ struct GpFamilyLaunch {
       lml_kernel<Kern, true><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
     } else {
       if ((rc = gp_set_smem(lml_kernel<Kern, false>, smem))) return rc;
-      lml_kernel<Kern, false><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, nullptr, 0, marks);
+      lml_kernel<Kern, false><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
     }
     return (int)cudaGetLastError();
   }

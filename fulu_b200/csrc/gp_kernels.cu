@@ -103,7 +103,8 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.run_x = take(tasks * (size_t)FG_MAXP * 8);
   w.run_nev = take(tasks * 4);
   w.run_end = take(tasks * 4);
-  w.gA_stride = w.globalA ? gp_mat_doubles((int)np) : 0;
+  // per-CTA slab: the matrix itself for long curves, a copy of the K tiles for the gradient pass otherwise (FULU_GP_NO_KSLAB=1: none)
+  w.gA_stride = w.globalA ? gp_mat_doubles((int)np) : (getenv("FULU_GP_NO_KSLAB") ? 0 : 64 * ((np / GP_NB) * (np / GP_NB + 1) / 2));
   w.gA = take((size_t)w.grid_eval * w.gA_stride * 8);
   w.gV_stride = globalV ? vtiles / sizeof(double) : 0;
   w.gV = take((size_t)w.grid_predict * w.gV_stride * 8);
