@@ -332,15 +332,17 @@ using GpKernDefault = GpKern<GP_F_NONE, GP_F_NONE>;   // C * RBF([l_t, l_lambda]
 // Scaled coordinates and the exponential's tables into shared memory; binds the kernel to the tables.
 template <class Ctx, class Kern>
 GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, Kern& kn) {
-  const double lt = kn.lt, ll = kn.ll;
+  // X / length_scale (kernels.py:1561) as a multiplication by the reciprocal: an FP64 division is ~25 instructions, two per
+  // observation and evaluation; the 1-ulp difference is far below the parity tolerance
+  const double ilt = 1.0 / kn.lt, ill = 1.0 / kn.ll;
   kn.tabc = s.tab;
   kn.f1.tab = s.tab + 16;
   kn.ex.tab = s.tab + 16;
   if (c.tid < 32) s.tab[c.tid] = (c.tid < 16 ? kn.cst : 1.0) * gp_exp2_tab[c.tid & 15];
   for (int i = c.tid; i < s.np; i += c.nthr) {
     if (i < cv.n) {
-      s.u[i] = cv.xs[i] / lt;              // X / length_scale  (kernels.py:1561)
-      s.v[i] = cv.lam[cv.band[i]] / ll;
+      s.u[i] = cv.xs[i] * ilt;
+      s.v[i] = cv.lam[cv.band[i]] * ill;
     } else {
       s.u[i] = 0.0; s.v[i] = 0.0;
     }
@@ -815,8 +817,8 @@ GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, con
       if (qd.n_obs > 0) { bq = q / qd.n_obs; tq = gp_linspace(qd.t_min, qd.t_max, qd.n_obs, q - bq * qd.n_obs); }
       else { tq = qd.qt[q]; bq = qd.qband[q]; }
     }
-    uq[e] = ((tq - stats[0]) / stats[1]) / kn.lt;   // ss.transform then X / length_scale
-    vq[e] = cv.lam[bq] / kn.ll;
+    uq[e] = ((tq - stats[0]) / stats[1]) * (1.0 / kn.lt);   // ss.transform then X / length_scale (scaled like the training points)
+    vq[e] = cv.lam[bq] * (1.0 / kn.ll);
   }
   // a V tile holds element (row k, query n) at 8 k + (n ^ (k & 2 ? 4 : 0)): the 16-byte stores in accumulator layout
   // ([row g][queries 2t, 2t + 1]) and the 8-byte loads in B-operand layout ([k = t][n = g], [k = 4 + t][n = g]) are then both
