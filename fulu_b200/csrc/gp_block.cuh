@@ -339,12 +339,18 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, Kern& 
   kn.f1.tab = s.tab + 16;
   kn.ex.tab = s.tab + 16;
   if (c.tid < 32) s.tab[c.tid] = (c.tid < 16 ? kn.cst : 1.0) * gp_exp2_tab[c.tid & 15];
+  // the noise diagonal and y ride in the scratch column until the triangular inverse needs it: the assembly then reads them from
+  // shared memory instead of waiting on global loads in its diagonal and border tiles
+  double* sc = s.A + gp_tile(s.T, 0);
   for (int i = c.tid; i < s.np; i += c.nthr) {
     if (i < cv.n) {
       s.u[i] = cv.xs[i] * ilt;
       s.v[i] = cv.lam[cv.band[i]] * ill;
+      sc[i] = cv.al[i];
+      sc[s.np + i] = cv.y[i];
     } else {
       s.u[i] = 0.0; s.v[i] = 0.0;
+      sc[i] = 0.0; sc[s.np + i] = 0.0;
     }
   }
   if (c.tid == 0) s.flag[0] = 0;
@@ -356,6 +362,8 @@ template <class Ctx, class Kern>
 GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Kern& kn) {
   const int T = s.T, n = cv.n, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const GpFrag f = gp_frag(c.lane);
+  const double* al = s.A + gp_tile(T, 0);   // staged by gp_load_curve in the scratch column
+  const double* yv = al + s.np;
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
@@ -370,15 +378,15 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Ke
     if (i >= n || j1 >= n) v1 = 0.0;
     // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding; the border's own diagonal entry
     // starts at 0 and collects -z.z during the factorisation (its pivot is taken as 1)
-    if (i == j0) v0 = (i < n) ? kn.diag() + cv.al[i] : (i == n ? 0.0 : 1.0);
-    if (i == j1) v1 = (i < n) ? kn.diag() + cv.al[i] : (i == n ? 0.0 : 1.0);
+    if (i == j0) v0 = (i < n) ? kn.diag() + al[i] : (i == n ? 0.0 : 1.0);
+    if (i == j1) v1 = (i < n) ? kn.diag() + al[i] : (i == n ? 0.0 : 1.0);
     // the border: row n = y^T, and its mirror image in the last diagonal tile
     if (i == n) {
-      if (j0 < n) v0 = cv.y[j0];
-      if (j1 < n) v1 = cv.y[j1];
+      if (j0 < n) v0 = yv[j0];
+      if (j1 < n) v1 = yv[j1];
     } else if (i < n) {
-      if (j0 == n) v0 = cv.y[i];
-      if (j1 == n) v1 = cv.y[i];
+      if (j0 == n) v0 = yv[i];
+      if (j1 == n) v1 = yv[i];
     }
     tp[f.a0] = v0;
     tp[f.a1] = v1;
