@@ -89,3 +89,26 @@ def test_exp_accuracy():
     err = np.abs((got - ref) / ref).astype(np.float64) / 2.0 ** -52
     assert err.max() < 1.6
     np.testing.assert_array_equal(H.exp_neg(np.array([0.0, -0.0, -1e-300, -690.5, -709.0, -1e6, -np.inf])), [1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0])
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 15, 16, 17, 24, 31, 32, 33])
+def test_block_sizes_around_tile_boundaries(n):
+    """The bordered layout at every position of the border row inside its tile (n mod 8 = 0 opens a tile-row of its own) and at
+    one and two tile-rows: LML, gradient and prediction against the closed-form oracle, default kernel and the 6-parameter one."""
+    g = load_golden("csv34299")
+    rng = np.random.default_rng(n)
+    t, f, e, b = g["t"][:n], g["flux"][:n] + rng.normal(size=n), g["flux_err"][:n], g["band"][:n]
+    p2l = {i: float(v) for i, v in enumerate(g["loglam"])}
+    p = H.prepare(t, f, e, b, g["loglam"], False, nthr=64)
+    for kind in (0, 34):
+        gp = O.ClosedFormGP(p2l, kind=kind).prepare(t, f, e, b)
+        th = rng.uniform(-1, 1, O.n_params(kind))
+        lml, grad, ok = H.lml_grad(p, th, nthr=64, family=kind)
+        l2, g2, gs = O.lml_and_grad(gp.X, gp.y, gp.alpha, th, kind, return_scale=True)
+        assert ok and abs(lml - l2) <= 1e-10 * max(1.0, abs(l2))
+        assert np.max(np.abs(grad - g2) / np.maximum(np.maximum(np.abs(g2), 1e-2 * gs), 1e-30)) < 1e-9
+        gp.fit(t, f, e, b, theta=th)
+        _, mo, so, _ = gp.augmentation(t.min(), t.max() + 1.0, 5)
+        m, s, l3, st = H.predict_grid(p, th, len(g["loglam"]), 5, float(t.min()), float(t.max() + 1.0), nthr=64, family=kind)
+        assert st == 0 and abs(l3 - l2) <= 1e-10 * max(1.0, abs(l2))
+        assert relerr(m, mo, floor=1e-3 * gp.y_std) < 1e-9 and relerr(s, so, floor=1e-6 * gp.y_std) < 1e-8
