@@ -82,14 +82,16 @@ extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const
 #define HOST_FAMILIES(X) X(0, 0) X(0, 1) X(0, 2) X(0, 3) X(0, 4) X(2, 0) X(2, 2)
 
 template <class Kern>
-static int lml_impl(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+static int lml_impl(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
                     const double* theta, int nthr, double* lml, double* grad) {
   std::vector<double> smem(gp_smem_doubles(n));
+  std::vector<double> kslab(gp_mat_doubles(gp_pad(n)));
   GpCurveView cv{n, xs, band, y, al, lam};
   int okout = 0;
   const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
     GpSmem s = gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
+    if (family & 0x200) s.kslab = kslab.data();   // bit 9: the gradient pass reads K back from a slab instead of recomputing it
     double l, g[Kern::P];
     bool ok;
     gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
@@ -100,7 +102,7 @@ static int lml_impl(int n, const double* xs, const int32_t* band, const double* 
 
 extern "C" int host_gp_lml(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
                            const double* theta, int nthr, double* lml, double* grad) {
-#define X(F1, EX) if (family == ((F1) | ((EX) << 4))) return lml_impl<GpKern<F1, EX>>(n, xs, band, y, al, lam, theta, nthr, lml, grad);
+#define X(F1, EX) if ((family & 0xff) == ((F1) | ((EX) << 4))) return lml_impl<GpKern<F1, EX>>(family, n, xs, band, y, al, lam, theta, nthr, lml, grad);
   HOST_FAMILIES(X)
 #undef X
   return -1;

@@ -42,6 +42,20 @@ def test_block_lml_grad_predict(name, nthr):
     assert abs(lml - float(g["lml_star"])) <= 1e-9 * max(1.0, abs(float(g["lml_star"])))
 
 
+@pytest.mark.parametrize("name", ["csv34299", "readme_err", "ztf_5"])
+def test_block_stored_k_gradient_equals_recomputed(name):
+    """Default family: the gradient pass fed from the K slab the assembly filled (what the GPU path does, there in L2) against the
+    pass that recomputes K_ij - same LML bit for bit, gradient to rounding; and against the reference fixture."""
+    g = load_golden(name)
+    p = H.prepare(g["t"], g["flux"], g["flux_err"], g["band"], g["loglam"], bool(g["use_err"]), nthr=128)
+    for k in (0, 2, 5, 6):
+        a = H.lml_grad(p, g["thetas"][k], nthr=128, family=0)
+        b = H.lml_grad(p, g["thetas"][k], nthr=128, family=0x200)
+        assert a[2] and b[2] and a[0] == b[0]
+        np.testing.assert_allclose(b[1], a[1], rtol=1e-11, atol=1e-12 * np.abs(a[1]).max())
+        assert abs(b[0] - g["lml"][k]) <= 1e-9 * max(1.0, abs(g["lml"][k]))
+
+
 def test_block_not_positive_definite_is_reported():
     # duplicate observations with (almost) no noise: K is numerically singular
     t = np.array([0.0, 0.0, 1.0, 1.0, 2.0, 2.0, 3.0, 3.0])
