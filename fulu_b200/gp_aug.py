@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from .datasets import CurveBatch
+from .plotting import LcPlotter
 from .engine import (STATUS_AT_BOUND, STATUS_BAD_INPUT, STATUS_NEG_VARIANCE, STATUS_NOT_CONVERGED, STATUS_NOT_PD, DeviceBatch, GPEngine,
                      kernel_spec_from_sklearn)
 
@@ -101,6 +102,7 @@ class GaussianProcessesAugmentation:
 
     def __init__(self, passband2lam, kernel=None, use_err=False, device=None):
         self.passband2lam = passband2lam
+        self.plotter = LcPlotter(passband2lam)   # fulu/_base_aug.py:37; matplotlib is imported when something is drawn
         self.t_train = None
         self.flux_train = None
         self.flux_err_train = None
@@ -177,3 +179,42 @@ class GaussianProcessesAugmentation:
         t_aug, passband_aug = create_aug_data(t_min, t_max, tuple(self.passband2lam), n_obs)
         flux_aug, flux_err_aug = self.predict(t_aug, passband_aug)
         return t_aug, flux_aug, flux_err_aug, passband_aug
+
+    def _peak_on_device(self, t_min, t_max, n_obs):
+        """Grid augmentation, band-summed curve and its peak through the batched grid / peak kernels
+        (fulu_gp_predict_grid_batch, fulu_gp_peak_batch) -> (t_aug, flux_aug, flux_err_aug, passband_aug), (t_grid, sum), peak_t."""
+        if self._batch is None:
+            raise RuntimeError("fit must be called before plot")
+        lo = torch.tensor([float(t_min)], dtype=torch.float64)
+        hi = torch.tensor([float(t_max)], dtype=torch.float64)
+        grid = self._engine.predict_grid(self._batch, self._theta, n_obs, lo, hi)
+        if int(grid["status"].cpu()[0]) & STATUS_NOT_PD:
+            raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix.")
+        pk = self._engine.peak(self._batch, grid["mean"], lo, hi, want_sum=True)
+        t_aug, passband_aug = create_aug_data(t_min, t_max, tuple(self.passband2lam), n_obs)
+        approx = (t_aug, grid["mean"].cpu().numpy().reshape(-1), grid["std"].cpu().numpy().reshape(-1), passband_aug)
+        return approx, (t_aug[:n_obs], pk["sum_flux"].cpu().numpy()[0]), float(pk["peak_t"].cpu()[0])
+
+    def _plot_passband(self, passband, ax, approx=None):
+        """Train points of one passband and, if given, its approximation with the one-sigma band (fulu/_base_aug.py:116-158)."""
+        self.plotter.errorbar_passband(self.t_train, self.flux_train, self.flux_err_train, self.passband_train, passband, ax=ax)
+        if approx:
+            self.plotter._draw_approx(ax, *approx, passband)
+
+    def plot(self, *, plot_approx=True, n_approx=1000, passband=None, ax=None, true_peak=None, plot_peak=False, title="", save=None):
+        """Train points with errors for all passbands (or one) on one graph, the approximation curves, optionally the true and the
+        predicted peak; same keywords and drawing order as fulu/_base_aug.py:160-230.  The approximation, the band-summed curve
+        and its peak come from the device (grid and peak kernels); matplotlib only draws."""
+        if ax is None:
+            ax = self.plotter._ax_adjust()
+        approx, (t_sum, f_sum), peak_t = self._peak_on_device(np.min(self.t_train), np.max(self.t_train), n_approx)
+        for band in (self.passband2lam if passband is None else (passband,)):
+            self._plot_passband(band, ax, approx if plot_approx else None)
+        if true_peak is not None:
+            self.plotter.plot_true_peak(true_peak=true_peak, ax=ax)
+        if plot_peak:
+            self.plotter._draw_sum(ax, t_sum, f_sum)    # LcPlotter.plot_sum_passbands (plotting.py:78-100) with the device's band sum
+            self.plotter._finish(ax, "", None)
+            self.plotter._draw_peak(ax, peak_t)         # LcPlotter.plot_peak (plotting.py:102-123) with the device's arg-max
+            self.plotter._finish(ax, "", None)
+        return self.plotter._finish(ax, title, save, title_first=True)
