@@ -2,6 +2,7 @@
 // stands in for __syncthreads, a per-warp barrier for __syncwarp, and the warp-collective DMMA / shuffle instructions are
 // emulated through a per-warp scratch area, so the block algorithm can be checked against the oracle without a GPU.
 #include <barrier>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -14,11 +15,24 @@ struct WarpShared {
   double a[32], b[32], x[32];
 };
 
+#ifdef SAN_SKIP_SYNC
+static int san_block_index = -1;   // written between run_block calls only
+#endif
+
 struct HostCtx {
   int tid, nthr, lane, warp, nwarp;
   std::barrier<>* block_bar;
   WarpShared* ws;
+#ifdef SAN_SKIP_SYNC   // self-test of the sanitizer run (sanitize_main.cpp): every thread drops its $SAN_SKIP_SYNC-th block barrier
+  int nsync = 0;
+  void sync() {   // $SAN_SKIP_BLOCK: which run_block call of the process (0 = prepare, 1 = lml, 2 = predict in sanitize_main)
+    static const int skip = getenv("SAN_SKIP_SYNC") ? atoi(getenv("SAN_SKIP_SYNC")) : 0;
+    static const int blk = getenv("SAN_SKIP_BLOCK") ? atoi(getenv("SAN_SKIP_BLOCK")) : 1;
+    if (++nsync != skip || san_block_index != blk) block_bar->arrive_and_wait();
+  }
+#else
   void sync() { block_bar->arrive_and_wait(); }
+#endif
   void mark(int) {}
   long long clock() { return 0; }
   void mark_value(int, long long) {}
@@ -54,6 +68,9 @@ struct HostCtx {
 template <class F>
 static void run_block(int nthr, F&& body) {
   const int nwarp = nthr / 32;
+#ifdef SAN_SKIP_SYNC
+  ++san_block_index;
+#endif
   std::barrier<> bar(nthr);
   std::vector<std::unique_ptr<WarpShared>> ws;
   for (int w = 0; w < nwarp; ++w) ws.emplace_back(new WarpShared);
