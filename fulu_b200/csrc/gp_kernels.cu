@@ -31,6 +31,7 @@ struct WsLayout {
   size_t gA, gV;                                                              // per-CTA global scratch
   size_t total;
   int window, max_rounds, grid_eval, grid_predict, threads_eval, occ_eval;
+  bool stream_tail;   // the default window of a long-curve class: the whole fit in fit_tail_kernel
   size_t gA_stride, gV_stride;   // doubles per CTA
   bool globalA;
   size_t smem_eval, smem_predict;
@@ -80,7 +81,15 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   if (occ_p > 2) occ_p = 2;
   if (occ_p < 1) occ_p = 1;
   w.grid_predict = sms * occ_p;
-  if (window <= 0) window = kDefaultWindow;
+  // Long curves (one CTA per SM, matrix in a global slab: an evaluation is 3 .. 190 ms): by default the window is one slot per CTA
+  // and the whole fit runs in the fused kernel, in which a CTA that finishes a run pulls the next task at once.  Rounds would make
+  // every slot wait for the slowest evaluation of the round (lengths are mixed in these classes) and run a second, partly empty
+  // wave whenever more slots are live than CTAs; the optimiser step on one thread (~80 us) is nothing next to such an evaluation.
+  w.stream_tail = false;
+  if (window <= 0) {
+    if (w.globalA && occ == 1) { window = w.grid_eval; w.stream_tail = true; }
+    else window = kDefaultWindow;
+  }
   size_t tasks = (size_t)(b.order ? b.n_order : b.n_curves) * (size_t)(S > 0 ? S : 1);
   if ((size_t)window > tasks) window = (int)(tasks > 0 ? tasks : 1);
   w.window = window;
@@ -574,8 +583,9 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   bool finished = false;
   // the tail (and every small fit): once the live slots fit one wave of CTAs, one fused launch finishes them (fit_tail_kernel)
   const bool use_tail = !prof && getenv("FULU_GP_NO_TAIL") == nullptr;
-  if (use_tail && d.n_tasks <= (int64_t)w.grid_eval) {
-    ops->tail(w.globalA, (unsigned)d.n_tasks, w.threads_eval, w.smem_eval, st, d, 0);
+  if (use_tail && (d.n_tasks <= (int64_t)w.grid_eval || w.stream_tail)) {
+    const unsigned ctas = (unsigned)(d.n_tasks < (int64_t)w.window ? d.n_tasks : (int64_t)w.window);   // fit_init_kernel filled that many slots at most
+    ops->tail(w.globalA, ctas, w.threads_eval, w.smem_eval, st, d, 0);
     CU_TRY(cudaGetLastError());
     finished = true;
     ++launches;

@@ -95,7 +95,9 @@ typedef struct fulu_gp_fit_options {
   int32_t maxiter;           /* 15000 */
   int32_t maxfun;            /* 15000 */
   int32_t maxls;             /* 20 */
-  int32_t window;            /* optimiser instances resident at once (0 = default) */
+  int32_t window;            /* optimiser instances resident at once (0 = default: one per task up to 65,536; for curves whose matrix
+                                lives in global memory with one CTA per SM, n_max >= 512, one per CTA - the fit then runs in one fused launch
+                                whose CTAs pull the next run as soon as theirs ends; results do not depend on the window) */
   int32_t max_rounds;        /* hard cap on evaluation rounds (0 = default) */
   int32_t starts_per_curve;  /* 0: theta_starts is [S,P], shared by all curves (sklearn's restarts); 1: [B,S,P], indexed by curve id
                                 (e.g. S = 1 continuation runs from each curve's current optimum) */

@@ -217,3 +217,30 @@ def test_config5_fit_reaches_oracle_lml(engine):
             warnings.simplefilter("ignore")
             _, lml_ref, _ = O.fit_theta(gp.X, gp.y, gp.alpha)
         assert float(fit["lml"][i]) >= lml_ref - 1e-6, (i, float(fit["lml"][i]), lml_ref)
+
+
+def test_long_curve_fit_streams_runs_through_one_launch(engine, monkeypatch):
+    """Curves whose matrix lives in global memory with one CTA per SM (n_max >= 512): by default the fit runs in one fused launch
+    whose CTAs pull the next (curve, start) run as soon as theirs ends (window = CTAs < tasks).  Same runs, same numbers as on
+    rounds of two launches (FULU_GP_NO_TAIL=1), bit for bit; mixed lengths, more tasks than CTAs, one unusable curve in the queue."""
+    from fulu_b200 import CurveBatch, DeviceBatch, datasets
+
+    parts = [datasets.ddf_like(14, n_points=n, first=60 + 20 * k) for k, n in enumerate((560, 520))]
+    curves = [p.curve(i) for p in parts for i in range(p.n_curves)]
+    t, f, e, b = curves[3]
+    curves[3] = (t, np.where(np.arange(len(f)) == 5, np.nan, f), e, b)     # NaN flux: skipped by the task queue, flagged
+    hb = CurveBatch.from_curves(curves, parts[0].loglam)
+    db = DeviceBatch.from_host(hb, engine.device)
+    assert db.n_curves * 6 > torch.cuda.get_device_properties(engine.device).multi_processor_count
+    a = engine.fit(db, profile="counts")
+    assert a["profile"]["rounds"] == 0 and a["profile"]["global_a"] == 1 and a["profile"]["ctas_per_sm"] == 1   # no rounds: one fused launch
+    assert a["profile"]["window"] == a["profile"]["grid_eval"]
+    monkeypatch.setenv("FULU_GP_NO_TAIL", "1")
+    r = engine.fit(db, profile="counts")
+    assert r["profile"]["rounds"] > 0
+    for k in ("theta", "lml", "n_eval", "status"):
+        x, y = a[k].cpu().numpy(), r[k].cpu().numpy()
+        ok = np.arange(db.n_curves) != 3
+        assert np.array_equal(x[ok], y[ok]), k
+    assert int(a["status"][3]) & 1 and int(r["status"][3]) & 1
+    assert np.all(a["n_eval"].cpu().numpy()[np.arange(db.n_curves) != 3] > 6)
