@@ -26,3 +26,14 @@ print("theta* =", aug.reg.kernel_.theta, " LML* =", aug.reg.log_marginal_likelih
 for band in passband2lam:
     sel = passband_aug == band
     print(f"band {band}: flux in [{flux_aug[sel].min():.3f}, {flux_aug[sel].max():.3f}], mean error {flux_err_aug[sel].mean():.3f}")
+
+try:   # the reference's README ends with the visualisation (README.md:60-64): same calls, drawn only where matplotlib is installed
+    import matplotlib  # noqa: F401
+except ImportError:
+    print("matplotlib is not installed: skipping LcPlotter.plot_one_graph_all(...)")
+else:
+    from fulu_b200 import LcPlotter                         # instead of: fulu.LcPlotter
+
+    plotic = LcPlotter(passband2lam)
+    plotic.plot_one_graph_all(t=t, flux=flux, flux_err=flux_err, passbands=passbands, t_approx=t_aug, flux_approx=flux_aug,
+                              flux_err_approx=flux_err_aug, passband_approx=passband_aug, save="readme_example.png")

@@ -6,6 +6,7 @@ from .datasets import CurveBatch  # noqa: F401
 from .engine import (AugmentResult, DeviceBatch, GPEngine, KernelSpec, fit_augment_batch, fit_augment_device, fit_augment_table,  # noqa: F401
                      kernel_spec_from_sklearn, pin_results)
 from .gp_aug import ConvergenceWarning, GaussianProcessesAugmentation, add_log_lam, create_aug_data  # noqa: F401
+from .plotting import LcPlotter  # noqa: F401  (fulu.LcPlotter, README.md:61; imports matplotlib only when something is drawn)
 
 __all__ = ["GaussianProcessesAugmentation", "fit_augment_batch", "GPEngine", "DeviceBatch", "CurveBatch", "KernelSpec", "AugmentResult",
-           "add_log_lam", "create_aug_data", "ConvergenceWarning", "fit_augment_table", "kernel_spec_from_sklearn"]
+           "add_log_lam", "create_aug_data", "ConvergenceWarning", "fit_augment_table", "kernel_spec_from_sklearn", "LcPlotter"]
