@@ -397,7 +397,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "curves/s", "h2d_bytes_per_step": int(res.h2d_bytes), "d2h_bytes_per_step": int(res.d2h_bytes)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel" if rounds else "fit_tail_kernel (long-curve classes: the whole fit is one fused launch)", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
                      "frac": achieved / peak_dfma if peak_dfma else None, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": (mean_in + 8 * 4 + 8 * 5) * (evals_all / world) / max(rounds, 1),
                      "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",

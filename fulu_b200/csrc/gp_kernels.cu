@@ -583,9 +583,16 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   bool finished = false;
   // the tail (and every small fit): once the live slots fit one wave of CTAs, one fused launch finishes them (fit_tail_kernel)
   const bool use_tail = !prof && getenv("FULU_GP_NO_TAIL") == nullptr;
-  if (use_tail && (d.n_tasks <= (int64_t)w.grid_eval || w.stream_tail)) {
+  cudaEvent_t tail_ev[2] = {nullptr, nullptr};   // profiling a streamed fit: the fused launch is the evaluation kernel of that fit
+  const bool streamed = w.stream_tail && getenv("FULU_GP_NO_TAIL") == nullptr;
+  if ((use_tail && d.n_tasks <= (int64_t)w.grid_eval) || streamed) {
     const unsigned ctas = (unsigned)(d.n_tasks < (int64_t)w.window ? d.n_tasks : (int64_t)w.window);   // fit_init_kernel filled that many slots at most
+    if (prof) {
+      for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreate(&tail_ev[i]));
+      cudaEventRecord(tail_ev[0], st);
+    }
     ops->tail(w.globalA, ctas, w.threads_eval, w.smem_eval, st, d, 0);
+    if (prof) cudaEventRecord(tail_ev[1], st);
     CU_TRY(cudaGetLastError());
     finished = true;
     ++launches;
@@ -656,6 +663,13 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
         step_ms += b;
       }
       for (cudaEvent_t e : ev) cudaEventDestroy(e);
+      if (tail_ev[0] != nullptr) {
+        float a = 0.f;
+        cudaEventSynchronize(tail_ev[1]);
+        cudaEventElapsedTime(&a, tail_ev[0], tail_ev[1]);
+        eval_ms += a;
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(tail_ev[i]);
+      }
     }
     double* pr = opt->profile;
     pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = launches + (finished ? 0 : 1); pr[4] = w.window; pr[5] = w.grid_eval;

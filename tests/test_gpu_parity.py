@@ -235,6 +235,8 @@ def test_long_curve_fit_streams_runs_through_one_launch(engine, monkeypatch):
     a = engine.fit(db, profile="counts")
     assert a["profile"]["rounds"] == 0 and a["profile"]["global_a"] == 1 and a["profile"]["ctas_per_sm"] == 1   # no rounds: one fused launch
     assert a["profile"]["window"] == a["profile"]["grid_eval"]
+    timed = engine.fit(db, profile=True)["profile"]     # with per-launch events: still the one fused launch, now timed
+    assert timed["rounds"] == 0 and timed["eval_ms"] > 0.0 and timed["step_ms"] == 0.0
     monkeypatch.setenv("FULU_GP_NO_TAIL", "1")
     r = engine.fit(db, profile="counts")
     assert r["profile"]["rounds"] > 0
