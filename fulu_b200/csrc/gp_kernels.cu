@@ -131,6 +131,7 @@ struct PrepArgs {
   const double *t, *flux, *ferr, *loglam;
   const int32_t* band;
   int n_bands, use_err;
+  int n_max;              // the caller's bound on the curve length: it sized the shared memory / slab of every later kernel
   double alpha0;
   double *xs, *y, *al, *lam, *stats;
   int32_t* pstatus;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepArgs a) {
     const int n = (int)(a.offsets[cu + 1] - o);
     int st = gp_prepare_curve(c, n, a.t + o, a.flux + o, a.ferr + o, a.band + o, a.loglam, a.n_bands, a.use_err, a.alpha0, a.xs + o,
                               a.y + o, a.al + o, a.lam + cu * a.n_bands, a.stats + cu * 6, red);
+    if (n > a.n_max) st = FULU_GP_STATUS_BAD_INPUT;   // longer than the caller said: flagged and skipped by every consumer, never run
     if (threadIdx.x == 0) a.pstatus[cu] = st;
     __syncthreads();
   }
@@ -441,7 +443,7 @@ inline int64_t n_active(const fulu_gp_batch& b) { return b.order ? b.n_order : b
 int run_prep(const fulu_gp_batch& b, const WsLayout& w, void* ws, int sms, cudaStream_t st, CurveTable& tab) {
   PrepArgs a;
   a.B = n_active(b); a.order = b.order; a.offsets = b.offsets; a.t = b.t; a.flux = b.flux; a.ferr = b.flux_err; a.loglam = b.loglam; a.band = b.band;
-  a.n_bands = b.n_bands; a.use_err = b.use_err; a.alpha0 = b.alpha0;
+  a.n_bands = b.n_bands; a.use_err = b.use_err; a.alpha0 = b.alpha0; a.n_max = b.n_max;
   a.xs = at<double>(ws, w.xs); a.y = at<double>(ws, w.y); a.al = at<double>(ws, w.al); a.lam = at<double>(ws, w.lam);
   a.stats = at<double>(ws, w.stats); a.pstatus = at<int32_t>(ws, w.pstatus);
   int64_t grid = a.B < (int64_t)sms * 16 ? a.B : (int64_t)sms * 16;

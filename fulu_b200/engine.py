@@ -506,7 +506,9 @@ def bucket_curves(lengths, buckets=N_BUCKETS):
     one instead of running alone (results do not depend on the class there: only the slab stride does)."""
     lengths = np.asarray(lengths)
     which = np.searchsorted(np.asarray(buckets), lengths, side="left")
-    groups = [[int(buckets[min(k, len(buckets) - 1)]), np.nonzero(which == k)[0]] for k in np.unique(which)]
+    # beyond the last bucket: one class bounded by its own longest curve (8k - 1 like the others), never a bound below a member
+    beyond = (int(lengths.max()) + 8) // 8 * 8 - 1 if len(lengths) else 0
+    groups = [[int(buckets[k]) if k < len(buckets) else beyond, np.nonzero(which == k)[0]] for k in np.unique(which)]
     out = []
     for bound, idx in groups:   # ascending bounds
         if out and out[-1][0] > MERGE_ABOVE and len(out[-1][1]) < MERGE_BELOW_CURVES:

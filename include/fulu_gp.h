@@ -61,7 +61,7 @@ extern "C" {
 
 /* per-curve status bits */
 #define FULU_GP_STATUS_OK 0
-#define FULU_GP_STATUS_BAD_INPUT 1       /* NaN/inf in t/flux/flux_err or band out of range (sklearn: ValueError, _gpr.py:257-265) */
+#define FULU_GP_STATUS_BAD_INPUT 1       /* NaN/inf in t/flux/flux_err, band out of range (sklearn: ValueError, _gpr.py:257-265), or longer than n_max */
 #define FULU_GP_STATUS_NOT_PD 2          /* K(theta*) not positive definite (sklearn: LinAlgError, _gpr.py:349-361) */
 #define FULU_GP_STATUS_NOT_CONVERGED 4   /* best run ended ABNORMAL / at the iteration limit (ConvergenceWarning, utils/optimize.py:436-458) */
 #define FULU_GP_STATUS_AT_BOUND 8        /* theta* numerically on a bound (ConvergenceWarning, kernels.py:436-464) */
@@ -70,7 +70,8 @@ extern "C" {
 typedef struct fulu_gp_batch {
   int64_t n_curves;          /* B */
   int64_t n_obs_total;       /* offsets[B] */
-  int32_t n_max;             /* max curve length in the batch (host-known upper bound) */
+  int32_t n_max;             /* upper bound on the length of the curves this call processes (host-known); it fixes the launch geometry.
+                                A listed curve longer than n_max is flagged FULU_GP_STATUS_BAD_INPUT and skipped, never run */
   int32_t n_bands;           /* entries of loglam */
   const int64_t* offsets;    /* [B+1] */
   const double* t;           /* [n_obs_total] observation times        (fulu fit arg `t`) */

@@ -130,6 +130,31 @@ def test_order_list_processes_only_the_listed_curves_in_place():
     np.testing.assert_array_equal(own["theta"].cpu().numpy(), sentinel["theta"].cpu().numpy()[order])
 
 
+def test_curve_longer_than_n_max_is_flagged_not_run():
+    """fulu_gp_batch.n_max sizes the shared memory / slab of every kernel: a listed curve longer than the caller said is flagged
+    BAD_INPUT and skipped by every consumer instead of overrunning the block's memory; the others are unaffected."""
+    import fulu_b200
+    from fulu_b200 import DeviceBatch, datasets
+
+    eng = fulu_b200.GPEngine()
+    hb = datasets.ztf_like(8, first=900, n_lo=20, n_hi=100)          # lengths 49 92 41 42 71 51 28 95
+    long_ = hb.lengths() > 63
+    assert long_.sum() == 3
+    db = DeviceBatch.from_host(hb, eng.device)
+    theta = torch.tensor(np.tile([0.1, -1.0, 1.5, -3.0], (8, 1)))
+    full = eng.lml(db, theta)
+    sub = db.select(np.arange(8, dtype=np.int32), n_max=63)
+    part = eng.lml(sub, theta)
+    st = part["status"].cpu().numpy()
+    assert np.all(st[long_] & 1) and np.all(st[~long_] == 0)
+    assert np.all(np.isnan(part["lml"].cpu().numpy()[long_]))
+    np.testing.assert_allclose(part["lml"].cpu().numpy()[~long_], full["lml"].cpu().numpy()[~long_], rtol=1e-10)   # another length class: rounding only
+    fit = eng.fit(sub)
+    pred = eng.predict_grid(sub, fit["theta"], 8)
+    assert np.all(fit["status"].cpu().numpy()[long_] & 1) and np.all(pred["status"].cpu().numpy()[long_] & 1)
+    assert np.all(np.isfinite(pred["mean"].cpu().numpy()[~long_])) and np.all(np.isnan(pred["mean"].cpu().numpy()[long_]))
+
+
 def test_edge_cases():
     import fulu_b200
     from fulu_b200 import CurveBatch, DeviceBatch
