@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libfulu_gp.so")
 SOURCES = ["gp_kernels.cu", "gp_family.cu"]
-HEADERS = ["gp_block.cuh", "gp_device.cuh", "lbfgsb.cuh"]
+HEADERS = ["gp_block.cuh", "gp_tiled.cuh", "gp_device.cuh", "lbfgsb.cuh"]
 # covariance families compiled into the library (product factor, added term; gp_block.cuh GP_F_*) - keep in step with
 # GP_FAMILY_LIST in csrc/gp_device.cuh.  One translation unit each, compiled in parallel.
 FAMILIES = [(0, 0), (0, 2), (2, 2), (0, 4), (0, 1), (0, 3), (2, 0)]

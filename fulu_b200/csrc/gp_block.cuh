@@ -567,8 +567,9 @@ GP_DEV void gp_chol_update_rows(Ctx& c, const GpSmem& s, const GpFrag& f, int k,
 // the matrix is loaded and stored twice instead of once per step.  Sets flag on breakdown.  On exit the strictly-lower tiles
 // hold L, the diagonal tiles hold the INVERSES of L's diagonal blocks, row n holds z^T = (L^-1 y)^T (left of the last diagonal
 // tile), and logdet = sum_i log L_ii, quad = z.z = y^T K^-1 y (both valid in thread 0, zero elsewhere).
+// border = false: the matrix is a diagonal block of a larger one that does not hold the border row (gp_tiled.cuh).
 template <class Ctx>
-GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, int n, double& logdet, double& quad) {
+GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, int n, double& logdet, double& quad, bool border = true) {
   const int T = s.T;
   double bq = 0.0;
   const GpFrag f = gp_frag(c.lane);
@@ -584,7 +585,7 @@ GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, int n, double& logdet, double& 
       double acc[2][2], z0, z1;
       const long long t0 = c.clock();
       gp_chol_accumulate(c, s, f, kb, kb, -1, Jlast, kb, acc);
-      if (!gp_chol8_warp(c, acc[0][0], acc[0][1], z0, z1, rdet, kb == T - 1 ? (n & 7) : 8, bq) && c.lane == 0) s.flag[0] = 1;
+      if (!gp_chol8_warp(c, acc[0][0], acc[0][1], z0, z1, rdet, (border && kb == T - 1) ? (n & 7) : 8, bq) && c.lane == 0) s.flag[0] = 1;
       double* D = s.A + gp_tile(kb, kb);
       D[f.a0] = z0;
       D[f.a1] = z1;

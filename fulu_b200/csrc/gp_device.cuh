@@ -8,6 +8,7 @@
 
 #include "../../include/fulu_gp.h"
 #include "gp_block.cuh"
+#include "gp_tiled.cuh"
 #include "lbfgsb.cuh"
 
 namespace {
@@ -35,7 +36,47 @@ struct DevCtx {
   }
   __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  // ---- bulk-asynchronous copies and their barriers (gp_tiled.cuh): SASS UBLKCP / SYNCS
+  static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  }
+  // waits until the phase of the given parity has completed; a wait that lasts ~10 s is a protocol bug: trap instead of hanging the GPU
+  __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    long long t0 = 0;
+    for (int spins = 0;; ++spins) {
+      uint32_t done;
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(a), "r"(parity)
+          : "memory");
+      if (done) break;
+      if (spins > 4096) {
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 20000000000LL) __trap();
+      }
+    }
+  }
+  // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the barrier
+  __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+  // orders this thread's generic-proxy writes (global or shared) before later asynchronous-proxy accesses (the copy engine)
+  __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 };
+
+using TiledCfg = GpTiledCfgDefault;
 
 // Threads per SM given to the evaluation kernel, split evenly between the resident CTAs; it also fixes the register budget
 // (65536 / threads).  Measured on B200 at N = 100 (4 CTAs per SM), 10,000 curves: 1024 threads (64 registers) 229 ms,
@@ -84,6 +125,31 @@ __device__ __forceinline__ void attach_kslab(GpSmem& s, double* gA, size_t gA_st
   if (!kGlobalA && gA != nullptr && gA_stride > 0) s.kslab = gA + (size_t)blockIdx.x * gA_stride;
 }
 
+// One LML + gradient evaluation by this CTA, whichever way the curve's class keeps its matrix: in shared memory (gp_block.cuh) or
+// as a slab in global memory streamed through shared-memory stages (gp_tiled.cuh).  pipe_it: the CTA's position in its ring of
+// stages (tiled path; carried from evaluation to evaluation).
+template <class Kern, bool kGlobalA>
+__device__ __forceinline__ void eval_curve(DevCtx& c, const GpCurveView& cv, const double* theta, double* smem, double* gA, size_t gA_stride,
+                                           uint32_t& pipe_it, double& l, double* g, bool& ok) {
+  if constexpr (kGlobalA) {
+    GpTiled tl = gp_tiled_carve<TiledCfg>(gA + (size_t)blockIdx.x * gA_stride, smem, cv.n, c.nwarp, pipe_it);
+    gp_tiled_eval_lml_grad<Kern, TiledCfg>(c, cv, theta, tl, l, g, ok);
+    pipe_it = tl.it;
+  } else {
+    GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
+    attach_kslab<kGlobalA>(s, gA, gA_stride);
+    gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
+  }
+}
+
+template <bool kGlobalA>
+__device__ __forceinline__ void eval_init(DevCtx& c, double* smem) {
+  if constexpr (kGlobalA) {
+    GpTiled tl = gp_tiled_carve<TiledCfg>(smem, smem, 1, c.nwarp, 0);   // (only the shared-memory part is used)
+    gp_tiled_init<TiledCfg>(c, tl);
+  }
+}
+
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
 template <class Kern, bool kGlobalA>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
@@ -91,6 +157,8 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab,
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
   if (blockIdx.x == 0) c.marks = marks;
+  uint32_t pipe_it = 0;
+  eval_init<kGlobalA>(c, smem);
   for (int64_t kk = blockIdx.x; kk < B; kk += gridDim.x) {
     const int64_t cu = curve_of(tab, kk);
     if (tab.pstatus[cu] != 0) {
@@ -98,11 +166,9 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab,
       continue;
     }
     GpCurveView cv = curve_view(tab, cu);
-    GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
-    attach_kslab<kGlobalA>(s, gA, gA_stride);
     double l, g[Kern::P];
     bool ok;
-    gp_eval_lml_grad<Kern>(c, cv, theta + cu * P, s, l, g, ok);
+    eval_curve<Kern, kGlobalA>(c, cv, theta + cu * P, smem, gA, gA_stride, pipe_it, l, g, ok);
     if (threadIdx.x == 0) { lml[cu] = l; for (int k = 0; k < Kern::P; ++k) grad[cu * P + k] = g[k]; }
     __syncthreads();
   }
@@ -185,16 +251,17 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
   const int count = d.counts[round];
+  if ((int)blockIdx.x >= count) return;
   const int32_t* list = d.list + (size_t)(round & 1) * d.window;
+  uint32_t pipe_it = 0;
+  eval_init<kGlobalA>(c, smem);
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
     const int slot = list[i];
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
-    GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
-    attach_kslab<kGlobalA>(s, d.gA, d.gA_stride);
     double l, g[Kern::P];
     bool ok;
-    gp_eval_lml_grad<Kern>(c, cv, d.slots[slot].x, s, l, g, ok);
+    eval_curve<Kern, kGlobalA>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
     if (threadIdx.x == 0) {
       d.f_out[slot] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = 0; k < Kern::P; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
@@ -215,14 +282,14 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, 
   DevCtx c;
   if ((int)blockIdx.x >= d.counts[round]) return;
   const int slot = d.list[(size_t)(round & 1) * d.window + blockIdx.x];
+  uint32_t pipe_it = 0;
+  eval_init<kGlobalA>(c, smem);
   for (;;) {
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
-    GpSmem s = carve<kGlobalA>(smem, d.gA, d.gA_stride, cv.n);
-    attach_kslab<kGlobalA>(s, d.gA, d.gA_stride);
     double l, g[FG_MAXP];
     bool ok;
-    gp_eval_lml_grad<Kern>(c, cv, d.slots[slot].x, s, l, g, ok);
+    eval_curve<Kern, kGlobalA>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
     if (threadIdx.x == 0) {
       for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
@@ -258,6 +325,8 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
   DevCtx c;
   // the warps' V tiles: behind the matrix and vectors in shared memory, or this CTA's global slab for long curves
   double* Vglobal = a.gV + (size_t)blockIdx.x * a.gV_stride;
+  uint32_t pipe_it = 0;
+  eval_init<kGlobalA>(c, smem);
   for (int64_t kk = blockIdx.x; kk < a.B; kk += gridDim.x) {
     const int64_t cu = curve_of(a.tab, kk);
     GpCurveView cv = curve_view(a.tab, cu);
@@ -287,6 +356,10 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
     double l = NAN;
     if (st) {
       for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }
+    } else if constexpr (kGlobalA) {
+      GpTiled tl = gp_tiled_carve<TiledCfg>(a.gA + (size_t)blockIdx.x * a.gA_stride, smem, cv.n, c.nwarp, pipe_it);
+      st = gp_tiled_predict_curve<Kern, TiledCfg>(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, tl, Vglobal, a.mean + out0, a.stdv + out0, l);
+      pipe_it = tl.it;
     } else {
       GpSmem s = carve<kGlobalA>(smem, a.gA, a.gA_stride, cv.n);
       double* V = a.gV_stride ? Vglobal : smem + gp_smem_doubles(cv.n);   // (classes near the shared-memory limit keep V in the slab too)

@@ -33,6 +33,7 @@ struct WsLayout {
   int window, max_rounds, grid_eval, grid_predict, threads_eval, occ_eval;
   bool stream_tail;   // the default window of a long-curve class: the whole fit in fit_tail_kernel
   size_t gA_stride, gV_stride;   // doubles per CTA
+  size_t slabs;                  // per-CTA slabs allocated at gA
   bool globalA;
   size_t smem_eval, smem_predict;
 };
@@ -60,16 +61,23 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   const size_t vec = gp_vec_doubles((int)np) * sizeof(double) + 16;
   const size_t full = gp_mat_doubles((int)np) * sizeof(double) + vec;
   w.globalA = full > kMaxSmem;
-  w.smem_eval = w.globalA ? vec : full;
+  // Residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation of a curve that fits shared memory is latency
+  // bound, so as many curves per SM as fit, and the 512 threads the register file allows are split between them.
+  // Longer curves (matrix in a global slab, streamed through shared-memory stages - gp_tiled.cuh): two 256-thread CTAs per SM up to
+  // np = 512 (the serial 64 x 64 diagonal blocks of one overlap the streamed products of the other), one 512-thread CTA above.
+  int occ;
+  if (w.globalA) {
+    occ = np <= 512 ? 2 : 1;
+    w.smem_eval = gp_tiled_smem_doubles<TiledCfg>(nmax, kEvalMaxThreads / occ / 32) * sizeof(double) + 16;
+    w.smem_predict = gp_tiled_smem_doubles<TiledCfg>(nmax, kPredictThreads / 32) * sizeof(double) + 16;
+  } else {
+    w.smem_eval = full;
+    occ = (int)((228 * 1024) / (w.smem_eval + 1024));
+  }
   // prediction: eight warps, each with its eight columns of V as T tiles (shared memory, or the CTA's global slab for long curves)
   const size_t vtiles = (size_t)(kPredictThreads / 32) * (np / GP_NB) * 64 * sizeof(double);
   const bool globalV = w.globalA || w.smem_eval + vtiles > kMaxSmem;
-  w.smem_predict = globalV ? w.smem_eval : w.smem_eval + vtiles;
-  // residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation is latency bound, so as many curves per
-  // SM as fit, and the 512 threads the register file allows are split between them
-  // (matrix in global memory: one 512-thread CTA per SM above np = 512 - two 256-thread CTAs per SM were measured 37 % slower at
-  // N = 1024..2048, the slab traffic is what limits that path)
-  int occ = w.globalA ? (np <= 512 ? 2 : 1) : (int)((228 * 1024) / (w.smem_eval + 1024));
+  if (!w.globalA) w.smem_predict = globalV ? w.smem_eval : w.smem_eval + vtiles;
   if (occ < 1) occ = 1;
   if (occ > 16) occ = 16;
   int threads = kEvalMaxThreads / occ / 32 * 32;
@@ -93,7 +101,8 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   size_t tasks = (size_t)(b.order ? b.n_order : b.n_curves) * (size_t)(S > 0 ? S : 1);
   if ((size_t)window > tasks) window = (int)(tasks > 0 ? tasks : 1);
   w.window = window;
-  w.max_rounds = max_rounds > 0 ? max_rounds : kDefaultMaxRounds;
+  // (a caller's cap can only lower the default: the workspace query does not know it, so the round counters are sized for the default)
+  w.max_rounds = (max_rounds > 0 && max_rounds < kDefaultMaxRounds) ? max_rounds : kDefaultMaxRounds;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   w.xs = take(NT * 8); w.y = take(NT * 8); w.al = take(NT * 8);
@@ -112,9 +121,19 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.run_x = take(tasks * (size_t)FG_MAXP * 8);
   w.run_nev = take(tasks * 4);
   w.run_end = take(tasks * 4);
-  // per-CTA slab: the matrix itself for long curves, a copy of the K tiles for the gradient pass otherwise (FULU_GP_NO_KSLAB=1: none)
-  w.gA_stride = w.globalA ? gp_mat_doubles((int)np) : (getenv("FULU_GP_NO_KSLAB") ? 0 : 64 * ((np / GP_NB) * (np / GP_NB + 1) / 2));
-  w.gA = take((size_t)w.grid_eval * w.gA_stride * 8);
+  // per-CTA slab: the matrix itself (+ the inverse's scratch panel and the inverted diagonal blocks) for long curves, a copy of the
+  // K tiles for the gradient pass otherwise (FULU_GP_NO_KSLAB=1: none).  One slab per CTA that can be at work: never more than the
+  // tasks (evaluation kernels) or the curves (prediction) of the call.
+  w.gA_stride = w.globalA ? gp_tiled_slab_doubles((int)np) : (getenv("FULU_GP_NO_KSLAB") ? 0 : 64 * ((np / GP_NB) * (np / GP_NB + 1) / 2));
+  const size_t curves = (size_t)(b.order ? b.n_order : b.n_curves);
+  size_t slabs = (size_t)w.grid_eval < tasks ? (size_t)w.grid_eval : tasks;
+  if (w.globalA) {
+    const size_t ps = (size_t)w.grid_predict < curves ? (size_t)w.grid_predict : curves;
+    if (ps > slabs) slabs = ps;
+  }
+  if (slabs < 1) slabs = 1;
+  w.slabs = slabs;
+  w.gA = take(slabs * w.gA_stride * 8);
   w.gV_stride = globalV ? vtiles / sizeof(double) : 0;
   w.gV = take((size_t)w.grid_predict * w.gV_stride * 8);
   w.total = o;

@@ -8,7 +8,10 @@
 #include <thread>
 #include <vector>
 
+#include <atomic>
+
 #include "../../fulu_b200/csrc/gp_block.cuh"
+#include "../../fulu_b200/csrc/gp_tiled.cuh"
 
 struct WarpShared {
   std::barrier<> bar{32};
@@ -63,7 +66,47 @@ struct HostCtx {
     ws->bar.arrive_and_wait();
     return r;
   }
+  // ---- emulation of mbarrier + bulk copies (gp_tiled.cuh).  The 8 bytes of a barrier hold {phase counter, count << 16 | pending};
+  // a bulk copy is a memcpy by the issuing thread, and the barrier's phase completes when the announced bytes have all been copied
+  // (announce-then-copy, as on the device), so a consumer can never see a stage before its data.
+  struct HostMbar { std::atomic<uint32_t> phase; std::atomic<uint32_t> pend; };
+  static_assert(sizeof(HostMbar) == 8, "a barrier is 8 bytes of shared memory");
+  static HostMbar* mb(uint64_t* bar) { return reinterpret_cast<HostMbar*>(bar); }
+  uint64_t* tx_bar = nullptr;
+  uint32_t tx_left = 0;
+  void mbar_init(uint64_t* bar, int count) {
+    new (bar) HostMbar;
+    mb(bar)->phase.store(0);
+    mb(bar)->pend.store(((uint32_t)count << 16) | (uint32_t)count);
+  }
+  void mbar_fence_init() {}
+  void mbar_arrive(uint64_t* bar) {
+    HostMbar* m = mb(bar);
+    const uint32_t v = m->pend.fetch_sub(1, std::memory_order_acq_rel) - 1;
+    if ((v & 0xffffu) == 0) {
+      m->pend.store((v & 0xffff0000u) | (v >> 16), std::memory_order_relaxed);
+      m->phase.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    tx_bar = bar;
+    tx_left = bytes;
+    if (bytes == 0) mbar_arrive(bar);
+  }
+  void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    if (bar != tx_bar || bytes > tx_left || (bytes & 15) || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) abort();
+    std::memcpy(dst, src, bytes);
+    tx_left -= bytes;
+    if (tx_left == 0) mbar_arrive(bar);
+  }
+  void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while ((mb(bar)->phase.load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
+  }
+  void fence_async() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 };
+
+// family code = F1 | EX << 4 (include/fulu_gp.h FULU_GP_KERNEL)
+#define HOST_FAMILIES(X) X(0, 0) X(0, 1) X(0, 2) X(0, 3) X(0, 4) X(2, 0) X(2, 2)
 
 template <class F>
 static void run_block(int nthr, F&& body) {
@@ -95,8 +138,6 @@ extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const
   return status;
 }
 
-// family code = F1 | EX << 4 (include/fulu_gp.h FULU_GP_KERNEL)
-#define HOST_FAMILIES(X) X(0, 0) X(0, 1) X(0, 2) X(0, 3) X(0, 4) X(2, 0) X(2, 2)
 
 template <class Kern>
 static int lml_impl(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
@@ -115,6 +156,75 @@ static int lml_impl(int family, int n, const double* xs, const int32_t* band, co
     if (c.tid == 0) { *lml = l; std::memcpy(grad, g, sizeof(g)); okout = ok; }
   });
   return okout;
+}
+
+// the long-curve path (gp_tiled.cuh): matrix in a "global" slab, operands streamed through "shared-memory" stages
+template <class Kern>
+static int lml_tiled_impl(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                          const double* theta, int nthr, int reps, double* lml, double* grad) {
+  using Cfg = GpTiledCfgDefault;
+  const int nwarp = nthr / 32;
+  std::vector<double> smem(gp_tiled_smem_doubles<Cfg>(n, nwarp));
+  std::vector<double> slab(gp_tiled_slab_doubles(gp_pad(n)), std::nan(""));   // a read of something never written shows up as NaN
+  GpCurveView cv{n, xs, band, y, al, lam};
+  int okout = 0;
+  run_block(nthr, [&](HostCtx& c) {
+    GpTiled g0 = gp_tiled_carve<Cfg>(slab.data(), smem.data(), 1, nwarp, 0);
+    gp_tiled_init<Cfg>(c, g0);
+    uint32_t it = 0;
+    for (int rep = 0; rep < reps; ++rep) {   // (several evaluations in a row: the ring of stages and its barriers carry on)
+      GpTiled g = gp_tiled_carve<Cfg>(slab.data(), smem.data(), n, nwarp, it);
+      double l, gr[Kern::P];
+      bool ok;
+      gp_tiled_eval_lml_grad<Kern, Cfg>(c, cv, theta, g, l, gr, ok);
+      it = g.it;
+      if (c.tid == 0) { *lml = l; std::memcpy(grad, gr, sizeof(gr)); okout = ok; }
+      c.sync();
+    }
+  });
+  return okout;
+}
+
+extern "C" int host_gp_lml_tiled(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                                 const double* theta, int nthr, int reps, double* lml, double* grad) {
+#define X(F1, EX) if ((family & 0xff) == ((F1) | ((EX) << 4))) return lml_tiled_impl<GpKern<F1, EX>>(n, xs, band, y, al, lam, theta, nthr, reps, lml, grad);
+  HOST_FAMILIES(X)
+#undef X
+  return -1;
+}
+
+template <class Kern>
+static int predict_tiled_impl(int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
+                              const double* theta, const double* stats, int m, int n_obs, double t_min, double t_max,
+                              const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
+  using Cfg = GpTiledCfgDefault;
+  const int nwarp = nthr / 32;
+  std::vector<double> smem(gp_tiled_smem_doubles<Cfg>(n, nwarp));
+  std::vector<double> slab(gp_tiled_slab_doubles(gp_pad(n)), std::nan(""));
+  std::vector<double> V((size_t)nwarp * (gp_pad(n) / 8) * 64);
+  GpCurveView cv{n, xs, band, y, al, lam};
+  GpQuery qd{m, n_obs, t_min, t_max, qt, qband};
+  int status = 0;
+  run_block(nthr, [&](HostCtx& c) {
+    GpTiled g0 = gp_tiled_carve<Cfg>(slab.data(), smem.data(), 1, nwarp, 0);
+    gp_tiled_init<Cfg>(c, g0);
+    GpTiled g = gp_tiled_carve<Cfg>(slab.data(), smem.data(), n, nwarp, 0);
+    double l;
+    int st = gp_tiled_predict_curve<Kern, Cfg>(c, cv, theta, stats, qd, g, V.data(), mean, stdv, l);
+    if (c.tid == 0) { status = st; *lml = l; }
+  });
+  return status;
+}
+
+extern "C" int host_gp_predict_tiled(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al,
+                                     const double* lam, const double* theta, const double* stats, int m, int n_obs, double t_min,
+                                     double t_max, const double* qt, const int32_t* qband, int nthr, double* mean, double* stdv, double* lml) {
+#define X(F1, EX) \
+  if (family == ((F1) | ((EX) << 4))) \
+    return predict_tiled_impl<GpKern<F1, EX>>(n, xs, band, y, al, lam, theta, stats, m, n_obs, t_min, t_max, qt, qband, nthr, mean, stdv, lml);
+  HOST_FAMILIES(X)
+#undef X
+  return -1;
 }
 
 extern "C" int host_gp_lml(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,

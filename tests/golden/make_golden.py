@@ -161,6 +161,15 @@ def main():
             run_case(cls, f"fam_{kn}_ztf_{i}", p2z, t, f, e, bd, use_err=False, n_obs=128, kernel=kn)
         if "--families-only" in sys.argv:
             return
+    if "--ddf" in sys.argv or "--ddf-only" in sys.argv:
+        # BASELINE config #5: one long LSST-DDF-like curve each at N = 1024 and N = 1536 (minutes of CPU per fit); the full-fit parity
+        # of the long-curve path is pinned against these (tests/test_gpu_parity.py)
+        p2l = {i: float(np.log10(v)) for i, v in enumerate(datasets.LSST_LAMBDA)}
+        for n_points, first in ((1024, 0), (1536, 1)):
+            t, f, e, bd = datasets.ddf_like(1, n_points=n_points, first=first).curve(0)
+            run_case(cls, f"ddf_{n_points}", p2l, t, f, e, bd, use_err=False, n_obs=128)
+        if "--ddf-only" in sys.argv:
+            return
     p2l, *lc = datasets.readme_example()
     run_case(cls, "readme", p2l, *lc, use_err=False, n_obs=100)
     run_case(cls, "readme_err", p2l, *lc, use_err=True, n_obs=100)
