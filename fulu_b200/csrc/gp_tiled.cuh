@@ -29,8 +29,19 @@
 #ifndef GP_TILED_KC
 #define GP_TILED_KC 2
 #endif
-#ifndef GP_TILED_NS
-#define GP_TILED_NS 3
+#ifndef GP_TILED_NS16
+#define GP_TILED_NS16 3   // stages of a 16-warp CTA (one per SM)
+#endif
+#ifndef GP_TILED_SLACK
+#define GP_TILED_SLACK 0  // stages kept out of the look-ahead
+#endif
+#ifndef GP_TILED_NS8
+#define GP_TILED_NS8 3    // stages of an 8-warp CTA (two per SM)
+#endif
+#if defined(__CUDACC__)
+#define GP_MBAR_WORDS 1   // an mbarrier is 8 bytes of shared memory
+#else
+#define GP_MBAR_WORDS 2   // (the host emulation of tests/_host keeps 16 bytes per barrier)
 #endif
 
 enum { GP_MODE_NT = 0, GP_MODE_NN = 1, GP_MODE_TN = 2 };
@@ -38,7 +49,12 @@ enum { GP_MODE_NT = 0, GP_MODE_NN = 1, GP_MODE_TN = 2 };
 struct GpTiledCfgDefault {
   static constexpr int RW = GP_TILED_RW;   // tile-rows of the output block per warp
   static constexpr int KC = GP_TILED_KC;   // k-tiles per stage
-  static constexpr int NS = GP_TILED_NS;   // stages
+  static constexpr int NS_MAX = GP_TILED_NS16 > GP_TILED_NS8 ? GP_TILED_NS16 : GP_TILED_NS8;
+  GP_HD static int stages(int nwarp) { return nwarp >= 16 ? GP_TILED_NS16 : GP_TILED_NS8; }
+  // chunks in flight ahead of the one being multiplied (measured on B200, N = 1024 / 2048, one evaluation per CTA: three stages with
+  // two chunks ahead 14.8 / 18.8 TFLOP/s; four stages with one of them as slack - so that the issuing warp never waits for the
+  // slowest warp to leave the stage it refills - 13.6 / 17.4)
+  GP_HD static int lookahead(int ns) { return ns - 1 - GP_TILED_SLACK > 0 ? ns - 1 - GP_TILED_SLACK : 1; }
 };
 
 // ---------------------------------------------------------------------------------------------- sizes
@@ -52,10 +68,11 @@ GP_HD size_t gp_tiled_slab_doubles(int np) {
 GP_HD size_t gp_tiled_dblock_doubles() { return 64 * (36 + GP_PW); }
 template <class Cfg>
 GP_HD size_t gp_tiled_stage_doubles(int nwarp) { return (size_t)64 * Cfg::KC * (nwarp * Cfg::RW + GP_PW); }
-// shared memory of a tiled CTA (doubles): vectors, the diagonal block (+ its scratch column), the stages, the barriers
+// shared memory of a tiled CTA (doubles): the barriers, the diagonal block (+ its scratch column), the stages, the vectors
 template <class Cfg>
 GP_HD size_t gp_tiled_smem_doubles(int n, int nwarp) {
-  return gp_vec_doubles(gp_pad(n)) + gp_tiled_dblock_doubles() + Cfg::NS * gp_tiled_stage_doubles<Cfg>(nwarp) + 2 * Cfg::NS;
+  return gp_vec_doubles(gp_pad(n)) + gp_tiled_dblock_doubles() + Cfg::stages(nwarp) * gp_tiled_stage_doubles<Cfg>(nwarp) +
+         2 * Cfg::NS_MAX * GP_MBAR_WORDS;
 }
 
 struct GpTiled {
@@ -64,19 +81,23 @@ struct GpTiled {
   double* XD;          // global: 36 tiles per panel
   double* D;           // shared: the diagonal block being factored / its inverse (36 + 8 tiles)
   double* stage;       // shared
-  uint64_t* bars;      // shared: full[NS], empty[NS]
-  uint32_t it;         // chunks streamed so far by this CTA (same value in every thread): stage = it % NS, use = it / NS
+  uint64_t* bars;      // shared: full[ns], empty[ns]
+  uint32_t it;         // chunks streamed so far by this CTA (same value in every thread): stage = it % ns, use = it / ns
+  int ns;              // stages
 };
+GP_DEV uint64_t* gp_bar_full(const GpTiled& g, int st) { return g.bars + (size_t)GP_MBAR_WORDS * st; }
+GP_DEV uint64_t* gp_bar_empty(const GpTiled& g, int st) { return g.bars + (size_t)GP_MBAR_WORDS * (g.ns + st); }
 
 // Shared memory: barriers, diagonal block and stages at fixed offsets (they outlive a curve: the barriers keep their phase across
-// the evaluations of a kernel), the curve's vectors last.  `it` is not touched here: the kernel carries it from curve to curve.
+// the evaluations of a kernel), the curve's vectors last.  `it` is carried by the kernel from curve to curve.
 template <class Cfg>
 GP_HD GpTiled gp_tiled_carve(double* slab, double* smem, int n, int nwarp, uint32_t it) {
   GpTiled g;
+  g.ns = Cfg::stages(nwarp);
   double* p = smem;
-  g.bars = reinterpret_cast<uint64_t*>(p); p += 2 * Cfg::NS;
+  g.bars = reinterpret_cast<uint64_t*>(p); p += 2 * Cfg::NS_MAX * GP_MBAR_WORDS;
   g.D = p; p += gp_tiled_dblock_doubles();
-  g.stage = p; p += Cfg::NS * gp_tiled_stage_doubles<Cfg>(nwarp);
+  g.stage = p; p += g.ns * gp_tiled_stage_doubles<Cfg>(nwarp);
   g.s = gp_carve(slab, p, n);
   const size_t T = (size_t)g.s.T;
   g.W = slab + 64 * (T * (T + 1) / 2 + T);
@@ -89,14 +110,14 @@ GP_HD GpTiled gp_tiled_carve(double* slab, double* smem, int n, int nwarp, uint3
 template <class Cfg, class Ctx>
 GP_DEV void gp_tiled_init(Ctx& c, GpTiled& g) {
   if (c.tid == 0) {
-    for (int s = 0; s < Cfg::NS; ++s) {
-      c.mbar_init(&g.bars[s], 1);                  // full: the producer's arrive.expect_tx (+ the copies' bytes)
-      c.mbar_init(&g.bars[Cfg::NS + s], c.nwarp);  // empty: one arrival per warp
+    for (int s = 0; s < g.ns; ++s) {
+      c.mbar_init(gp_bar_full(g, s), 1);         // full: the producer's arrive.expect_tx (+ the copies' bytes)
+      c.mbar_init(gp_bar_empty(g, s), c.nwarp);  // empty: one arrival per warp
     }
     c.mbar_fence_init();
   }
   // stale stage contents are only ever multiplied by zero operands of masked tiles, but they must be finite for that
-  const size_t ns = Cfg::NS * gp_tiled_stage_doubles<Cfg>(c.nwarp);
+  const size_t ns = g.ns * gp_tiled_stage_doubles<Cfg>(c.nwarp);
   for (size_t i = c.tid; i < ns; i += c.nthr) g.stage[i] = 0.0;
   g.it = 0;
   c.fence_async();   // (the stages are written by the copy engine from now on)
@@ -112,33 +133,39 @@ struct GpStreamJob {
   int b0, nb;        // output columns: tile-rows (NT) / tile-columns (TN) b0 .. b0 + nb - 1 of the panel, nb <= 8 (NN: nb only)
   int kborder;       // TN: the k-tile that holds the border row (T - 1), whose row `rb` is left out of the sum
   int rb;
+  int tri;           // NT, TN: output tile (row r, column tile b0 + j) is wanted only for b0 + j <= r (blocks that meet the diagonal)
 };
 
 // slot of (warp w, i-th row of the warp): interleaved, so that a block with few rows spreads them over all warps
 #define GP_SLOT(w, i, nwarp) ((i) * (nwarp) + (w))
 
+// Chunk `chunk` of the job into its stage: called by every lane of warp 0; lane e issues the copies e, e + 32, ...
 template <int MODE, class Cfg, class Ctx>
 GP_DEV void gp_stream_issue(Ctx& c, GpTiled& g, const GpStreamJob& job, int chunk, uint32_t it) {
-  constexpr int KC = Cfg::KC, NS = Cfg::NS;
-  const int BM = c.nwarp * Cfg::RW;
+  constexpr int KC = Cfg::KC;
+  const int BM = c.nwarp * Cfg::RW, NS = g.ns;
   const uint32_t st = it % NS, use = it / NS;
-  uint64_t* full = &g.bars[st];
-  if (use > 0) c.mbar_wait(&g.bars[NS + st], (use - 1) & 1);   // every warp has released the previous contents of this stage
+  uint64_t* full = gp_bar_full(g, st);
+  if (use > 0) c.mbar_wait(gp_bar_empty(g, st), (use - 1) & 1);   // every warp has released the previous contents of this stage
   double* dst = g.stage + (size_t)st * gp_tiled_stage_doubles<Cfg>(c.nwarp);
   const int kc = job.k0 + chunk * KC;
   const int kn = (job.k1 - kc < KC) ? job.k1 - kc : KC;
-  // bytes first (the barrier must know them before the first copy can complete it)
-  uint32_t tiles = 0;
+  // the bytes of the whole chunk first (every lane computes the same number; lane 0 announces it)
+  int tiles = 0;
   if (MODE == GP_MODE_NT) {
-    tiles = (uint32_t)(job.nrows + job.nb) * kn;
+    tiles = (job.nrows + job.nb) * kn;
   } else if (MODE == GP_MODE_NN) {
-    for (int sl = 0; sl < job.nrows; ++sl) {
-      const int r = job.r0 + sl;
-      int cnt = r + 1 - kc;
-      if (cnt > kn) cnt = kn;
-      if (cnt > 0) tiles += cnt;
+    // row r holds k-tiles <= r: rows r >= kc + kn - 1 take the whole chunk, rows kc + d (d < kn - 1) take d + 1 tiles
+    const int rlast = job.r0 + job.nrows - 1;
+    int full_rows = rlast - (kc + kn - 1) + 1;
+    if (job.r0 > kc + kn - 1) full_rows = job.nrows;
+    if (full_rows < 0) full_rows = 0;
+    tiles = full_rows * kn;
+    for (int d = 0; d < kn - 1; ++d) {
+      const int r = kc + d;
+      if (r >= job.r0 && r <= rlast) tiles += d + 1;
     }
-    tiles += (uint32_t)GP_PW * kn;
+    tiles += GP_PW * kn;
   } else {
     for (int kk = 0; kk < kn; ++kk) {
       const int k = kc + kk;
@@ -148,37 +175,48 @@ GP_DEV void gp_stream_issue(Ctx& c, GpTiled& g, const GpStreamJob& job, int chun
       tiles += (ca > 0 ? ca : 0) + (cb > 0 ? cb : 0);
     }
   }
-  c.mbar_expect_tx(full, tiles * 512u);
+  if (c.lane == 0) c.mbar_expect_tx(full, (uint32_t)tiles * 512u);
+  c.warp_sync();
   if (MODE == GP_MODE_NT) {
-    for (int sl = 0; sl < job.nrows; ++sl) c.bulk_g2s(dst + 64 * sl * KC, job.A + gp_tile(job.r0 + sl, kc), 512u * kn, full);
-    for (int j = 0; j < job.nb; ++j) c.bulk_g2s(dst + 64 * (BM + j) * KC, job.A + gp_tile(job.b0 + j, kc), 512u * kn, full);
-  } else if (MODE == GP_MODE_NN) {
-    for (int sl = 0; sl < job.nrows; ++sl) {
-      const int r = job.r0 + sl;
-      int cnt = r + 1 - kc;
-      if (cnt > kn) cnt = kn;
-      if (cnt > 0) c.bulk_g2s(dst + 64 * sl * KC, job.A + gp_tile(r, kc), 512u * cnt, full);
+    for (int e = c.lane; e < job.nrows + job.nb; e += 32) {
+      if (e < job.nrows) c.bulk_g2s(dst + 64 * e * KC, job.A + gp_tile(job.r0 + e, kc), 512u * kn, full);
+      else c.bulk_g2s(dst + 64 * (BM + e - job.nrows) * KC, job.A + gp_tile(job.b0 + e - job.nrows, kc), 512u * kn, full);
     }
-    c.bulk_g2s(dst + 64 * BM * KC, job.Wp + (size_t)64 * GP_PW * kc, 512u * GP_PW * kn, full);
+  } else if (MODE == GP_MODE_NN) {
+    for (int e = c.lane; e <= job.nrows; e += 32) {
+      if (e < job.nrows) {
+        const int r = job.r0 + e;
+        int cnt = r + 1 - kc;
+        if (cnt > kn) cnt = kn;
+        if (cnt > 0) c.bulk_g2s(dst + 64 * e * KC, job.A + gp_tile(r, kc), 512u * cnt, full);
+      } else {
+        c.bulk_g2s(dst + 64 * BM * KC, job.Wp + (size_t)64 * GP_PW * kc, 512u * GP_PW * kn, full);
+      }
+    }
   } else {
-    for (int kk = 0; kk < kn; ++kk) {
-      const int k = kc + kk;
-      int ca = k + 1 - job.r0, cb = k + 1 - job.b0;
-      if (ca > job.nrows) ca = job.nrows;
-      if (cb > job.nb) cb = job.nb;
-      if (ca > 0) c.bulk_g2s(dst + 64 * kk * BM, job.A + gp_tile(k, job.r0), 512u * ca, full);
-      if (cb > 0) c.bulk_g2s(dst + 64 * (KC * BM + kk * GP_PW), job.A + gp_tile(k, job.b0), 512u * cb, full);
+    for (int e = c.lane; e < 2 * kn; e += 32) {
+      const int kk = e >> 1, k = kc + kk;
+      if ((e & 1) == 0) {
+        int ca = k + 1 - job.r0;
+        if (ca > job.nrows) ca = job.nrows;
+        if (ca > 0) c.bulk_g2s(dst + 64 * kk * BM, job.A + gp_tile(k, job.r0), 512u * ca, full);
+      } else {
+        int cb = k + 1 - job.b0;
+        if (cb > job.nb) cb = job.nb;
+        if (cb > 0) c.bulk_g2s(dst + 64 * (KC * BM + kk * GP_PW), job.A + gp_tile(k, job.b0), 512u * cb, full);
+      }
     }
   }
 }
 
 // acc[i][j][0..1] += sum over the job's k-tiles of A(row i of this warp, k) B(k, column tile j); accumulators in the PERMUTED layout
-// (column t, column 4 + t) for NT and NN, in the natural one (columns 2t, 2t + 1) for TN - as in gp_block.cuh.
-// Every thread of the block must call this with the same job (block-wide barriers inside).
+// (column t, column 4 + t) for NT and NN, in the natural one (columns 2t, 2t + 1) for TN - as in gp_block.cuh.  Tile products that
+// are not wanted (above the diagonal, k outside a row's range) are skipped, warp by warp.
+// Every thread of the block must call this with the same job (block-wide barrier inside).
 template <int MODE, class Cfg, class Ctx>
 GP_DEV void gp_stream_mma(Ctx& c, GpTiled& g, const GpStreamJob& job, const GpFrag& f, double (&acc)[Cfg::RW][GP_PW][2]) {
-  constexpr int KC = Cfg::KC, NS = Cfg::NS, RW = Cfg::RW;
-  const int BM = c.nwarp * RW;
+  constexpr int KC = Cfg::KC, RW = Cfg::RW;
+  const int BM = c.nwarp * RW, NS = g.ns, LA = Cfg::lookahead(g.ns);
 #pragma unroll
   for (int i = 0; i < RW; ++i)
 #pragma unroll
@@ -187,85 +225,98 @@ GP_DEV void gp_stream_mma(Ctx& c, GpTiled& g, const GpStreamJob& job, const GpFr
   if (nk <= 0) return;
   const int nchunk = (nk + KC - 1) / KC;
   const uint32_t it0 = g.it;
-  c.sync();   // whatever this block wrote to global memory before (and fenced) is visible to the producer thread's copies
-  if (c.tid == 0) {
-    const int pre = nchunk < NS - 1 ? nchunk : NS - 1;
+  c.sync();   // whatever this block wrote to global memory before (and fenced) is visible to the copies issued from here on
+  if (c.warp == 0) {
+    const int pre = nchunk < LA ? nchunk : LA;
     for (int q = 0; q < pre; ++q) gp_stream_issue<MODE, Cfg>(c, g, job, q, it0 + q);
   }
-  const int g8 = c.lane >> 2, t4 = c.lane & 3;
-  bool rowok[RW];
-  int rowid[RW];
+  const int t4 = c.lane & 3;
+  int rowid[RW], jlim[RW];   // this warp's rows and how many of the panel's column tiles each wants (0: no such row)
+  int jmax = 0;
 #pragma unroll
   for (int i = 0; i < RW; ++i) {
     const int sl = GP_SLOT(c.warp, i, c.nwarp);
-    rowok[i] = sl < job.nrows;
     rowid[i] = job.r0 + sl;
+    int jl = job.nb;
+    if (job.tri && rowid[i] - job.b0 + 1 < jl) jl = rowid[i] - job.b0 + 1;
+    if (sl >= job.nrows || jl < 0) jl = 0;
+    jlim[i] = jl;
+    if (jl > jmax) jmax = jl;
   }
-  const bool any = rowok[0];
   for (int q = 0; q < nchunk; ++q) {
-    if (c.tid == 0 && q + NS - 1 < nchunk) gp_stream_issue<MODE, Cfg>(c, g, job, q + NS - 1, it0 + q + NS - 1);
+    if (c.warp == 0 && q + LA < nchunk) gp_stream_issue<MODE, Cfg>(c, g, job, q + LA, it0 + q + LA);
     const uint32_t it = it0 + q, st = it % NS, use = it / NS;
-    c.mbar_wait(&g.bars[st], use & 1);
+    c.mbar_wait(gp_bar_full(g, st), use & 1);
     const double* S = g.stage + (size_t)st * gp_tiled_stage_doubles<Cfg>(c.nwarp);
     const int kc = job.k0 + q * KC;
     const int kn = (job.k1 - kc < KC) ? job.k1 - kc : KC;
-    if (any) {
+    if (jmax > 0) {
 #pragma unroll
       for (int kk = 0; kk < KC; ++kk) {
         if (kk < kn) {
           const int k = kc + kk;
           double a0[RW], a1[RW];
+          bool act[RW];
+          bool anyact = false;
 #pragma unroll
           for (int i = 0; i < RW; ++i) {
             const int sl = GP_SLOT(c.warp, i, c.nwarp);
-            bool ok = rowok[i];
-            const double* Ap;
+            act[i] = jlim[i] > 0;
+            a0[i] = 0.0; a1[i] = 0.0;
             if (MODE == GP_MODE_TN) {
-              Ap = S + 64 * (kk * BM + sl);
-              ok = ok && rowid[i] <= k;
-              a0[i] = ok ? Ap[f.t0] : 0.0;
-              a1[i] = ok ? Ap[f.t1] : 0.0;
-              if (k == job.kborder) {   // the border row of M^-1 (-alpha) is not a row of X
-                if (t4 == job.rb) a0[i] = 0.0;
-                if (4 + t4 == job.rb) a1[i] = 0.0;
+              act[i] = act[i] && rowid[i] <= k;        // tile (k, i) of X exists
+              if (act[i]) {
+                const double* Ap = S + 64 * (kk * BM + sl);
+                a0[i] = Ap[f.t0];
+                a1[i] = Ap[f.t1];
+                if (k == job.kborder) {   // the border row of M^-1 (-alpha) is not a row of X
+                  if (t4 == job.rb) a0[i] = 0.0;
+                  if (4 + t4 == job.rb) a1[i] = 0.0;
+                }
               }
             } else {
-              Ap = S + 64 * (sl * KC + kk);
-              if (MODE == GP_MODE_NN) ok = ok && k <= rowid[i];
-              a0[i] = ok ? Ap[f.a0] : 0.0;
-              a1[i] = ok ? Ap[f.a1] : 0.0;
+              if (MODE == GP_MODE_NN) act[i] = act[i] && k <= rowid[i];   // tile (r, k) of X exists
+              if (act[i]) {
+                const double* Ap = S + 64 * (sl * KC + kk);
+                a0[i] = Ap[f.a0];
+                a1[i] = Ap[f.a1];
+              }
             }
+            anyact = anyact || act[i];
           }
+          if (anyact) {
 #pragma unroll
-          for (int j = 0; j < GP_PW; ++j) {
-            double b0, b1;
-            if (MODE == GP_MODE_NT) {
-              const double* Bp = S + 64 * ((BM + j) * KC + kk);
-              const bool ok = j < job.nb;
-              b0 = ok ? Bp[f.b0] : 0.0;
-              b1 = ok ? Bp[f.b1] : 0.0;
-            } else if (MODE == GP_MODE_NN) {
-              const double* Bp = S + 64 * (BM * KC + kk * GP_PW + j);
-              b0 = Bp[f.p0];
-              b1 = Bp[f.p1];
-            } else {
-              const double* Bp = S + 64 * (KC * BM + kk * GP_PW + j);
-              const bool ok = j < job.nb && job.b0 + j <= k;
-              b0 = ok ? Bp[f.t0] : 0.0;
-              b1 = ok ? Bp[f.t1] : 0.0;
-            }
+            for (int j = 0; j < GP_PW; ++j) {
+              if (j < jmax) {
+                double b0, b1;
+                if (MODE == GP_MODE_NT) {
+                  const double* Bp = S + 64 * ((BM + j) * KC + kk);
+                  b0 = Bp[f.b0];
+                  b1 = Bp[f.b1];
+                } else if (MODE == GP_MODE_NN) {
+                  const double* Bp = S + 64 * (BM * KC + kk * GP_PW + j);
+                  b0 = Bp[f.p0];
+                  b1 = Bp[f.p1];
+                } else {
+                  const double* Bp = S + 64 * (KC * BM + kk * GP_PW + j);
+                  b0 = Bp[f.t0];   // (tile (k, b0 + j) exists: b0 + j <= row <= k for every row that is active here)
+                  b1 = Bp[f.t1];
+                }
 #pragma unroll
-            for (int i = 0; i < RW; ++i) {
-              c.mma(acc[i][j][0], acc[i][j][1], a0[i], b0);
-              c.mma(acc[i][j][0], acc[i][j][1], a1[i], b1);
+                for (int i = 0; i < RW; ++i) {
+                  if (act[i] && j < jlim[i]) {
+                    c.mma(acc[i][j][0], acc[i][j][1], a0[i], b0);
+                    c.mma(acc[i][j][0], acc[i][j][1], a1[i], b1);
+                  }
+                }
+              }
             }
           }
         }
       }
     }
     c.warp_sync();
-    if (c.lane == 0) c.mbar_arrive(&g.bars[NS + st]);
-    (void)g8;
+    if (c.lane == 0) c.mbar_arrive(gp_bar_empty(g, st));
   }
   g.it = it0 + nchunk;
 }
@@ -331,7 +382,7 @@ GP_DEV void gp_tiled_cholesky(Ctx& c, GpTiled& g, int n, const Kern& kn, double&
       job.nrows = (T - job.r0 < per) ? T - job.r0 : per;
       job.k0 = 0; job.k1 = c0;
       job.b0 = c0; job.nb = pw;
-      job.kborder = -1; job.rb = 0;
+      job.kborder = -1; job.rb = 0; job.tri = 1;
       double acc[RW][GP_PW][2];
       gp_stream_mma<GP_MODE_NT, Cfg>(c, g, job, f, acc);
 #pragma unroll
@@ -493,7 +544,7 @@ GP_DEV void gp_tiled_trtri(Ctx& c, GpTiled& g) {
       job.nrows = (T - job.r0 < per) ? T - job.r0 : per;
       job.k0 = r1; job.k1 = job.r0 + job.nrows;   // k <= r: masked per row inside
       job.b0 = c0; job.nb = pw;
-      job.kborder = -1; job.rb = 0;
+      job.kborder = -1; job.rb = 0; job.tri = 0;
       double acc[RW][GP_PW][2];
       gp_stream_mma<GP_MODE_NN, Cfg>(c, g, job, f, acc);
 #pragma unroll
@@ -542,7 +593,7 @@ GP_DEV void gp_tiled_traces(Ctx& c, GpTiled& g, int n, const Kern& kn, double (&
       job.r0 = i0; job.nrows = ni;
       job.k0 = i0; job.k1 = T;
       job.b0 = b0; job.nb = (jmax + 1 - b0 < GP_PW) ? jmax + 1 - b0 : GP_PW;
-      job.kborder = T - 1; job.rb = rb;
+      job.kborder = T - 1; job.rb = rb; job.tri = 1;
       double acc[RW][GP_PW][2];
       gp_stream_mma<GP_MODE_TN, Cfg>(c, g, job, f, acc);
 #pragma unroll

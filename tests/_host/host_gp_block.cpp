@@ -66,38 +66,34 @@ struct HostCtx {
     ws->bar.arrive_and_wait();
     return r;
   }
-  // ---- emulation of mbarrier + bulk copies (gp_tiled.cuh).  The 8 bytes of a barrier hold {phase counter, count << 16 | pending};
-  // a bulk copy is a memcpy by the issuing thread, and the barrier's phase completes when the announced bytes have all been copied
-  // (announce-then-copy, as on the device), so a consumer can never see a stage before its data.
-  struct HostMbar { std::atomic<uint32_t> phase; std::atomic<uint32_t> pend; };
-  static_assert(sizeof(HostMbar) == 8, "a barrier is 8 bytes of shared memory");
+  // ---- emulation of mbarrier + bulk copies (gp_tiled.cuh).  A barrier is 16 bytes here (GP_MBAR_WORDS = 2): the phase counter, the
+  // arrival count it is re-armed with, and one 64-bit state word = pending arrivals << 48 | outstanding bytes (biased), so that
+  // "last arrival and no byte outstanding" is one atomic observation, whoever makes it true.  A bulk copy is a memcpy by the issuing
+  // thread followed by the subtraction of its bytes: a consumer can never see a stage before its data.
+  struct HostMbar { std::atomic<uint32_t> phase; uint32_t count; std::atomic<uint64_t> state; };
+  static_assert(sizeof(HostMbar) == 16, "a barrier is 16 bytes of (emulated) shared memory");
+  static constexpr uint64_t kBias = 1ull << 40;
   static HostMbar* mb(uint64_t* bar) { return reinterpret_cast<HostMbar*>(bar); }
-  uint64_t* tx_bar = nullptr;
-  uint32_t tx_left = 0;
-  void mbar_init(uint64_t* bar, int count) {
-    new (bar) HostMbar;
-    mb(bar)->phase.store(0);
-    mb(bar)->pend.store(((uint32_t)count << 16) | (uint32_t)count);
-  }
-  void mbar_fence_init() {}
-  void mbar_arrive(uint64_t* bar) {
-    HostMbar* m = mb(bar);
-    const uint32_t v = m->pend.fetch_sub(1, std::memory_order_acq_rel) - 1;
-    if ((v & 0xffffu) == 0) {
-      m->pend.store((v & 0xffff0000u) | (v >> 16), std::memory_order_relaxed);
+  static void mb_update(HostMbar* m, uint64_t delta) {
+    const uint64_t v = m->state.fetch_add(delta, std::memory_order_acq_rel) + delta;
+    if (v == kBias) {   // no arrival pending, no byte outstanding: the phase completes, the barrier re-arms
+      m->state.store(((uint64_t)m->count << 48) | kBias, std::memory_order_relaxed);
       m->phase.fetch_add(1, std::memory_order_release);
     }
   }
-  void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    tx_bar = bar;
-    tx_left = bytes;
-    if (bytes == 0) mbar_arrive(bar);
+  void mbar_init(uint64_t* bar, int count) {
+    HostMbar* m = new (bar) HostMbar;
+    m->phase.store(0);
+    m->count = (uint32_t)count;
+    m->state.store(((uint64_t)count << 48) | kBias);
   }
+  void mbar_fence_init() {}
+  void mbar_arrive(uint64_t* bar) { mb_update(mb(bar), (uint64_t)0 - (1ull << 48)); }
+  void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { mb_update(mb(bar), (uint64_t)bytes - (1ull << 48)); }
   void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    if (bar != tx_bar || bytes > tx_left || (bytes & 15) || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) abort();
+    if (bytes == 0 || (bytes & 15) || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) abort();
     std::memcpy(dst, src, bytes);
-    tx_left -= bytes;
-    if (tx_left == 0) mbar_arrive(bar);
+    mb_update(mb(bar), (uint64_t)0 - (uint64_t)bytes);
   }
   void mbar_wait(uint64_t* bar, uint32_t parity) {
     while ((mb(bar)->phase.load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
