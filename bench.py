@@ -218,7 +218,8 @@ WORKLOADS = {
     "ztf": ("BASELINE config #4 sample (ZTF-like, 2 bands g/r, ragged N = round(exp(U(ln 20, ln 300))), 128-point grid x 2 bands), "
             "one batch per GPU per step, length classes run as index-list launches over the resident batch", 20000, N_OBS),
     "ddf": ("BASELINE config #5 (LSST-DDF-like, 6 bands, N in {1024, 1536, 2048} in equal parts, 128-point grid x 6 bands), "
-            "one CTA per (curve, start) with the matrix in an L2/HBM-resident slab", 48, N_OBS),
+            "one CTA per (curve, start) run, the matrix in a global slab streamed through shared-memory stages by bulk copies (gp_tiled.cuh); "
+            "the whole fit of the class is one fused launch fed by a task queue", 96, N_OBS),
 }
 
 

@@ -110,6 +110,12 @@ __device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t c
   return v;
 }
 
+// Where a length class keeps a curve's matrix (plan() in gp_kernels.cu):
+//   GP_PLACE_SMEM   packed tiles in shared memory, 1 .. 16 CTAs per SM                                      (N <= 223)
+//   GP_PLACE_SLAB   the same 8x8 block code on a per-CTA slab in global memory (L2 resident), two CTAs per SM (N <= 511)
+//   GP_PLACE_TILED  slab in global memory streamed through shared-memory stages by bulk copies (gp_tiled.cuh), one CTA per SM
+enum { GP_PLACE_SMEM = 0, GP_PLACE_SLAB = 1, GP_PLACE_TILED = 2 };
+
 template <bool kGlobalA>
 __device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
   if (!kGlobalA) {
@@ -128,37 +134,37 @@ __device__ __forceinline__ void attach_kslab(GpSmem& s, double* gA, size_t gA_st
 // One LML + gradient evaluation by this CTA, whichever way the curve's class keeps its matrix: in shared memory (gp_block.cuh) or
 // as a slab in global memory streamed through shared-memory stages (gp_tiled.cuh).  pipe_it: the CTA's position in its ring of
 // stages (tiled path; carried from evaluation to evaluation).
-template <class Kern, bool kGlobalA>
+template <class Kern, int kPlace>
 __device__ __forceinline__ void eval_curve(DevCtx& c, const GpCurveView& cv, const double* theta, double* smem, double* gA, size_t gA_stride,
                                            uint32_t& pipe_it, double& l, double* g, bool& ok) {
-  if constexpr (kGlobalA) {
+  if constexpr (kPlace == GP_PLACE_TILED) {
     GpTiled tl = gp_tiled_carve<TiledCfg>(gA + (size_t)blockIdx.x * gA_stride, smem, cv.n, c.nwarp, pipe_it);
     gp_tiled_eval_lml_grad<Kern, TiledCfg>(c, cv, theta, tl, l, g, ok);
     pipe_it = tl.it;
   } else {
-    GpSmem s = carve<kGlobalA>(smem, gA, gA_stride, cv.n);
-    attach_kslab<kGlobalA>(s, gA, gA_stride);
+    GpSmem s = carve<kPlace != GP_PLACE_SMEM>(smem, gA, gA_stride, cv.n);
+    attach_kslab<kPlace != GP_PLACE_SMEM>(s, gA, gA_stride);
     gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
   }
 }
 
-template <bool kGlobalA>
+template <int kPlace>
 __device__ __forceinline__ void eval_init(DevCtx& c, double* smem) {
-  if constexpr (kGlobalA) {
+  if constexpr (kPlace == GP_PLACE_TILED) {
     GpTiled tl = gp_tiled_carve<TiledCfg>(smem, smem, 1, c.nwarp, 0);   // (only the shared-memory part is used)
     gp_tiled_init<TiledCfg>(c, tl);
   }
 }
 
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
-template <class Kern, bool kGlobalA>
+template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
                                                             double* gA, size_t gA_stride, long long* marks) {
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
   if (blockIdx.x == 0) c.marks = marks;
   uint32_t pipe_it = 0;
-  eval_init<kGlobalA>(c, smem);
+  eval_init<kPlace>(c, smem);
   for (int64_t kk = blockIdx.x; kk < B; kk += gridDim.x) {
     const int64_t cu = curve_of(tab, kk);
     if (tab.pstatus[cu] != 0) {
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab,
     GpCurveView cv = curve_view(tab, cu);
     double l, g[Kern::P];
     bool ok;
-    eval_curve<Kern, kGlobalA>(c, cv, theta + cu * P, smem, gA, gA_stride, pipe_it, l, g, ok);
+    eval_curve<Kern, kPlace>(c, cv, theta + cu * P, smem, gA, gA_stride, pipe_it, l, g, ok);
     if (threadIdx.x == 0) { lml[cu] = l; for (int k = 0; k < Kern::P; ++k) grad[cu * P + k] = g[k]; }
     __syncthreads();
   }
@@ -246,7 +252,7 @@ __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f
   return live;
 }
 
-template <class Kern, bool kGlobalA>
+template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
@@ -254,14 +260,14 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
   if ((int)blockIdx.x >= count) return;
   const int32_t* list = d.list + (size_t)(round & 1) * d.window;
   uint32_t pipe_it = 0;
-  eval_init<kGlobalA>(c, smem);
+  eval_init<kPlace>(c, smem);
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
     const int slot = list[i];
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
     double l, g[Kern::P];
     bool ok;
-    eval_curve<Kern, kGlobalA>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
+    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
     if (threadIdx.x == 0) {
       d.f_out[slot] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = 0; k < Kern::P; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
 // launch in which CTA b owns slot list[b] and alternates evaluation (all warps) and optimiser step (thread 0) until the slot runs
 // dry.  No rounds, no host round trips: a tail round costs an evaluation plus a step latency instead of two launches and two
 // under-filled kernels.  Same block geometry as fit_eval_kernel, so a run's numbers do not depend on which kernel finished it.
-template <class Kern, bool kGlobalA>
+template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int go;
@@ -283,13 +289,13 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, 
   if ((int)blockIdx.x >= d.counts[round]) return;
   const int slot = d.list[(size_t)(round & 1) * d.window + blockIdx.x];
   uint32_t pipe_it = 0;
-  eval_init<kGlobalA>(c, smem);
+  eval_init<kPlace>(c, smem);
   for (;;) {
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
     double l, g[FG_MAXP];
     bool ok;
-    eval_curve<Kern, kGlobalA>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
+    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
     if (threadIdx.x == 0) {
       for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
@@ -318,7 +324,7 @@ struct PredictArgs {
   size_t gA_stride, gV_stride;
 };
 
-template <class Kern, bool kGlobalA>
+template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double tlim[2];
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
   // the warps' V tiles: behind the matrix and vectors in shared memory, or this CTA's global slab for long curves
   double* Vglobal = a.gV + (size_t)blockIdx.x * a.gV_stride;
   uint32_t pipe_it = 0;
-  eval_init<kGlobalA>(c, smem);
+  eval_init<kPlace>(c, smem);
   for (int64_t kk = blockIdx.x; kk < a.B; kk += gridDim.x) {
     const int64_t cu = curve_of(a.tab, kk);
     GpCurveView cv = curve_view(a.tab, cu);
@@ -356,12 +362,12 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
     double l = NAN;
     if (st) {
       for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }
-    } else if constexpr (kGlobalA) {
+    } else if constexpr (kPlace == GP_PLACE_TILED) {
       GpTiled tl = gp_tiled_carve<TiledCfg>(a.gA + (size_t)blockIdx.x * a.gA_stride, smem, cv.n, c.nwarp, pipe_it);
       st = gp_tiled_predict_curve<Kern, TiledCfg>(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, tl, Vglobal, a.mean + out0, a.stdv + out0, l);
       pipe_it = tl.it;
     } else {
-      GpSmem s = carve<kGlobalA>(smem, a.gA, a.gA_stride, cv.n);
+      GpSmem s = carve<kPlace != GP_PLACE_SMEM>(smem, a.gA, a.gA_stride, cv.n);
       double* V = a.gV_stride ? Vglobal : smem + gp_smem_doubles(cv.n);   // (classes near the shared-memory limit keep V in the slab too)
       st = gp_predict_curve<Kern>(c, cv, a.theta + cu * a.P, a.tab.stats + cu * 6, qd, s, V, a.mean + out0, a.stdv + out0, l);
     }
@@ -377,12 +383,12 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
 // What gp_kernels.cu needs from a family: its parameter count and three launch functions (return a cudaError_t as int).
 struct GpFamilyOps {
   int n_params;
-  int (*lml)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P, const double* theta,
+  int (*lml)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P, const double* theta,
              double* lml, double* grad, double* gA, size_t gA_stride, long long* marks);
-  int (*eval_prepare)(bool globalA, size_t smem);
-  int (*eval)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
-  int (*tail)(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
-  int (*predict)(bool globalA, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a);
+  int (*eval_prepare)(int place, size_t smem);
+  int (*eval)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
+  int (*tail)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
+  int (*predict)(int place, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a);
 };
 
 template <class K>
@@ -391,44 +397,47 @@ inline int gp_set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
+// runs `body(std::integral_constant<int, place>)` for the runtime placement
+#define GP_PLACE_SWITCH(place, ...)                                               \
+  switch (place) {                                                                \
+    case GP_PLACE_SMEM: { constexpr int kP = GP_PLACE_SMEM; __VA_ARGS__; } break;         \
+    case GP_PLACE_SLAB: { constexpr int kP = GP_PLACE_SLAB; __VA_ARGS__; } break;         \
+    default: { constexpr int kP = GP_PLACE_TILED; __VA_ARGS__; } break;                   \
+  }
+
 template <class Kern>
 struct GpFamilyLaunch {
-  static int lml(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P,
+  static int lml(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P,
                  const double* theta, double* lml, double* grad, double* gA, size_t gA_stride, long long* marks) {
-    int rc;
-    if (globalA) {
-      if ((rc = gp_set_smem(lml_kernel<Kern, true>, smem))) return rc;
-      lml_kernel<Kern, true><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
-    } else {
-      if ((rc = gp_set_smem(lml_kernel<Kern, false>, smem))) return rc;
-      lml_kernel<Kern, false><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
-    }
+    int rc = 0;
+    GP_PLACE_SWITCH(place, {
+      if ((rc = gp_set_smem(lml_kernel<Kern, kP>, smem))) return rc;
+      lml_kernel<Kern, kP><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
+    })
     return (int)cudaGetLastError();
   }
-  static int eval_prepare(bool globalA, size_t smem) {
-    int rc = globalA ? gp_set_smem(fit_eval_kernel<Kern, true>, smem) : gp_set_smem(fit_eval_kernel<Kern, false>, smem);
-    if (rc) return rc;
-    return globalA ? gp_set_smem(fit_tail_kernel<Kern, true>, smem) : gp_set_smem(fit_tail_kernel<Kern, false>, smem);
+  static int eval_prepare(int place, size_t smem) {
+    int rc = 0;
+    GP_PLACE_SWITCH(place, {
+      if ((rc = gp_set_smem(fit_eval_kernel<Kern, kP>, smem))) return rc;
+      rc = gp_set_smem(fit_tail_kernel<Kern, kP>, smem);
+    })
+    return rc;
   }
-  static int eval(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
-    if (globalA) fit_eval_kernel<Kern, true><<<grid, threads, smem, st>>>(d, round);
-    else fit_eval_kernel<Kern, false><<<grid, threads, smem, st>>>(d, round);
+  static int eval(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
+    GP_PLACE_SWITCH(place, { fit_eval_kernel<Kern, kP><<<grid, threads, smem, st>>>(d, round); })
     return 0;
   }
-  static int tail(bool globalA, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
-    if (globalA) fit_tail_kernel<Kern, true><<<grid, threads, smem, st>>>(d, round);
-    else fit_tail_kernel<Kern, false><<<grid, threads, smem, st>>>(d, round);
+  static int tail(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
+    GP_PLACE_SWITCH(place, { fit_tail_kernel<Kern, kP><<<grid, threads, smem, st>>>(d, round); })
     return 0;
   }
-  static int predict(bool globalA, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a) {
-    int rc;
-    if (globalA) {
-      if ((rc = gp_set_smem(predict_kernel<Kern, true>, smem))) return rc;
-      predict_kernel<Kern, true><<<grid, kPredictThreads, smem, st>>>(a);
-    } else {
-      if ((rc = gp_set_smem(predict_kernel<Kern, false>, smem))) return rc;
-      predict_kernel<Kern, false><<<grid, kPredictThreads, smem, st>>>(a);
-    }
+  static int predict(int place, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a) {
+    int rc = 0;
+    GP_PLACE_SWITCH(place, {
+      if ((rc = gp_set_smem(predict_kernel<Kern, kP>, smem))) return rc;
+      predict_kernel<Kern, kP><<<grid, kPredictThreads, smem, st>>>(a);
+    })
     return (int)cudaGetLastError();
   }
   static const GpFamilyOps* ops() {

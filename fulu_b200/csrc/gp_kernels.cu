@@ -34,7 +34,8 @@ struct WsLayout {
   bool stream_tail;   // the default window of a long-curve class: the whole fit in fit_tail_kernel
   size_t gA_stride, gV_stride;   // doubles per CTA
   size_t slabs;                  // per-CTA slabs allocated at gA
-  bool globalA;
+  bool globalA;   // the matrix lives in a global slab (place != GP_PLACE_SMEM)
+  int place;      // GP_PLACE_*
   size_t smem_eval, smem_predict;
 };
 
@@ -66,10 +67,14 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   // Longer curves (matrix in a global slab, streamed through shared-memory stages - gp_tiled.cuh): two 256-thread CTAs per SM up to
   // np = 512 (the serial 64 x 64 diagonal blocks of one overlap the streamed products of the other), one 512-thread CTA above.
   int occ;
-  if (w.globalA) {
-    occ = np <= 512 ? 2 : 1;
-    w.smem_eval = gp_tiled_smem_doubles<TiledCfg>(nmax, kEvalMaxThreads / occ / 32) * sizeof(double) + 16;
+  w.place = !w.globalA ? GP_PLACE_SMEM : (np <= 512 ? GP_PLACE_SLAB : GP_PLACE_TILED);
+  if (w.place == GP_PLACE_TILED) {
+    occ = 1;
+    w.smem_eval = gp_tiled_smem_doubles<TiledCfg>(nmax, kEvalMaxThreads / 32) * sizeof(double) + 16;
     w.smem_predict = gp_tiled_smem_doubles<TiledCfg>(nmax, kPredictThreads / 32) * sizeof(double) + 16;
+  } else if (w.place == GP_PLACE_SLAB) {
+    occ = 2;
+    w.smem_eval = vec;
   } else {
     w.smem_eval = full;
     occ = (int)((228 * 1024) / (w.smem_eval + 1024));
@@ -77,7 +82,7 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   // prediction: eight warps, each with its eight columns of V as T tiles (shared memory, or the CTA's global slab for long curves)
   const size_t vtiles = (size_t)(kPredictThreads / 32) * (np / GP_NB) * 64 * sizeof(double);
   const bool globalV = w.globalA || w.smem_eval + vtiles > kMaxSmem;
-  if (!w.globalA) w.smem_predict = globalV ? w.smem_eval : w.smem_eval + vtiles;
+  if (w.place != GP_PLACE_TILED) w.smem_predict = globalV ? w.smem_eval : w.smem_eval + vtiles;
   if (occ < 1) occ = 1;
   if (occ > 16) occ = 16;
   int threads = kEvalMaxThreads / occ / 32 * 32;
@@ -124,7 +129,9 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   // per-CTA slab: the matrix itself (+ the inverse's scratch panel and the inverted diagonal blocks) for long curves, a copy of the
   // K tiles for the gradient pass otherwise (FULU_GP_NO_KSLAB=1: none).  One slab per CTA that can be at work: never more than the
   // tasks (evaluation kernels) or the curves (prediction) of the call.
-  w.gA_stride = w.globalA ? gp_tiled_slab_doubles((int)np) : (getenv("FULU_GP_NO_KSLAB") ? 0 : 64 * ((np / GP_NB) * (np / GP_NB + 1) / 2));
+  w.gA_stride = w.place == GP_PLACE_TILED ? gp_tiled_slab_doubles((int)np)
+                : w.place == GP_PLACE_SLAB ? gp_mat_doubles((int)np)
+                                           : (getenv("FULU_GP_NO_KSLAB") ? 0 : 64 * ((np / GP_NB) * (np / GP_NB + 1) / 2));
   const size_t curves = (size_t)(b.order ? b.n_order : b.n_curves);
   size_t slabs = (size_t)w.grid_eval < tasks ? (size_t)w.grid_eval : tasks;
   if (w.globalA) {
@@ -533,7 +540,7 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
   if (rc) return rc;
   const int64_t B = n_active(*batch);
   unsigned grid = (unsigned)(B < w.grid_eval ? B : w.grid_eval);
-  rc = family_ops(batch->kernel)->lml(w.globalA, grid, w.threads_eval, w.smem_eval, st, tab, B, n_params, theta, lml, grad,
+  rc = family_ops(batch->kernel)->lml(w.place, grid, w.threads_eval, w.smem_eval, st, tab, B, n_params, theta, lml, grad,
                                       at<double>(workspace, w.gA), w.gA_stride, marks);
   if (rc) return rc;
   const unsigned g1 = (unsigned)((B + 255) / 256);
@@ -592,7 +599,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   fit_init_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
   CU_TRY(cudaGetLastError());
   const GpFamilyOps* ops = family_ops(batch->kernel);
-  rc = ops->eval_prepare(w.globalA, w.smem_eval);
+  rc = ops->eval_prepare(w.place, w.smem_eval);
   if (rc) return rc;
 
   const unsigned step_grid = (unsigned)((w.window + GP_STEP_THREADS - 1) / GP_STEP_THREADS);
@@ -612,7 +619,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
       for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreate(&tail_ev[i]));
       cudaEventRecord(tail_ev[0], st);
     }
-    ops->tail(w.globalA, ctas, w.threads_eval, w.smem_eval, st, d, 0);
+    ops->tail(w.place, ctas, w.threads_eval, w.smem_eval, st, d, 0);
     if (prof) cudaEventRecord(tail_ev[1], st);
     CU_TRY(cudaGetLastError());
     finished = true;
@@ -636,7 +643,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
         for (int i = 0; i < 3; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); ev.push_back(e); }
         cudaEventRecord(ev[3 * round], st);
       }
-      ops->eval(w.globalA, w.grid_eval, w.threads_eval, w.smem_eval, st, d, round);
+      ops->eval(w.place, w.grid_eval, w.threads_eval, w.smem_eval, st, d, round);
       if (prof) cudaEventRecord(ev[3 * round + 1], st);
       fit_step_kernel<<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round);
       if (prof) cudaEventRecord(ev[3 * round + 2], st);
@@ -658,7 +665,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     CU_TRY(cudaStreamSynchronize(cs));
     if (remaining == 0) { finished = true; break; }
     if (use_tail && remaining <= w.grid_eval) {   // (the count can only have gone down since: an upper bound on the CTAs needed)
-      ops->tail(w.globalA, (unsigned)remaining, w.threads_eval, w.smem_eval, st, d, round);
+      ops->tail(w.place, (unsigned)remaining, w.threads_eval, w.smem_eval, st, d, round);
       CU_TRY(cudaGetLastError());
       finished = true;
       ++launches;
@@ -728,7 +735,7 @@ static int predict_common(const fulu_gp_batch* batch, int32_t n_params, PredictA
   a.gA = at<double>(workspace, w.gA); a.gV = at<double>(workspace, w.gV);
   a.gA_stride = w.gA_stride; a.gV_stride = w.gV_stride;
   unsigned grid = (unsigned)(a.B < w.grid_predict ? a.B : w.grid_predict);
-  return family_ops(batch->kernel)->predict(w.globalA, grid, w.smem_predict, st, a);
+  return family_ops(batch->kernel)->predict(w.place, grid, w.smem_predict, st, a);
 }
 
 int fulu_gp_predict_grid_batch(const fulu_gp_batch* batch, int32_t n_params, const double* theta, const double* t_min, const double* t_max,

@@ -27,16 +27,16 @@
 #define GP_TILED_RW 2
 #endif
 #ifndef GP_TILED_KC
-#define GP_TILED_KC 2
+#define GP_TILED_KC 4
 #endif
 #ifndef GP_TILED_NS16
-#define GP_TILED_NS16 3   // stages of a 16-warp CTA (one per SM)
+#define GP_TILED_NS16 2   // stages of a 16-warp CTA (the evaluation kernels)
 #endif
 #ifndef GP_TILED_SLACK
 #define GP_TILED_SLACK 0  // stages kept out of the look-ahead
 #endif
 #ifndef GP_TILED_NS8
-#define GP_TILED_NS8 3    // stages of an 8-warp CTA (two per SM)
+#define GP_TILED_NS8 2    // stages of an 8-warp CTA (the prediction kernel)
 #endif
 #if defined(__CUDACC__)
 #define GP_MBAR_WORDS 1   // an mbarrier is 8 bytes of shared memory
@@ -51,9 +51,10 @@ struct GpTiledCfgDefault {
   static constexpr int KC = GP_TILED_KC;   // k-tiles per stage
   static constexpr int NS_MAX = GP_TILED_NS16 > GP_TILED_NS8 ? GP_TILED_NS16 : GP_TILED_NS8;
   GP_HD static int stages(int nwarp) { return nwarp >= 16 ? GP_TILED_NS16 : GP_TILED_NS8; }
-  // chunks in flight ahead of the one being multiplied (measured on B200, N = 1024 / 2048, one evaluation per CTA: three stages with
-  // two chunks ahead 14.8 / 18.8 TFLOP/s; four stages with one of them as slack - so that the issuing warp never waits for the
-  // slowest warp to leave the stage it refills - 13.6 / 17.4)
+  // chunks in flight ahead of the one being multiplied.  Measured on B200, N = 1024 / 2048, one evaluation per CTA, algorithmic
+  // TFLOP/s: KC = 2 with three stages and two chunks ahead 14.8 / 18.8; four stages, one of them slack (so that the issuing warp never
+  // waits for the slowest warp to leave the stage it refills) 13.6 / 17.4; four stages, three ahead 13.4 / 17.1; KC = 4 with two
+  // stages (2 KB copies, half the barrier rounds per k-tile) 15.7 / 20.4
   GP_HD static int lookahead(int ns) { return ns - 1 - GP_TILED_SLACK > 0 ? ns - 1 - GP_TILED_SLACK : 1; }
 };
 

@@ -496,14 +496,15 @@ class AugmentResult:
     peak_index: np.ndarray = None  # [B]
 
 
-MERGE_ABOVE = 511     # classes above this bound share one launch geometry (one 512-thread CTA per SM, matrix in a global slab)
-MERGE_BELOW_CURVES = 50   # ... and are merged upwards while they hold fewer curves than this (6 starts x 50 = two waves of 148 CTAs)
+MERGE_ABOVE = 511     # classes above this bound share one launch geometry (one 512-thread CTA per SM, the matrix in a global slab streamed
+                      # through shared-memory stages) and are merged into ONE class, run longest curves first: a fit there is one fused
+                      # launch fed by a task queue, and every class run on its own would end in its own tail of a few long optimiser runs
 
 
 def bucket_curves(lengths, buckets=N_BUCKETS):
     """Group curve indices by padded length so one kernel launch sees similar N (cost ~ N^3).  The long-curve classes
-    (bound > MERGE_ABOVE) all run with the same geometry, so a class too small to fill the GPU is merged into the next larger
-    one instead of running alone (results do not depend on the class there: only the slab stride does)."""
+    (bound > MERGE_ABOVE) all run with the same geometry and are merged into one class bounded by the longest (results do not
+    depend on the class there: only the slab stride and the size of the shared-memory vectors do)."""
     lengths = np.asarray(lengths)
     which = np.searchsorted(np.asarray(buckets), lengths, side="left")
     # beyond the last bucket: one class bounded by its own longest curve (8k - 1 like the others), never a bound below a member
@@ -511,7 +512,7 @@ def bucket_curves(lengths, buckets=N_BUCKETS):
     groups = [[int(buckets[k]) if k < len(buckets) else beyond, np.nonzero(which == k)[0]] for k in np.unique(which)]
     out = []
     for bound, idx in groups:   # ascending bounds
-        if out and out[-1][0] > MERGE_ABOVE and len(out[-1][1]) < MERGE_BELOW_CURVES:
+        if out and out[-1][0] > MERGE_ABOVE:
             prev = out.pop()
             idx = np.sort(np.concatenate([prev[1], idx]))
         out.append([bound, idx])

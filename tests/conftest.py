@@ -20,8 +20,13 @@ def _all_golden():
 
 
 def golden_names():
-    """Fixtures of the default kernel (fulu/gp_aug.py:29)."""
-    return [n for n in _all_golden() if not n.startswith("fam_")]
+    """Fixtures of the default kernel (fulu/gp_aug.py:29), short curves."""
+    return [n for n in _all_golden() if not n.startswith("fam_") and not n.startswith("ddf_")]
+
+
+def long_golden_names():
+    """BASELINE config #5 fixtures (N = 1024, 1536; tests/golden/make_golden.py --ddf): the long-curve path."""
+    return [n for n in _all_golden() if n.startswith("ddf_")]
 
 
 def family_golden_names():

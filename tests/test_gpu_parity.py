@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, relerr
+from conftest import golden_names, load_golden, long_golden_names, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -199,6 +199,40 @@ def test_config5_long_curves_fixed_theta_parity(engine, n):
         _, m, s_, _ = gp.augmentation(t.min(), t.max(), 24)
         assert relerr(pred["mean"][i].cpu().numpy().reshape(-1), m, floor=1e-3 * gp.y_std) < 1e-9
         assert relerr(pred["std"][i].cpu().numpy().reshape(-1), s_) < 1e-9
+
+
+@pytest.mark.parametrize("name", long_golden_names())
+def test_config5_reference_fixtures_fixed_theta_and_full_fit(engine, name):
+    """BASELINE config #5 against the REAL reference (fixtures from fulu/gp_aug.py:68-77 at N = 1024 / 1536, make_golden.py --ddf),
+    through the tiled long-curve path: LML / gradient at the six starts and theta*, the augmentation at theta* and at a fixed
+    restart point within 1e-9; then the whole fit - six L-BFGS-B runs in the streamed kernel - ends no worse than the reference's
+    LML by more than 1e-6."""
+    from oracle import gp_oracle as O
+
+    gs, hb, db = _batch_from_golden([name], engine, False)
+    g = gs[0]
+    assert db.n_max >= 1024
+    p2l = {b: float(v) for b, v in enumerate(g["loglam"])}
+    gp = O.ClosedFormGP(p2l).prepare(g["t"], g["flux"], g["flux_err"], g["band"])
+    for k in range(7):
+        out = engine.lml(db, torch.tensor(g["thetas"][k][None, :]))
+        lml, grad = float(out["lml"][0]), out["grad"][0].cpu().numpy()
+        assert abs(lml - g["lml"][k]) <= 1e-9 * max(1.0, abs(g["lml"][k])), k
+        _, _, gs_ = O.lml_and_grad(gp.X, gp.y, gp.alpha, g["thetas"][k], return_scale=True)
+        den = np.maximum(np.maximum(np.abs(g["grad"][k]), 1e-2 * gs_), 1e-30)
+        assert np.max(np.abs(grad - g["grad"][k]) / den) < 1e-9, k
+    n_obs = int(g["n_obs"])
+    for tk, fk, ek in (("theta_star", "flux_aug", "flux_err_aug"), (5, "flux_aug_theta5", "flux_err_aug_theta5")):
+        theta = torch.tensor((g[tk] if isinstance(tk, str) else g["thetas"][tk])[None, :])
+        out = engine.predict_grid(db, theta, n_obs, np.array([float(g["t_min"])]), np.array([float(g["t_max"])]))
+        assert relerr(out["mean"][0].cpu().numpy().reshape(-1), g[fk], floor=1e-3 * float(g["y_std"])) < 1e-9, tk
+        assert relerr(out["std"][0].cpu().numpy().reshape(-1), g[ek]) < 1e-9, tk
+    fit = engine.fit(db, profile="counts")
+    assert fit["profile"]["rounds"] == 0 and fit["profile"]["global_a"] == 1      # the streamed, tiled fit
+    lml = float(fit["lml"][0])
+    assert lml >= float(g["lml_star"]) - 1e-6, (lml, float(g["lml_star"]))
+    assert abs(lml - float(g["lml_star"])) < 1e-4
+    assert 0.5 * int(g["n_eval"]) <= int(fit["n_eval"][0]) <= 2 * int(g["n_eval"])
 
 
 def test_config5_fit_reaches_oracle_lml(engine):

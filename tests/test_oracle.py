@@ -79,6 +79,25 @@ def test_sklearn_port_is_the_reference(name):
     np.testing.assert_array_equal(t_aug, g["t_aug"])
 
 
+@pytest.mark.parametrize("name", ["ddf_1024", "ddf_1536"])
+def test_closed_form_on_config5_fixtures(name):
+    """The long curves of BASELINE config #5 as the real reference fitted them: LML and gradient at theta = 0, a restart point and
+    theta*, the augmentation at theta*."""
+    from conftest import load_golden
+
+    g = load_golden(name)
+    _, gp = _prep(g)
+    for k in (0, 4, 6):
+        l, gr, gs = O.lml_and_grad(gp.X, gp.y, gp.alpha, g["thetas"][k], return_scale=True)
+        assert abs(l - g["lml"][k]) <= 1e-10 * max(1.0, abs(g["lml"][k]))
+        assert np.max(np.abs(gr - g["grad"][k]) / np.maximum(np.maximum(np.abs(g["grad"][k]), 1e-3 * gs), 1e-30)) < 1e-9
+    gp.fit(g["t"], g["flux"], g["flux_err"], g["band"], theta=g["theta_star"])
+    t_aug, m, s, pb = gp.augmentation(float(g["t_min"]), float(g["t_max"]), int(g["n_obs"]))
+    np.testing.assert_array_equal(t_aug, g["t_aug"])
+    assert relerr(m, g["flux_aug"], floor=1e-3 * gp.y_std) < 1e-9
+    assert relerr(s, g["flux_err_aug"], floor=1e-6 * gp.y_std) < 1e-8
+
+
 def test_start_points_match_survey():
     s = O.start_points(4)
     assert s.shape == (6, 4)
