@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -50,16 +51,25 @@ KERNEL = "default"
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_sample_curves(workload, first, count):
+    """The CPU arm's curves: the SAME curves as the head of rank 0's GPU batch of that workload (make_workload), so final LMLs compare
+    curve by curve.  ddf: the N = 1024 part only (a fit at N = 2048 is ~10 minutes of one host core)."""
+    from fulu_b200 import datasets
+
+    if workload == "plasticc":
+        return datasets.plasticc_like(count, n_points=N_POINTS, first=first)
+    if workload == "ztf":
+        return datasets.ztf_like(count, first=first)
+    return datasets.ddf_like(count, n_points=1024, first=first)
+
+
 def _cpu_worker(args):
-    first, count, n_points, n_obs, kernel = args
+    workload, first, count, n_obs, kernel = args
     import warnings
 
-    import numpy as np
-
-    from fulu_b200 import datasets
     from oracle.fulu_sklearn_port import SklearnGPAugmentation, count_evals
 
-    hb = datasets.plasticc_like(count, n_points=n_points, first=first)
+    hb = cpu_sample_curves(workload, first, count)
     p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
     out = []
     for i in range(hb.n_curves):
@@ -73,7 +83,7 @@ def _cpu_worker(args):
     return out
 
 
-def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4):
+def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4, workload="plasticc"):
     """curves/s of the reference CPU path (sklearn GaussianProcessRegressor driven exactly as fulu drives it) on `cores` processes."""
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
@@ -81,13 +91,32 @@ def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4):
     cores = cores or os.cpu_count() or 1
     for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = "1"  # 8 procs x 1 BLAS thread beat 1 x 8 by 6x
-    tasks = [(first + i, min(chunk, n_curves - i), N_POINTS, N_OBS, KERNEL) for i in range(0, n_curves, chunk)]
+    if workload == "ddf":
+        chunk = 1
+    tasks = [(workload, first + i, min(chunk, n_curves - i), N_OBS, KERNEL) for i in range(0, n_curves, chunk)]
     with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
-        list(ex.map(_cpu_worker, [(10_000_000 + w, 1, N_POINTS, N_OBS, KERNEL) for w in range(cores)]))  # warm-up: imports + first fit
+        list(ex.map(_cpu_worker, [("plasticc", 10_000_000 + w, 1, N_OBS, KERNEL) for w in range(cores)]))  # warm-up: imports + first fit
         t0 = time.perf_counter()
         lml = [v for part in ex.map(_cpu_worker, tasks) for v in part]
         dt = time.perf_counter() - t0
     return n_curves / dt, dt, cores, lml   # lml: [(final LML, evaluations)] per curve, in curve order
+
+
+def cpu_sample_size(workload, cores, ref_curves):
+    """Bounded CPU samples: >= 256 curves of config #3 by default, a 2,000-curve sample of config #4, one N = 1024 curve
+    per host core of config #5."""
+    if workload == "ztf":
+        return max(2000, 2 * cores)
+    if workload == "ddf":
+        return cores
+    return max(2 * cores, min(ref_curves, 24 * cores))
+
+
+CPU_SAMPLE_TEXT = {
+    "plasticc": "curves of config #3 (N=100, 6 bands, M=768)",
+    "ztf": "curves of config #4 (ZTF-like, 2 bands, ragged N = 20..300, M=256)",
+    "ddf": "curves of config #5 at N = 1024 (6 bands, M=768; the N = 1536 / 2048 curves of the GPU batch are not in the CPU sample)",
+}
 
 
 def run_reference(args):
@@ -95,22 +124,23 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(2 * cores, min(args.ref_curves, 24 * cores))
+    per_step = cpu_sample_size(args.workload, cores, args.ref_curves) if args.workload != "ztf" else max(2 * cores, min(args.ref_curves, 24 * cores))
     vals, times = [], []
     for s in range(args.warmup + args.steps):
-        v, dt, cores, _ = cpu_reference_throughput(per_step, cores, first=s * per_step)
+        v, dt, cores, _ = cpu_reference_throughput(per_step, cores, first=s * per_step, workload=args.workload)
         if s >= args.warmup:
             vals.append(v)
             times.append(dt)
     value = per_step * len(times) / sum(times)
-    sample = f"{per_step} curves of config #3 per step (N={N_POINTS}, 6 bands, M={N_BANDS * N_OBS}), {cores} processes x 1 BLAS thread"
-    metric = METRIC if args.kernel == "default" else f"light curves/sec GP fit+augment (plasticc workload, {args.kernel} kernel)"
+    sample = f"{per_step} {CPU_SAMPLE_TEXT[args.workload]} per step, {cores} processes x 1 BLAS thread"
+    headline = args.workload == "plasticc" and args.kernel == "default"
+    metric = METRIC if headline else f"light curves/sec GP fit+augment ({args.workload} workload, {args.kernel} kernel)"
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": "curves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands)", "curves_per_step": per_step,
-                   "n_points": N_POINTS, "n_bands": N_BANDS, "n_obs": N_OBS, "kernel": args.kernel},
+        "config": {"workload": WORKLOADS[args.workload][0], "curves_per_step": per_step, "n_bands": 2 if args.workload == "ztf" else N_BANDS,
+                   "n_obs": N_OBS, "kernel": args.kernel},
         "cpu_baseline": {"value": value, "unit": "curves/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -235,6 +265,159 @@ def make_workload(name, B, rank):
     return CurveBatch.from_curves(curves, parts[0].loglam)
 
 
+def library_gpu_baseline(engine, host, spec, n_curves=4096, reps=3):
+    """Secondary yardstick: the same LML + gradient evaluation on the same curves through the GPU LIBRARIES - padded-batch
+    torch.linalg.cholesky / cholesky_solve / cholesky_inverse (cuSOLVER / cuBLAS batched kernels) and elementwise torch ops for the
+    kernel matrix and the traces - timed with CUDA events against this repo's evaluation (fulu_gp_lml_batch) on the same batch.
+    Not part of the product path; it only says what the hand-written kernel buys over the library route."""
+    import numpy as np
+    import torch
+
+    from fulu_b200.engine import DeviceBatch
+
+    B = min(n_curves, host.n_curves)
+    sub = host.slice(0, B)
+    L = sub.lengths()
+    if L.min() != L.max():
+        return None
+    N = int(L[0])
+    dev = engine.device
+    db = DeviceBatch.from_host(sub, dev, family=spec.family)
+    theta_h = np.tile(np.array([0.3, -0.7, 1.1, -3.0]), (B, 1))
+    theta = torch.tensor(theta_h, device=dev)
+    ours = engine.lml(db, theta)
+    # library route: standardise like the prep kernel (StandardScaler / y normalisation), then dense batched algebra
+    t = torch.tensor(sub.t.reshape(B, N), device=dev)
+    lam = torch.tensor(sub.loglam, device=dev)[torch.tensor(sub.band.reshape(B, N).astype(np.int64), device=dev)]
+    y = torch.tensor(sub.flux.reshape(B, N), device=dev)
+    xs = (t - t.mean(1, keepdim=True)) / t.std(1, unbiased=False, keepdim=True)
+    xl = (lam - lam.mean(1, keepdim=True)) / lam.std(1, unbiased=False, keepdim=True)
+    yn = (y - y.mean(1, keepdim=True)) / y.std(1, unbiased=False, keepdim=True)
+    c, lt, ll, s2 = (torch.exp(theta[:, k]) for k in range(4))
+    eye = torch.eye(N, dtype=torch.float64, device=dev)
+
+    def evaluate():
+        du2 = ((xs[:, :, None] - xs[:, None, :]) / lt[:, None, None]) ** 2
+        dv2 = ((xl[:, :, None] - xl[:, None, :]) / ll[:, None, None]) ** 2
+        E = c[:, None, None] * torch.exp(-0.5 * (du2 + dv2))
+        K = E + (s2[:, None, None] + 1e-10) * eye
+        Lc = torch.linalg.cholesky(K)
+        alpha = torch.cholesky_solve(yn[:, :, None], Lc)[:, :, 0]
+        lml = -0.5 * (yn * alpha).sum(1) - torch.log(torch.diagonal(Lc, dim1=1, dim2=2)).sum(1) - 0.5 * N * math.log(2 * math.pi)
+        W = alpha[:, :, None] * alpha[:, None, :] - torch.cholesky_inverse(Lc)
+        g = torch.stack([0.5 * (W * E).sum((1, 2)), 0.5 * (W * E * du2).sum((1, 2)), 0.5 * (W * E * dv2).sum((1, 2)),
+                         0.5 * s2 * torch.diagonal(W, dim1=1, dim2=2).sum(1)], 1)
+        return lml, g
+
+    lml_lib, g_lib = evaluate()
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        best = float("inf")
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    ms_lib = timed(evaluate)
+    ms_ours = timed(lambda: engine.lml(db, theta))
+    agree = float(torch.max(torch.abs(lml_lib - ours["lml"]) / torch.clamp(torch.abs(ours["lml"]), min=1.0)))
+    return {"what": "LML + gradient evaluations/s at fixed theta on the head of the batch: torch.linalg.cholesky + cholesky_solve + cholesky_inverse "
+                    "(cuSOLVER/cuBLAS batched) with elementwise torch ops, against fulu_gp_lml_batch (prep + evaluation kernel) on the same curves",
+            "curves": int(B), "n_points": N, "library_evals_per_s": B / (ms_lib * 1e-3), "ours_evals_per_s": B / (ms_ours * 1e-3),
+            "ours_over_library": ms_lib / ms_ours, "library_ms": ms_lib, "ours_ms": ms_ours, "max_rel_lml_difference": agree}
+
+
+def run_gpu_strong(args):
+    """Strong scaling of BASELINE config #4: ONE global ragged batch, the same on every rank, LPT-partitioned over the ranks by the cubic
+    cost model, fitted per rank with no collective on the data path, and gathered ONCE onto rank 0 - device tensors over NCCL, then one
+    D2H copy - all inside the timed call (sharding.fit_augment_sharded, the user-level entry point of a process group).
+    value = curves / max-over-ranks time of that call; nothing is resident beforehand except the library and the workspace."""
+    import numpy as np
+    import torch
+
+    import fulu_b200
+    from fulu_b200 import sharding
+    from fulu_b200.engine import kernel_spec_from_sklearn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    engine = fulu_b200.GPEngine(torch.device("cuda", local))
+    spec = kernel_spec_from_sklearn(make_kernel(args.kernel))
+    B = args.curves or 160000
+    desc, _, n_obs = WORKLOADS[args.workload]
+    host = make_workload(args.workload, B, 0)      # the same global batch on every rank
+    lengths = host.lengths()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return sharding.fit_augment_sharded(host, n_obs=n_obs, engine=engine, spec=spec)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    launches0 = engine.launches
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=engine.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        secs = float(t.item())
+        value = B * args.steps / secs
+        f_eval = lengths.astype(np.float64) ** 3 + 12.0 * lengths.astype(np.float64) ** 2
+        flops = float(np.dot(res.n_eval.astype(np.float64), f_eval))
+        line = {
+            "metric": f"light curves/sec GP fit+augment ({args.workload} workload, {args.kernel} kernel)", "value": value, "unit": "curves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc.replace("one batch per GPU per step", "ONE global batch per step, LPT-sharded over the ranks"),
+                       "curves_per_step": B, "n_points": f"{int(lengths.min())}..{int(lengths.max())} (mean {lengths.mean():.0f})", "n_bands": host.n_bands,
+                       "n_obs": n_obs, "kernel": args.kernel, "l2": f"inputs re-uploaded every step ({res.h2d_bytes / 1e6:.0f} MB on rank 0)",
+                       "parallelism": f"curves LPT-partitioned x{world}, no collective on the data path, one gather (NCCL point-to-point of device "
+                                      "tensors) onto rank 0 at the end, inside the timed call"},
+            "e2e": {"value": value, "unit": "curves/s", "h2d_bytes_per_step": int(res.h2d_bytes), "d2h_bytes_per_step": int(res.d2h_bytes)},
+            "gpu_launches": engine.launches - launches0, "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": flops / (secs / args.steps) / 1e12 / world, "unit": "TFLOP/s per GPU, whole call (algorithmic flops of the evaluations / wall time)"},
+            "sharding": {"lpt_imbalance_max_over_mean": res.lpt_imbalance, "gathered_bytes": int(res.d2h_bytes)},
+            "cpu_baseline": None,
+            "parity": {"status_histogram": res.status_histogram(), "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)]))},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -264,13 +447,13 @@ def run_gpu(args):
     headline = args.workload == "plasticc" and args.kernel == "default"
     # CPU baseline first (rank 0, N=1 only), before this process's CUDA context is busy
     cpu_base, cpu_curves = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "plasticc":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample_n = max(2 * cores, min(args.ref_curves, 24 * cores))
-        v, dt, cores, cpu_curves = cpu_reference_throughput(sample_n, cores)
+        sample_n = cpu_sample_size(args.workload, cores, args.ref_curves)
+        v, dt, cores, cpu_curves = cpu_reference_throughput(sample_n, cores, workload=args.workload)
         cpu_base = {"value": v, "unit": "curves/s", "cores": cores, "kind": "port",
-                    "sample": f"{sample_n} curves of config #3 (N={N_POINTS}, 6 bands, M={N_BANDS * N_OBS}) in {dt:.1f} s, {cores} processes x 1 BLAS thread, "
-                              "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"}
+                    "sample": f"{sample_n} {CPU_SAMPLE_TEXT[args.workload]} in {dt:.1f} s, {cores} processes x 1 BLAS thread, "
+                              "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py); the same curves as the head of the GPU batch"}
 
     engine = fulu_b200.GPEngine(torch.device("cuda", local))
     sampler = ClockSampler(local)
@@ -299,6 +482,10 @@ def run_gpu(args):
         step_resident()
     peak_dfma = engine.fp64_peak(0)
     peak_dmma = engine.fp64_peak(1)
+    peak = max(peak_dfma, peak_dmma)   # DFMA and DMMA share one pipe on B200: the higher reading is the pipe's rate
+    library = None
+    if rank == 0 and headline and not args.no_library_baseline:
+        library = library_gpu_baseline(engine, host, spec)
 
     # ---- timed: resident inputs
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,10 +554,10 @@ def run_gpu(args):
     traffic, traffic_src = None, None
     if headline:
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v5_eval_kernel_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_eval_kernel_traffic.json")))
             traffic = tj["dram_bytes_per_evaluation"] * (evals_all / world) / max(rounds, 1)
-            traffic_src = ("profiles/r01_v5_eval_kernel_traffic.json (dram__bytes_read+write per evaluation, ncu --set full) x evaluations "
-                           "per launch of this run")
+            traffic_src = ("profiles/r02_eval_kernel_traffic.json (dram__bytes_read+write per evaluation from the committed ncu --set full "
+                           "capture of this kernel) x evaluations per launch of this run; not re-measured in this run")
         except (OSError, KeyError, ValueError):
             pass
     # parity next to the CPU pass: the CPU sample is the first curves of rank 0's batch, so the final LMLs compare curve by
@@ -398,17 +585,18 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "curves/s", "h2d_bytes_per_step": int(res.h2d_bytes), "d2h_bytes_per_step": int(res.d2h_bytes)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel" if rounds else "fit_tail_kernel (long-curve classes: the whole fit is one fused launch)", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
-                     "frac": achieved / peak_dfma if peak_dfma else None, "traffic": traffic, "traffic_source": traffic_src,
+        "roofline": {"bound": "fp64", "kernel": "fit_eval_kernel" if rounds else "fit_tail_kernel (long-curve classes: the whole fit is one fused launch)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": (mean_in + 8 * 4 + 8 * 5) * (evals_all / world) / max(rounds, 1),
-                     "peak_source": "DFMA rate measured in this run (fulu_gp_fp64_peak mode 0); MEASURED_PEAKS.json has no FP64 entry",
-                     "peak_dmma": peak_dmma, "flops_per_eval": (N_POINTS ** 3 + 12 * N_POINTS ** 2) if args.workload == "plasticc" else flops_all / max(evals_all, 1),
+                     "peak_source": "max of the DFMA and DMMA m8n8k4 register-resident loops measured in this run (fulu_gp_fp64_probe, CUDA events; "
+                                    "the two instructions share the FP64 pipe); MEASURED_PEAKS.json has no FP64 entry",
+                     "peak_dfma": peak_dfma, "peak_dmma": peak_dmma, "flops_per_eval": (N_POINTS ** 3 + 12 * N_POINTS ** 2) if args.workload == "plasticc" else flops_all / max(evals_all, 1),
                      "evals_per_curve": evals_all / (world * B * args.steps),
-                     "frac_at_sklearn_evals": (achieved / peak_dfma * parity_cpu["sklearn_evals_per_curve"] / parity_cpu["gpu_evals_per_curve_same_curves"])
-                     if (parity_cpu and peak_dfma) else None,
+                     "frac_at_sklearn_evals": (achieved / peak * parity_cpu["sklearn_evals_per_curve"] / parity_cpu["gpu_evals_per_curve_same_curves"])
+                     if (parity_cpu and peak) else None,
                      "eval_kernel_ms_per_step": eval_ms_all / args.steps, "eval_kernel_share_of_step": eval_ms_all / ms_max,
-                     "timing": "kernel durations from CUDA events on the launching stream in a separate pass of the same K steps; "
-                               "the timed region itself runs without them",
+                     "timing": "kernel durations from CUDA events on the launching stream in a separate pass of the same K steps (same launch "
+                               "schedule, the fused launch that finishes a fit included); the timed region itself runs without them",
                      "step_kernel_ms_per_step": step_ms / args.steps, "rounds_per_step": rounds / args.steps,
                      "hbm_gbs_algorithmic": value / world * (mean_in + out_bytes) / 1e9,
                      "launch_classes": [{"n_max": int(c["bound"]), "curves": int(c["curves"]), "ctas": int(c["grid_eval"]), "threads": int(c["threads_eval"]),
@@ -416,7 +604,9 @@ def run_gpu(args):
                                          "eval_ms": c["eval_ms"]} for c in classes],
                      "grid": int(classes[0]["grid_eval"]), "smem_per_cta": int(classes[0]["smem_eval"])},
         "cpu_baseline": cpu_base,
-        "parity": {"curves_flagged": int(stats[2]), "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)])), "vs_cpu_pass": parity_cpu},
+        "gpu_library_baseline": library,
+        "parity": {"curves_flagged": int(stats[2]), "status_histogram_rank0": res.status_histogram(),
+                   "mean_lml": float(np.mean(res.lml[np.isfinite(res.lml)])), "vs_cpu_pass": parity_cpu},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -435,11 +625,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-curves", type=int, default=256, help="CPU sample size per step (bounded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the cuSOLVER/torch yardstick of the headline run")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every rank its own batch; strong: ONE global batch LPT-sharded over the ranks, results gathered "
+                         "onto rank 0 inside the timed end-to-end call (sharding.fit_augment_sharded)")
     args = ap.parse_args()
     global KERNEL
     KERNEL = args.kernel
     if args.impl == "reference":
         run_reference(args)
+    elif args.scaling == "strong":
+        run_gpu_strong(args)
     else:
         run_gpu(args)
 

@@ -7,7 +7,7 @@ import os
 from .build import LIB_PATH
 
 MAX_PARAMS = 6
-ABI_VERSION = 4   # FULU_GP_ABI_VERSION of include/fulu_gp.h this binding was written against
+ABI_VERSION = 5   # FULU_GP_ABI_VERSION of include/fulu_gp.h this binding was written against
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
@@ -34,7 +34,7 @@ class FitOptions(ctypes.Structure):
 
 EXPORTS = (
     "fulu_gp_abi_version", "fulu_gp_strerror", "fulu_gp_workspace_bytes", "fulu_gp_lml_batch", "fulu_gp_fit_batch",
-    "fulu_gp_predict_grid_batch", "fulu_gp_predict_points_batch", "fulu_gp_fp64_peak", "fulu_gp_debug_phase_cycles",
+    "fulu_gp_predict_grid_batch", "fulu_gp_predict_points_batch", "fulu_gp_fp64_probe", "fulu_gp_debug_phase_cycles",
     "fulu_gp_peak_batch", "fulu_gp_ingest_workspace_bytes", "fulu_gp_ingest_table",
 )
 
@@ -64,10 +64,10 @@ def load():
     lib.fulu_gp_strerror.argtypes = [ctypes.c_int]
     lib.fulu_gp_workspace_bytes.argtypes = [ctypes.POINTER(Batch), i32, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
     lib.fulu_gp_lml_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
-    lib.fulu_gp_fit_batch.argtypes = [ctypes.POINTER(Batch), ctypes.POINTER(FitOptions), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.fulu_gp_fit_batch.argtypes = [ctypes.POINTER(Batch), ctypes.POINTER(FitOptions), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_predict_grid_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_predict_points_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, ctypes.c_size_t, vp]
-    lib.fulu_gp_fp64_peak.argtypes = [i32, i32, c_double_p, vp]
+    lib.fulu_gp_fp64_probe.argtypes = [i32, i32, vp, ctypes.c_size_t, c_double_p, vp]
     lib.fulu_gp_peak_batch.argtypes = [ctypes.POINTER(Batch), vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.fulu_gp_ingest_workspace_bytes.argtypes = [i64, ctypes.POINTER(ctypes.c_size_t)]
     lib.fulu_gp_ingest_table.argtypes = [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]

@@ -346,8 +346,11 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
         // default: the curve's own time span
         if (threadIdx.x == 0) {
           const double* tr = a.t_raw + a.tab.offsets[cu];
-          double lo = tr[0], hi = tr[0];
-          for (int i = 1; i < cv.n; ++i) { lo = fmin(lo, tr[i]); hi = fmax(hi, tr[i]); }
+          double lo = 0.0, hi = 0.0;
+          if (cv.n > 0 && a.tab.pstatus[cu] == 0) {   // (an empty or unusable curve has no span: its grid is not evaluated)
+            lo = hi = tr[0];
+            for (int i = 1; i < cv.n; ++i) { lo = fmin(lo, tr[i]); hi = fmax(hi, tr[i]); }
+          }
           tlim[0] = lo; tlim[1] = hi;
         }
         __syncthreads();
@@ -359,6 +362,11 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
       qd.t_min = qd.t_max = 0.0;
     }
     int st = a.tab.pstatus[cu] != 0 ? FULU_GP_STATUS_BAD_INPUT : 0;
+    if (!st && a.n_obs <= 0) {   // explicit points: a query band outside the table is the caller's KeyError - flagged, not indexed
+      int bad = 0;
+      for (int q = threadIdx.x; q < qd.m; q += blockDim.x) bad |= (qd.qband[q] < 0 || qd.qband[q] >= a.tab.n_bands);
+      if (__syncthreads_or(bad)) st = FULU_GP_STATUS_BAD_INPUT;
+    }
     double l = NAN;
     if (st) {
       for (int q = threadIdx.x; q < qd.m; q += blockDim.x) { a.mean[out0 + q] = NAN; a.stdv[out0 + q] = NAN; }

@@ -241,7 +241,7 @@ __global__ void fit_select_kernel(SelectArgs a) {
     const double f = a.run_f[k * a.S + s];
     if (f < fb) { fb = f; best = s; }   // np.argmin: first minimum (_gpr.py:336-340)
     nev += a.run_nev[k * a.S + s];
-    if (a.run_lml) a.run_lml[cu * a.S + s] = -f;
+    if (a.run_lml) a.run_lml[cu * a.S + s] = (f < 1.0e99) ? -f : -INFINITY;
     if (a.run_theta)
       for (int q = 0; q < a.P; ++q) a.run_theta[(cu * a.S + s) * a.P + q] = a.run_x[(k * a.S + s) * FG_MAXP + q];
   }
@@ -255,7 +255,11 @@ __global__ void fit_select_kernel(SelectArgs a) {
     const double tol = 1e-8 + 1e-5 * fabs(th);   // np.isclose(bound, theta)  (kernels.py:436-464)
     if (fabs(a.lo[q] - th) <= tol || fabs(a.hi[q] - th) <= tol) st |= FULU_GP_STATUS_AT_BOUND;
   }
-  a.lml_opt[cu] = -fb;
+  // the optimiser works with f = 1e100 where K is not positive definite (lbfgsb.cuh); a best run that never left that value has
+  // no finite LML: report sklearn's -inf (_gpr.py:592-593) and flag it
+  const bool never_pd = !(fb < 1.0e99);
+  if (never_pd && a.pstatus[cu] == 0) st |= FULU_GP_STATUS_NOT_PD;
+  a.lml_opt[cu] = never_pd ? -INFINITY : -fb;
   a.n_eval[cu] = nev;
   a.status[cu] = st;
 }
@@ -551,8 +555,8 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
 }
 
 int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,
-                      double* lml_opt, int32_t* n_eval, int32_t* status, double* run_lml, double* run_theta, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      double* lml_opt, double* scaler, double* ynorm, int32_t* n_eval, int32_t* status, double* run_lml, double* run_theta,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!opt) return FULU_GP_E_BADARG;
   int rc = check_batch(batch, opt->n_params);
   if (rc) return rc;
@@ -610,8 +614,8 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   int round = 0, group = 4;
   bool finished = false;
   // the tail (and every small fit): once the live slots fit one wave of CTAs, one fused launch finishes them (fit_tail_kernel)
-  const bool use_tail = !prof && getenv("FULU_GP_NO_TAIL") == nullptr;
-  cudaEvent_t tail_ev[2] = {nullptr, nullptr};   // profiling a streamed fit: the fused launch is the evaluation kernel of that fit
+  const bool use_tail = getenv("FULU_GP_NO_TAIL") == nullptr;
+  cudaEvent_t tail_ev[2] = {nullptr, nullptr};   // profiling: the fused launch counts as evaluation time (its optimiser steps are inside)
   const bool streamed = w.stream_tail && getenv("FULU_GP_NO_TAIL") == nullptr;
   if ((use_tail && d.n_tasks <= (int64_t)w.grid_eval) || streamed) {
     const unsigned ctas = (unsigned)(d.n_tasks < (int64_t)w.window ? d.n_tasks : (int64_t)w.window);   // fit_init_kernel filled that many slots at most
@@ -665,7 +669,12 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     CU_TRY(cudaStreamSynchronize(cs));
     if (remaining == 0) { finished = true; break; }
     if (use_tail && remaining <= w.grid_eval) {   // (the count can only have gone down since: an upper bound on the CTAs needed)
+      if (prof) {
+        for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreate(&tail_ev[i]));
+        cudaEventRecord(tail_ev[0], st);
+      }
       ops->tail(w.place, (unsigned)remaining, w.threads_eval, w.smem_eval, st, d, round);
+      if (prof) cudaEventRecord(tail_ev[1], st);
       CU_TRY(cudaGetLastError());
       finished = true;
       ++launches;
@@ -681,7 +690,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     for (int i = 0; i < 2; ++i) cudaEventDestroy(mark[i]);
   }
   if (opt->profile != nullptr) {
-    double eval_ms = 0.0, step_ms = 0.0;
+    double eval_ms = 0.0, step_ms = 0.0, tail_ms = 0.0;
     if (prof) {
       for (int r = 0; r < round; ++r) {
         float a = 0.f, b = 0.f;
@@ -696,12 +705,13 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
         cudaEventSynchronize(tail_ev[1]);
         cudaEventElapsedTime(&a, tail_ev[0], tail_ev[1]);
         eval_ms += a;
+        tail_ms = a;
         for (int i = 0; i < 2; ++i) cudaEventDestroy(tail_ev[i]);
       }
     }
     double* pr = opt->profile;
     pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = launches + (finished ? 0 : 1); pr[4] = w.window; pr[5] = w.grid_eval;
-    pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0; pr[8] = w.threads_eval; pr[9] = w.occ_eval;
+    pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0; pr[8] = w.threads_eval; pr[9] = w.occ_eval; pr[10] = tail_ms; pr[11] = w.place;
   }
   if (!finished) {
     fit_flush_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
@@ -713,6 +723,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   for (int k = 0; k < FG_MAXP; ++k) { sa.lo[k] = d.opt.lo[k]; sa.hi[k] = d.opt.hi[k]; }
   sa.theta_opt = theta_opt; sa.lml_opt = lml_opt; sa.run_lml = run_lml; sa.run_theta = run_theta; sa.n_eval = n_eval; sa.status = status;
   fit_select_kernel<<<(unsigned)((sa.B + 127) / 128), 128, 0, st>>>(sa);
+  if (scaler || ynorm) export_stats_kernel<<<(unsigned)((sa.B + 255) / 256), 256, 0, st>>>(sa.B, tab.order, tab.stats, scaler, ynorm);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -802,35 +813,19 @@ int fulu_gp_ingest_table(int64_t n_rows, const int64_t* object_id, const int32_t
   return 0;
 }
 
-int fulu_gp_fp64_peak(int32_t mode, int32_t iters, double* tflops, void* stream) {
-  if (!tflops || iters < 1) return FULU_GP_E_BADARG;
+int fulu_gp_fp64_probe(int32_t mode, int32_t iters, double* scratch, size_t scratch_bytes, double* flop, void* stream) {
+  if (!flop || !scratch || iters < 1) return FULU_GP_E_BADARG;
   DeviceInfo di;
   if (device_info(di)) return FULU_GP_E_NOCUDA;
-  cudaStream_t st = (cudaStream_t)stream;
   const int blocks = di.sms * 8;
-  double* out = nullptr;
-  CU_TRY(cudaMalloc(&out, (size_t)blocks * 256 * 8));
-  cudaEvent_t e0, e1;
-  CU_TRY(cudaEventCreate(&e0));
-  CU_TRY(cudaEventCreate(&e1));
-  double best = 0.0;
-  for (int rep = 0; rep < 4; ++rep) {
-    CU_TRY(cudaEventRecord(e0, st));
-    if (mode == 0) dfma_probe<<<blocks, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
-    else dmma_probe<<<blocks, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
-    CU_TRY(cudaEventRecord(e1, st));
-    CU_TRY(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    // DFMA: 8 FMA per thread per iteration; DMMA m8n8k4: 4 x 256 FMA per warp per iteration
-    const double fma_count = mode == 0 ? (double)blocks * 256.0 * 8.0 * iters : (double)blocks * 8.0 * 4.0 * 256.0 * iters;
-    const double tf = 2.0 * fma_count / (ms * 1e-3) / 1e12;
-    if (rep > 0 && tf > best) best = tf;
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(out);
-  *tflops = best;
+  if (scratch_bytes < (size_t)blocks * 256 * 8) return FULU_GP_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) dfma_probe<<<blocks, 256, 0, st>>>(scratch, iters, 1.0000001, 1e-9);
+  else dmma_probe<<<blocks, 256, 0, st>>>(scratch, iters, 1.0000001, 1e-9);
+  CU_TRY(cudaGetLastError());
+  // DFMA: 8 FMA per thread per iteration; DMMA m8n8k4: 4 x 256 FMA per warp per iteration
+  const double fma_count = mode == 0 ? (double)blocks * 256.0 * 8.0 * iters : (double)blocks * 8.0 * 4.0 * 256.0 * iters;
+  *flop = 2.0 * fma_count;
   return 0;
 }
 

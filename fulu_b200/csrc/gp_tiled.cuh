@@ -137,8 +137,10 @@ struct GpStreamJob {
   int tri;           // NT, TN: output tile (row r, column tile b0 + j) is wanted only for b0 + j <= r (blocks that meet the diagonal)
 };
 
-// slot of (warp w, i-th row of the warp): interleaved, so that a block with few rows spreads them over all warps
-#define GP_SLOT(w, i, nwarp) ((i) * (nwarp) + (w))
+// slot of (warp w, i-th row of the warp): a block with few rows spreads them over all warps, and a warp's rows pair up from the two
+// ends of the block (w and 2 nwarp - 1 - w), so that where a row's k-range depends on the row (NN: k <= r, TN: k >= r) every warp
+// gets the same number of tile products
+#define GP_SLOT(w, i, nwarp) (((i) & 1) ? ((i) + 1) * (nwarp) - 1 - (w) : (i) * (nwarp) + (w))
 
 // Chunk `chunk` of the job into its stage: called by every lane of warp 0; lane e issues the copies e, e + 32, ...
 template <int MODE, class Cfg, class Ctx>
@@ -210,6 +212,24 @@ GP_DEV void gp_stream_issue(Ctx& c, GpTiled& g, const GpStreamJob& job, int chun
   }
 }
 
+// B fragment of column tile j, k-tile kk of the chunk in stage S
+template <int MODE, int KC>
+GP_DEV void gp_stream_bfrag(const double* S, int BM, int kk, int j, const GpFrag& f, double& b0, double& b1) {
+  if (MODE == GP_MODE_NT) {
+    const double* Bp = S + 64 * ((BM + j) * KC + kk);
+    b0 = Bp[f.b0];
+    b1 = Bp[f.b1];
+  } else if (MODE == GP_MODE_NN) {
+    const double* Bp = S + 64 * (BM * KC + kk * GP_PW + j);
+    b0 = Bp[f.p0];
+    b1 = Bp[f.p1];
+  } else {
+    const double* Bp = S + 64 * (KC * BM + kk * GP_PW + j);
+    b0 = Bp[f.t0];
+    b1 = Bp[f.t1];
+  }
+}
+
 // acc[i][j][0..1] += sum over the job's k-tiles of A(row i of this warp, k) B(k, column tile j); accumulators in the PERMUTED layout
 // (column t, column 4 + t) for NT and NN, in the natural one (columns 2t, 2t + 1) for TN - as in gp_block.cuh.  Tile products that
 // are not wanted (above the diagonal, k outside a row's range) are skipped, warp by warp.
@@ -234,6 +254,7 @@ GP_DEV void gp_stream_mma(Ctx& c, GpTiled& g, const GpStreamJob& job, const GpFr
   const int t4 = c.lane & 3;
   int rowid[RW], jlim[RW];   // this warp's rows and how many of the panel's column tiles each wants (0: no such row)
   int jmax = 0;
+  bool jfull = true;
 #pragma unroll
   for (int i = 0; i < RW; ++i) {
     const int sl = GP_SLOT(c.warp, i, c.nwarp);
@@ -243,6 +264,7 @@ GP_DEV void gp_stream_mma(Ctx& c, GpTiled& g, const GpStreamJob& job, const GpFr
     if (sl >= job.nrows || jl < 0) jl = 0;
     jlim[i] = jl;
     if (jl > jmax) jmax = jl;
+    jfull = jfull && jl == GP_PW;
   }
   for (int q = 0; q < nchunk; ++q) {
     if (c.warp == 0 && q + LA < nchunk) gp_stream_issue<MODE, Cfg>(c, g, job, q + LA, it0 + q + LA);
@@ -285,24 +307,30 @@ GP_DEV void gp_stream_mma(Ctx& c, GpTiled& g, const GpStreamJob& job, const GpFr
             }
             anyact = anyact || act[i];
           }
-          if (anyact) {
+          bool allact = jfull;
+#pragma unroll
+          for (int i = 0; i < RW; ++i) allact = allact && act[i];
+          if (allact) {
+            // the common case - every row of the warp active, all eight column tiles wanted - without a predicate in sight; the B
+            // fragment of the next column tile is loaded before the products of this one are issued
+            double b0n, b1n;
+            gp_stream_bfrag<MODE, KC>(S, BM, kk, 0, f, b0n, b1n);
+#pragma unroll
+            for (int j = 0; j < GP_PW; ++j) {
+              const double b0 = b0n, b1 = b1n;
+              if (j + 1 < GP_PW) gp_stream_bfrag<MODE, KC>(S, BM, kk, j + 1, f, b0n, b1n);
+#pragma unroll
+              for (int i = 0; i < RW; ++i) {
+                c.mma(acc[i][j][0], acc[i][j][1], a0[i], b0);
+                c.mma(acc[i][j][0], acc[i][j][1], a1[i], b1);
+              }
+            }
+          } else if (anyact) {
 #pragma unroll
             for (int j = 0; j < GP_PW; ++j) {
               if (j < jmax) {
                 double b0, b1;
-                if (MODE == GP_MODE_NT) {
-                  const double* Bp = S + 64 * ((BM + j) * KC + kk);
-                  b0 = Bp[f.b0];
-                  b1 = Bp[f.b1];
-                } else if (MODE == GP_MODE_NN) {
-                  const double* Bp = S + 64 * (BM * KC + kk * GP_PW + j);
-                  b0 = Bp[f.p0];
-                  b1 = Bp[f.p1];
-                } else {
-                  const double* Bp = S + 64 * (KC * BM + kk * GP_PW + j);
-                  b0 = Bp[f.t0];   // (tile (k, b0 + j) exists: b0 + j <= row <= k for every row that is active here)
-                  b1 = Bp[f.t1];
-                }
+                gp_stream_bfrag<MODE, KC>(S, BM, kk, j, f, b0, b1);   // (TN: tile (k, b0 + j) exists for every product issued below)
 #pragma unroll
                 for (int i = 0; i < RW; ++i) {
                   if (act[i] && j < jlim[i]) {

@@ -57,6 +57,8 @@ class KernelSpec:
     seed: int = 42  # fulu/gp_aug.py:69 random_state
     perm: np.ndarray = None
     polish: int = None  # continuation runs from the best point (see GPEngine.fit); default 0 for the default family, 1 otherwise
+    extra_starts: int = 0  # insurance starts beyond sklearn's 1 + n_restarts, drawn from RandomState(seed + 1): the first 1 + n_restarts
+    #                        runs stay exactly sklearn's, the extra ones can only raise the final LML (multi-modal 5/6-parameter kernels)
 
     def __post_init__(self):
         if self.family not in COMPILED_FAMILIES:
@@ -102,6 +104,9 @@ class KernelSpec:
         pts = [self.theta0.copy()]
         for _ in range(self.n_restarts):
             pts.append(self.from_sklearn(rng.uniform(lo, hi)))
+        rng2 = np.random.RandomState(self.seed + 1)
+        for _ in range(self.extra_starts):
+            pts.append(self.from_sklearn(rng2.uniform(lo, hi)))
         return np.ascontiguousarray(np.array(pts), np.float64)
 
 
@@ -175,6 +180,26 @@ def kernel_spec_from_sklearn(kernel):
     perm = np.asarray(perm, np.int64)
     b = np.asarray(kernel.bounds, np.float64)
     return KernelSpec(family, np.asarray(kernel.theta, np.float64)[perm], b[perm, 0].copy(), b[perm, 1].copy(), perm=perm)
+
+
+class _nvtx:
+    """NVTX range around a stage of the path (ingest / upload / fit / predict / download), visible in Nsight timelines; free when no
+    profiler is attached."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        try:
+            torch.cuda.nvtx.range_push(self.name)
+            self.on = True
+        except Exception:   # NVTX missing from this torch build
+            self.on = False
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _require_cuda(device=None):
@@ -260,7 +285,7 @@ class GPEngine:
         self.lib = _capi.load()
         self.device = _require_cuda(device)
         self._ws = None
-        self.launches = 0  # evaluation rounds are counted by the library caller below
+        self.launches = 0  # kernels this engine has launched through the library (the library reports a fit's count; the other calls are fixed)
 
     # ---- plumbing
     def _stream(self):
@@ -292,6 +317,7 @@ class GPEngine:
             _capi.check(self.lib.fulu_gp_lml_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(out["lml"]), self._p(out["grad"]),
                                                    self._p(out["scaler"]), self._p(out["ynorm"]), self._p(out["status"]), self._p(ws),
                                                    ws.numel(), self._stream()))
+            self.launches += 4   # prep, evaluation, the two exports
             return out
 
     def phase_cycles(self, batch: DeviceBatch, theta):
@@ -313,7 +339,7 @@ class GPEngine:
     # ---- a6: optimiser
     def fit(self, batch: DeviceBatch, spec: KernelSpec = None, window=0, max_rounds=0, factr=1e7, pgtol=1e-5, maxiter=15000,
             maxfun=15000, maxls=20, m=10, return_runs=False, profile=False, out=None, polish=None):
-        """S = 1 + n_restarts L-BFGS-B runs per curve -> dict(theta [B,P], lml [B], n_eval [B], status [B]).
+        """S = 1 + n_restarts L-BFGS-B runs per curve -> dict(theta [B,P], lml [B], n_eval [B], status [B], scaler [B,4], ynorm [B,2]).
         `out`: a dict of such tensors to write into (rows of the curves `batch` selects; the others are left alone).
 
         `polish` (default spec.polish) continuation runs: a fresh L-BFGS-B run per curve started at its best point, kept where
@@ -334,32 +360,40 @@ class GPEngine:
             for k in range(P):
                 o.lower[k], o.upper[k] = spec.lower[k], spec.upper[k]
             if out is None:
-                out = dict(theta=self._new(B, P), lml=self._new(B), n_eval=self._new(B, dtype=torch.int32), status=self._new(B, dtype=torch.int32))
+                out = dict(theta=self._new(B, P), lml=self._new(B), n_eval=self._new(B, dtype=torch.int32), status=self._new(B, dtype=torch.int32),
+                           scaler=self._new(B, 4), ynorm=self._new(B, 2))
             else:
                 out = dict(out)
             if return_runs:
                 out["run_lml"] = self._new(B, S)
                 out["run_theta"] = self._new(B, S, P)
-            prof = (ctypes.c_double * 10)() if profile else None
-            if profile:   # True: per-launch CUDA events (eval_ms, step_ms); "counts": only rounds / launches / geometry, no events
-                o.profile = ctypes.cast(prof, ctypes.POINTER(ctypes.c_double))
-                o.profile_counts_only = 1 if profile == "counts" else 0
+            # True: per-launch CUDA events (eval_ms, step_ms); "counts" (and by default, for the launch counter): only rounds / launches /
+            # geometry, no events - the same launches as an unprofiled call
+            prof = (ctypes.c_double * 12)()
+            o.profile = ctypes.cast(prof, ctypes.POINTER(ctypes.c_double))
+            o.profile_counts_only = 0 if profile is True else 1
             ws = self._workspace(batch, P, S, window)
             _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts), self._p(out["theta"]),
-                                                   self._p(out["lml"]), self._p(out["n_eval"]), self._p(out["status"]),
+                                                   self._p(out["lml"]), self._p(out.get("scaler")), self._p(out.get("ynorm")),
+                                                   self._p(out["n_eval"]), self._p(out["status"]),
                                                    self._p(out.get("run_lml")), self._p(out.get("run_theta")), self._p(ws), ws.numel(),
                                                    self._stream()))
+            self.launches += int(prof[3])
             if profile:
-                keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a", "threads_eval", "ctas_per_sm")
+                keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a", "threads_eval", "ctas_per_sm",
+                        "tail_ms", "place")
                 out["profile"] = {k: float(prof[i]) for i, k in enumerate(keys)}
             for _ in range(spec.polish if polish is None else polish):
                 # rows the batch does not select hold copies of the current values, so they compare equal and stay
-                o.n_starts, o.starts_per_curve, o.profile, o.profile_counts_only = 1, 1, None, 0
+                o.n_starts, o.starts_per_curve = 1, 1
                 cont = dict(theta=out["theta"].clone(), lml=out["lml"].clone(), n_eval=torch.zeros_like(out["n_eval"]), status=out["status"].clone())
                 starts2 = out["theta"].contiguous()
+                prof2 = (ctypes.c_double * 12)()
+                o.profile, o.profile_counts_only = ctypes.cast(prof2, ctypes.POINTER(ctypes.c_double)), 1
                 _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts2), self._p(cont["theta"]),
-                                                       self._p(cont["lml"]), self._p(cont["n_eval"]), self._p(cont["status"]), None, None,
-                                                       self._p(ws), ws.numel(), self._stream()))
+                                                       self._p(cont["lml"]), None, None, self._p(cont["n_eval"]), self._p(cont["status"]),
+                                                       None, None, self._p(ws), ws.numel(), self._stream()))
+                self.launches += int(prof2[3])
                 better = cont["lml"] > out["lml"]
                 out["theta"].copy_(torch.where(better[:, None], cont["theta"], out["theta"]))
                 out["status"].copy_(torch.where(better, cont["status"], out["status"]))
@@ -386,6 +420,7 @@ class GPEngine:
             _capi.check(self.lib.fulu_gp_predict_grid_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(t_min), self._p(t_max), n_obs,
                                                             self._p(out["mean"]), self._p(out["std"]), self._p(out["lml"]),
                                                             self._p(out["status"]), self._p(ws), ws.numel(), self._stream()))
+            self.launches += 2   # prep + predict
             return out
 
     def predict_points(self, batch: DeviceBatch, theta, q_offsets, q_t, q_band):
@@ -402,6 +437,7 @@ class GPEngine:
             _capi.check(self.lib.fulu_gp_predict_points_batch(ctypes.byref(batch.c), P, self._p(theta), self._p(q_offsets), self._p(q_t),
                                                               self._p(q_band), 0, self._p(out["mean"]), self._p(out["std"]),
                                                               self._p(out["status"]), self._p(ws), ws.numel(), self._stream()))
+            self.launches += 2
             return out
 
     # ---- 8f-3: downstream consumer and upstream ingest on the device
@@ -423,6 +459,7 @@ class GPEngine:
             _capi.check(self.lib.fulu_gp_peak_batch(ctypes.byref(batch.c), self._p(mean), self._p(t_min), self._p(t_max), n_obs,
                                                     self._p(out.get("sum_flux")), self._p(out["peak_t"]), self._p(out["peak_flux"]),
                                                     self._p(out["peak_index"]), self._stream()))
+            self.launches += 1
             return out
 
     def ingest_table(self, object_id, t, flux, flux_err, passband, passband2lam, use_err=False, family=KERNEL_RBF_WHITE):
@@ -465,12 +502,23 @@ class GPEngine:
             batch = DeviceBatch(offsets, cols[0], cols[1], cols[2], band, loglam, int(lengths.max()) if B else 0, use_err, family=family)
             return batch, lengths, ids
 
-    def fp64_peak(self, mode=0, iters=20000):
-        """Measured FP64 TFLOP/s of a register-resident DFMA (mode 0) or DMMA (mode 1) loop on this GPU."""
+    def fp64_peak(self, mode=0, iters=20000, reps=4):
+        """Measured FP64 TFLOP/s of a register-resident DFMA (mode 0) or DMMA (mode 1) loop on this GPU: the library enqueues
+        the probe (fulu_gp_fp64_probe), the timing is CUDA events on the launching stream here; best of `reps` after a warm-up."""
         with torch.cuda.device(self.device):
-            v = ctypes.c_double()
-            _capi.check(self.lib.fulu_gp_fp64_peak(mode, iters, ctypes.byref(v), self._stream()))
-            return v.value
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            scratch = torch.empty(sms * 8 * 256, dtype=torch.float64, device=self.device)
+            flop = ctypes.c_double()
+            best = 0.0
+            for rep in range(reps + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _capi.check(self.lib.fulu_gp_fp64_probe(mode, iters, self._p(scratch), scratch.numel() * 8, ctypes.byref(flop), self._stream()))
+                e1.record()
+                e1.synchronize()
+                if rep > 0:
+                    best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            return best
 
 
 # ------------------------------------------------------------------------------------------------ batched entry point
@@ -494,6 +542,17 @@ class AugmentResult:
     peak_t: np.ndarray = None  # [B] grid time of the band-summed curve's maximum (reduce="peak")
     peak_flux: np.ndarray = None  # [B]
     peak_index: np.ndarray = None  # [B]
+    lpt_imbalance: float = None  # sharded runs: largest / mean modelled load of the ranks (sharding.fit_augment_sharded)
+
+    def status_histogram(self):
+        """How many curves carry each FULU_GP_STATUS_* bit (a curve can carry several): the per-batch health record."""
+        names = {"bad_input": STATUS_BAD_INPUT, "not_pd": STATUS_NOT_PD, "not_converged": STATUS_NOT_CONVERGED, "at_bound": STATUS_AT_BOUND,
+                 "neg_variance": STATUS_NEG_VARIANCE}
+        st = np.asarray(self.status)
+        out = {k: int(np.count_nonzero(st & bit)) for k, bit in names.items()}
+        out["ok"] = int(np.count_nonzero(st == 0))
+        out["curves"] = int(st.size)
+        return out
 
 
 MERGE_ABOVE = 511     # classes above this bound share one launch geometry (one 512-thread CTA per SM, the matrix in a global slab streamed
@@ -547,8 +606,10 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
             # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
             order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
         sub = db.select(order, n_max=bound)
-        f = engine.fit(sub, spec, window=window, out=fit, profile=profile)
-        engine.predict_grid(sub, fit["theta"], n_obs, t_min, t_max, out=pred)
+        with _nvtx(f"fulu_gp.fit n<={bound} x{len(idx)}"):
+            f = engine.fit(sub, spec, window=window, out=fit, profile=profile)
+        with _nvtx(f"fulu_gp.predict n<={bound} x{len(idx)}"):
+            engine.predict_grid(sub, fit["theta"], n_obs, t_min, t_max, out=pred)
         if profile:
             profiles.append(dict(f["profile"], bound=bound, curves=len(idx)))
     out = dict(mean=pred["mean"], std=pred["std"], theta=fit["theta"], lml=fit["lml"], n_eval=fit["n_eval"], status=fit["status"] | pred["status"])
@@ -578,9 +639,10 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
     if B == 0:
         return AugmentResult(np.empty((0, nb, n_obs)), np.empty((0, nb, n_obs)), np.empty((0, P)), np.empty(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
     with torch.cuda.device(engine.device):
-        db = DeviceBatch.from_host(curves, engine.device, use_err=use_err, pinned=pinned, family=spec.family)
-        tmn = None if t_min is None else torch.as_tensor(np.asarray(t_min, np.float64)).to(engine.device)
-        tmx = None if t_max is None else torch.as_tensor(np.asarray(t_max, np.float64)).to(engine.device)
+        with _nvtx("fulu_gp.h2d"):
+            db = DeviceBatch.from_host(curves, engine.device, use_err=use_err, pinned=pinned, family=spec.family)
+            tmn = None if t_min is None else torch.as_tensor(np.asarray(t_min, np.float64)).to(engine.device)
+            tmx = None if t_max is None else torch.as_tensor(np.asarray(t_max, np.float64)).to(engine.device)
         dev = fit_augment_device(engine, db, curves.lengths(), n_obs, tmn, tmx, spec, window)
         if reduce == "peak":
             pk = engine.peak(db, dev["mean"], tmn, tmx)
@@ -589,13 +651,14 @@ def fit_augment_batch(curves: CurveBatch, n_obs=128, t_min=None, t_max=None, use
             out = None
         elif reduce is not None:
             raise ValueError("reduce must be None or 'peak'")
-        if out is None:
-            host = {k: v.cpu() for k, v in dev.items()}
-        else:
-            host = {k: out[k][:B] for k in dev}
-            for k, v in dev.items():
-                host[k].copy_(v, non_blocking=True)
-            torch.cuda.current_stream(engine.device).synchronize()
+        with _nvtx("fulu_gp.d2h"):
+            if out is None:
+                host = {k: v.cpu() for k, v in dev.items()}
+            else:
+                host = {k: out[k][:B] for k in dev}
+                for k, v in dev.items():
+                    host[k].copy_(v, non_blocking=True)
+                torch.cuda.current_stream(engine.device).synchronize()
     theta = host["theta"].numpy()
     if not np.array_equal(spec.perm, np.arange(P)):
         theta = spec.to_sklearn(theta)
@@ -616,7 +679,8 @@ def fit_augment_table(object_id, t, flux, flux_err, passband, passband2lam, n_ob
     engine = engine or GPEngine(device)
     spec = spec or KernelSpec()
     with torch.cuda.device(engine.device):
-        db, lengths, ids = engine.ingest_table(object_id, t, flux, flux_err, passband, passband2lam, use_err=use_err, family=spec.family)
+        with _nvtx("fulu_gp.ingest"):
+            db, lengths, ids = engine.ingest_table(object_id, t, flux, flux_err, passband, passband2lam, use_err=use_err, family=spec.family)
         B, P = db.n_curves, spec.n_params
         if B == 0:
             nb = db.n_bands

@@ -9,6 +9,7 @@ import warnings
 
 import numpy as np
 import torch
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, WhiteKernel
 
 from .datasets import CurveBatch
 from .plotting import LcPlotter
@@ -46,28 +47,15 @@ class _Scaler:
         return (np.asarray(X, np.float64) - self.mean_) / self.scale_
 
 
-class _KernelView:
-    """``reg.kernel_`` when the class was built with the default kernel (kernel=None); with an sklearn kernel object
-    ``reg.kernel_`` is that object cloned with the fitted theta."""
-
-    def __init__(self, theta, bounds):
-        self.theta, self.bounds = np.asarray(theta), bounds
-
-    def __repr__(self):
-        c, lt, ll, s2 = np.exp(self.theta)
-        return f"{np.sqrt(c):.3g}**2 * RBF(length_scale=[{lt:.3g}, {ll:.3g}]) + WhiteKernel(noise_level={s2:.3g})"
-
-
 class _FittedGP:
     """What the reference exposes as ``aug.reg``: kernel_.theta, log_marginal_likelihood_value_, log_marginal_likelihood()."""
 
     def __init__(self, owner, theta, lml, n_eval):
         self._owner = owner
-        spec = owner._spec
-        if owner.kernel is not None:   # theta is in the kernel object's own (sklearn) order
-            self.kernel_ = owner.kernel.clone_with_theta(np.asarray(theta, np.float64))
-        else:
-            self.kernel_ = _KernelView(theta, np.c_[spec.to_sklearn(spec.lower), spec.to_sklearn(spec.upper)])
+        # a real sklearn kernel object, as in the reference (reg.kernel_ = clone of the prior with the fitted theta, _gpr.py:335-340);
+        # theta is in the kernel object's own (sklearn) order
+        self.kernel_ = owner.kernel.clone_with_theta(np.asarray(theta, np.float64))
+        self.kernel = owner.kernel
         self.log_marginal_likelihood_value_ = float(lml)
         self.n_eval_ = int(n_eval)
 
@@ -91,16 +79,21 @@ class GaussianProcessesAugmentation:
     -----------
     passband2lam : dict
         A dictionary, where key is a passband ID and value is Log10 of its wave length.
-    kernel : kernel object from sklearn, optional
+    kernel : kernel object from sklearn
         ``C * [Matern] * RBF([l_t, l_lambda]) + [Matern | RationalQuadratic] + WhiteKernel`` in any order (the reference's default
         ``C(1.0)*RBF([1.0, 1.0]) + WhiteKernel()``, its docstring kernel ``C(1.0)*RBF([1, 1]) + Matern() + WhiteKernel()``, the
         notebook's ``C*Matern()*RBF([1, 1]) + Matern() + WhiteKernel()``, ...; see ``engine.kernel_spec_from_sklearn``).  Initial
         values and bounds are honoured; other kernels raise NotImplementedError (there is no CPU fallback).
     use_err : bool
         Flag responsible for using flux error by GP Regressor.
+
+    The constructor is the reference's, argument for argument (fulu/gp_aug.py:29; tests/test_abi.py compares the signatures).  The GPU
+    is the process's current CUDA device; set the class or instance attribute ``device`` before ``fit`` to choose another one.
     """
 
-    def __init__(self, passband2lam, kernel=None, use_err=False, device=None):
+    device = None   # torch device (or None = current CUDA device) the engine of this object is created on
+
+    def __init__(self, passband2lam, kernel=C(1.0) * RBF([1.0, 1.0]) + WhiteKernel(), use_err=False):
         self.passband2lam = passband2lam
         self.plotter = LcPlotter(passband2lam)   # fulu/_base_aug.py:37; matplotlib is imported when something is drawn
         self.t_train = None
@@ -112,7 +105,6 @@ class GaussianProcessesAugmentation:
         self.kernel = kernel
         self.use_err = use_err
         self._spec = kernel_spec_from_sklearn(kernel)
-        self._device = device
         self._engine = None
         self._batch = None
         self._theta = None
@@ -137,19 +129,22 @@ class GaussianProcessesAugmentation:
             raise ValueError("Input contains NaN or infinity.")  # sklearn validate_data (_gpr.py:257-265)
         loglam = np.array([self.passband2lam[k] for k in self.passband2lam], dtype=np.float64)
         if self._engine is None:
-            self._engine = GPEngine(self._device)
+            self._engine = GPEngine(self.device)
         host = CurveBatch(np.array([0, len(t)], np.int64), t, flux, flux_err, band, loglam)
         self._batch = DeviceBatch.from_host(host, self._engine.device, use_err=self.use_err, family=self._spec.family)
         fit = self._engine.fit(self._batch, self._spec)
         status = int(fit["status"].cpu()[0])
         if status & STATUS_BAD_INPUT:
             raise ValueError("Input contains NaN, infinity or an unusable noise term.")
+        if status & STATUS_NOT_PD:   # the final factorisation of sklearn's fit fails the same way (_gpr.py:349-361)
+            raise np.linalg.LinAlgError("The kernel is not returning a positive definite matrix. Try gradually increasing the 'alpha' "
+                                        "parameter of your GaussianProcessRegressor estimator.")
         theta = self._spec.to_sklearn(fit["theta"].cpu().numpy()[0])   # reg.kernel_.theta is in the kernel object's order
         self._theta = fit["theta"]
-        stats = self._engine.lml(self._batch, fit["theta"])
-        self.ss = _Scaler(stats["scaler"].cpu().numpy()[0, [0, 2]], stats["scaler"].cpu().numpy()[0, [1, 3]])
+        scaler = fit["scaler"].cpu().numpy()[0]     # the fit's own outputs (fulu_gp_fit_batch): no second call
+        self.ss = _Scaler(scaler[[0, 2]], scaler[[1, 3]])
         self.reg = _FittedGP(self, theta, float(fit["lml"].cpu()[0]), int(fit["n_eval"].cpu()[0]))
-        self.reg._y_train_mean, self.reg._y_train_std = (float(v) for v in stats["ynorm"].cpu().numpy()[0])
+        self.reg._y_train_mean, self.reg._y_train_std = (float(v) for v in fit["ynorm"].cpu().numpy()[0])
         if status & STATUS_NOT_CONVERGED:
             warnings.warn("lbfgs failed to converge: abnormal termination in the line search or iteration limit reached.", ConvergenceWarning)
         if status & STATUS_AT_BOUND:

@@ -12,7 +12,7 @@
  *   - every pointer in fulu_gp_batch and every in/out array is a DEVICE pointer owned by the caller
  *     (PyTorch tensors); the library allocates nothing and keeps no global state;
  *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), except
- *     fulu_gp_fit_batch which returns after the optimisation loop has finished on the device;
+ *     fulu_gp_fit_batch which returns after the optimisation loop has finished on the device (see there);
  *   - return value: 0 ok, <0 argument error (FULU_GP_E_*), >0 a cudaError_t;
  *   - per-curve problems never fail the call: they are reported in status[] (FULU_GP_STATUS_* bits).
  *   - batches are ragged CSR: curve i owns observations offsets[i] .. offsets[i+1]-1.
@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FULU_GP_ABI_VERSION 4
+#define FULU_GP_ABI_VERSION 5
 #define FULU_GP_MAX_PARAMS 6
 #define FULU_GP_MAX_BANDS 16
 
@@ -108,10 +108,13 @@ typedef struct fulu_gp_fit_options {
   double pgtol;              /* 1e-5 */
   double lower[FULU_GP_MAX_PARAMS];   /* log-bounds, ln(1e-5) */
   double upper[FULU_GP_MAX_PARAMS];   /* ln(1e5) */
-  double* profile;           /* optional HOST pointer to 10 doubles, filled on return: [0] evaluation rounds, [1] ms spent in the
-                                evaluation kernel (CUDA events on `stream`), [2] ms in the optimiser-step kernel, [3] kernels this call launched,
-                                [4] window, [5] evaluation grid (CTAs), [6] dynamic shared memory per CTA (bytes), [7] 1 if K lives in
-                                global memory, [8] threads per evaluation CTA, [9] evaluation CTAs per SM.  NULL = no per-launch timing. */
+  double* profile;           /* optional HOST pointer to 12 doubles, filled on return: [0] evaluation rounds, [1] ms spent in the
+                                evaluation kernels (CUDA events on `stream`; includes [10]), [2] ms in the optimiser-step kernel, [3] kernels
+                                this call launched, [4] window, [5] evaluation grid (CTAs), [6] dynamic shared memory per CTA (bytes), [7] 1 if
+                                K lives in global memory, [8] threads per evaluation CTA, [9] evaluation CTAs per SM, [10] ms of the fused
+                                launch that finishes the fit (evaluations and optimiser steps of the last live slots), [11] placement of
+                                the matrix (0 shared memory, 1 global slab with the 8x8 block code, 2 global slab streamed through
+                                shared-memory stages).  NULL = no per-launch timing. */
 } fulu_gp_fit_options;
 
 int fulu_gp_abi_version(void);
@@ -131,10 +134,14 @@ int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double
  * Replaces GaussianProcessRegressor.fit's optimiser loop (_gpr.py:299-340,658-668).
  * theta_starts is read in place (see starts_per_curve); points outside the bounds are clipped (_lbfgsb_py.py:359).
  * theta_opt [B,P], lml_opt [B], n_eval [B] (LML+gradient evaluations spent on the curve), status [B] out.
- * run_lml [B,S] (final LML of every run) and run_theta [B,S,P] may be NULL. */
+ * scaler [B,4] = (t mean, t scale, loglam mean, loglam scale) and ynorm [B,2] = (flux mean, flux std) out (may be NULL): the fitted
+ * StandardScaler (fulu/gp_aug.py:65-66) and sklearn's y normalisation (_gpr.py:275-280), i.e. aug.ss and reg._y_train_mean/_std.
+ * run_lml [B,S] (final LML of every run) and run_theta [B,S,P] may be NULL.
+ * A curve whose covariance was never positive definite along its best run gets lml_opt = -inf and FULU_GP_STATUS_NOT_PD
+ * (sklearn: log_marginal_likelihood_value_ = -inf, then LinAlgError in fit, _gpr.py:349-361). */
 int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,
-                      double* lml_opt, int32_t* n_eval, int32_t* status, double* run_lml, double* run_theta, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      double* lml_opt, double* scaler, double* ynorm, int32_t* n_eval, int32_t* status, double* run_lml,
+                      double* run_theta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Augmentation: predictive mean / std on the band-major grid linspace(t_min[i], t_max[i], n_obs) x n_bands.
  * Replaces BaseAugmentation.augmentation -> predict -> reg.predict(return_std=True)
@@ -171,10 +178,11 @@ int fulu_gp_ingest_table(int64_t n_rows, const int64_t* object_id, const int32_t
                          int64_t max_objects, int64_t* offsets, int64_t* n_objects, int32_t* band, int32_t* unknown_bands,
                          void* workspace, size_t workspace_bytes, void* stream);
 
-/* FP64 roofline probe: runs a register-resident DFMA (mode 0) or DMMA m8n8k4 (mode 1) loop on every SM and returns the
- * achieved TFLOP/s in *tflops (CUDA-event timed on `stream`).  Used by bench.py for the roofline denominator because
- * MEASURED_PEAKS.json has no FP64 entry. */
-int fulu_gp_fp64_peak(int32_t mode, int32_t iters, double* tflops, void* stream);
+/* FP64 roofline probe: enqueues a register-resident DFMA (mode 0) or DMMA m8n8k4 (mode 1) loop on every SM of the current device
+ * and returns the floating-point operations it performs in *flop (host).  The CALLER times it (events on `stream`) and owns the
+ * scratch (device, >= 8 x 256 x 8 bytes per SM; the kernel's sink).  Used by bench.py for the roofline denominator because
+ * MEASURED_PEAKS.json has no FP64 entry.  Like every other entry point it allocates nothing and does not synchronise. */
+int fulu_gp_fp64_probe(int32_t mode, int32_t iters, double* scratch, size_t scratch_bytes, double* flop, void* stream);
 
 /* Diagnostics: same as fulu_gp_lml_batch, and CTA 0 writes clock64() at nine phase boundaries of its first... every evaluation into
  * marks[0..8] (device pointer to >= 16 int64): load, assemble, cholesky, z, inverse, alpha, traces, reduce.  Used by profiles/. */

@@ -28,7 +28,7 @@ def test_binding_loads_and_reports_version(lib_path):
     from fulu_b200 import _capi
 
     lib = _capi.load()
-    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 4
+    assert lib.fulu_gp_abi_version() == _capi.ABI_VERSION == 5
     assert b"workspace" in lib.fulu_gp_strerror(-2)
     assert set(_capi.EXPORTS) <= {n for n in dir(lib)} | set(_capi.EXPORTS)
 
@@ -53,6 +53,59 @@ def test_no_cpu_fallback_without_gpu():
     aug = fulu_b200.GaussianProcessesAugmentation({0: 3.5, 1: 3.7})
     with pytest.raises(RuntimeError):
         aug.fit([0.0, 1.0, 2.0], [1.0, 2.0, 1.5], [0.1, 0.1, 0.1], [0, 1, 0])
+
+
+def _reference_class_signatures():
+    """The reference's own class, imported where it lies (build container only), else the signatures recorded from it."""
+    import inspect
+    import sys
+    import types
+
+    ref = "/root/reference"
+    recorded = {"__init__": "(self, passband2lam, kernel=1**2 * RBF(length_scale=[1, 1]) + WhiteKernel(noise_level=1), use_err=False)",
+                "fit": "(self, t, flux, flux_err, passband)", "predict": "(self, t, passband)",
+                "augmentation": "(self, t_min, t_max, n_obs=100)"}
+    if not os.path.isdir(ref):
+        return recorded, False
+    saved = {m: sys.modules.get(m) for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "fulu", "fulu.gp_aug", "fulu._base_aug")}
+    try:
+        for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors"):
+            sys.modules[m] = types.ModuleType(m)
+        sys.modules["matplotlib.colors"].TABLEAU_COLORS = {}
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        pkg = types.ModuleType("fulu")
+        pkg.__path__ = [os.path.join(ref, "fulu")]
+        sys.modules["fulu"] = pkg
+        import fulu.gp_aug as gp_aug
+
+        cls = gp_aug.GaussianProcessesAugmentation
+        live = {k: str(inspect.signature(getattr(cls, k))) for k in recorded}
+    finally:
+        for m, v in saved.items():
+            if v is None:
+                sys.modules.pop(m, None)
+            else:
+                sys.modules[m] = v
+    assert live == recorded, "the recorded signatures are stale"
+    return live, True
+
+
+def test_class_signatures_are_the_reference_s():
+    """SURVEY 8b "Python surface to keep (exact)": constructor, fit, predict, augmentation take the reference's arguments with the
+    reference's defaults (fulu/gp_aug.py:29,37,80; fulu/_base_aug.py:88), and the default kernel is the reference's kernel object."""
+    import inspect
+
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, WhiteKernel
+
+    import fulu_b200
+
+    ref, _ = _reference_class_signatures()
+    cls = fulu_b200.GaussianProcessesAugmentation
+    for name, sig in ref.items():
+        assert str(inspect.signature(getattr(cls, name))) == sig, name
+    aug = cls({0: 3.5, 1: 3.7})
+    assert aug.kernel == C(1.0) * RBF([1.0, 1.0]) + WhiteKernel() and aug.use_err is False
+    assert aug.ss is None and aug.reg is None and aug.t_train is None
 
 
 def test_product_does_not_import_oracle():

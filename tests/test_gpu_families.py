@@ -159,12 +159,22 @@ def test_batched_entry_point_against_live_sklearn(engine, kname):
         assert relerr(res.flux_aug[i].reshape(-1), fr, floor=1e-3 * reg._y_train_std) < 1e-9, i
         assert relerr(res.flux_err_aug[i].reshape(-1), er, floor=1e-6 * reg._y_train_std) < 1e-9, i
     # The 5/6-parameter landscapes are multi-modal with nearly flat valleys: a restart can end in another basin than sklearn's run
-    # from the same start when the two differ by rounding (the same happens between two BLAS builds of sklearn).  The bar of
-    # 1e-6 is therefore asked of all curves but at most one of the twelve; the default kernel's tests ask it of every curve.
+    # from the same start when the two differ by rounding (the same happens between two BLAS builds of sklearn).  With sklearn's own
+    # six starts the bar of 1e-6 is therefore asked of all curves but at most one of the twelve (INTEGRATION.md states this
+    # per-family tolerance; the default kernel's tests ask it of every curve) ...
     deficits = np.array(deficits)
     print(kname, "LML deficits vs sklearn (positive = sklearn better):", np.array2string(deficits, precision=2))
     assert np.count_nonzero(deficits > 1e-6) <= 1, deficits
     assert np.median(deficits) <= 1e-8
+    # ... and with the insurance starts (KernelSpec.extra_starts: six more runs from an independent stream, sklearn's six untouched)
+    # no run may end lower than with the six alone, and the curves that missed are re-examined
+    spec2 = kernel_spec_from_sklearn(family_kernel(kname))
+    spec2.extra_starts = 6
+    res2 = fulu_b200.fit_augment_batch(hb, n_obs=32, engine=engine, spec=spec2)
+    assert np.all(res2.lml >= res.lml - 1e-9)
+    deficits2 = deficits - (res2.lml - res.lml)
+    print(kname, "with 6 extra starts:", np.array2string(deficits2, precision=2))
+    assert np.count_nonzero(deficits2 > 1e-6) <= np.count_nonzero(deficits > 1e-6)
 
 
 def test_unsupported_family_and_parameter_count_are_refused(engine):
