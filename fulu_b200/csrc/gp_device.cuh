@@ -191,6 +191,8 @@ struct FitDev {
   double *f_out, *g_out;
   int32_t* list;     // [2][window]
   int32_t* counts;   // [max_rounds + 2]
+  const volatile int32_t* ended;   // nonzero once a fit_tail_kernel launch has taken over what was live (its stamp, round + 1): every later launch has nothing to do
+  int32_t* ended_mark;             // the same word, for the launch that sets it
   unsigned long long* next_task;
   double *run_f, *run_x;
   int32_t *run_nev, *run_end;
@@ -252,11 +254,35 @@ __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f
   return live;
 }
 
+// One slot run to the end by this CTA: evaluation (all warps) and optimiser step (thread 0) in turn until the slot has nothing left
+// to do (a finished run pulls the next task of the queue into the slot).
+template <class Kern, int kPlace>
+__device__ __forceinline__ void run_slot_to_end(DevCtx& c, const FitDev& d, int slot, double* smem, uint32_t& pipe_it, int* go) {
+  for (;;) {
+    const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
+    GpCurveView cv = curve_view(d.tab, cu);
+    double l, g[FG_MAXP];
+    bool ok;
+    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
+      for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
+      *go = advance_slot(d, slot, -l, g) ? 1 : 0;
+      __threadfence_block();
+    }
+    __syncthreads();
+    if (!*go) break;   // (thread 0 next writes `go` after the barriers of a whole evaluation: no second barrier needed here)
+  }
+}
+
+// One round of the fit: every live slot's objective is evaluated at its current point.  Rounds are enqueued ahead of time, without
+// the host looking at the device (fulu_gp_fit_batch is stream-ordered), so a round may find nothing to do: no live slot, or the fit
+// already ended by fit_tail_kernel (d.ended).
 template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
   DevCtx c;
-  const int count = d.counts[round];
+  const int count = *d.ended ? 0 : d.counts[round];
   if ((int)blockIdx.x >= count) return;
   const int32_t* list = d.list + (size_t)(round & 1) * d.window;
   uint32_t pipe_it = 0;
@@ -276,34 +302,30 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
   }
 }
 
-
-// The tail of a fit - fewer live slots than CTAs - and every small fit (a single curve through the drop-in class is six tasks): one
-// launch in which CTA b owns slot list[b] and alternates evaluation (all warps) and optimiser step (thread 0) until the slot runs
-// dry.  No rounds, no host round trips: a tail round costs an evaluation plus a step latency instead of two launches and two
-// under-filled kernels.  Same block geometry as fit_eval_kernel, so a run's numbers do not depend on which kernel finished it.
+// The END of a fit: if `round`'s list holds at most `tail_below` live slots (and the fit has not ended yet), they are run to the end
+// here - CTA b takes the slots list[b], list[b + grid], ..., alternating evaluation (all warps) and optimiser step (thread 0) until a
+// slot runs dry - and the fit is marked ended, so that every later round finds nothing to do.  No under-filled rounds, no host round
+// trips.  Same block geometry as fit_eval_kernel, so a run's numbers do not depend on which kernel finished it.  Launched
+//   (i) as the whole fit when it is small (at most one wave of tasks) or its class streams (long curves: one slot per CTA fed by the
+//       task queue),
+//  (ii) every few rounds with tail_below = one wave of CTAs: the device-side switch from rounds to the fused end,
+// (iii) behind the last enqueued round with tail_below = "any": the fit always ends on the device however many rounds it needed.
 template <class Kern, int kPlace>
-__global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, int round) {
+__global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, int round, int tail_below) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int go;
   DevCtx c;
-  if ((int)blockIdx.x >= d.counts[round]) return;
-  const int slot = d.list[(size_t)(round & 1) * d.window + blockIdx.x];
+  // the mark is this launch's own stamp (round + 1): CTAs of this launch that start after block 0 has set it must not mistake it for
+  // an earlier launch's
+  const int seen = *d.ended;
+  const int count = (seen != 0 && seen != round + 1) ? 0 : d.counts[round];
+  if (count > tail_below || (int)blockIdx.x >= count) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(d.ended_mark, round + 1);   // (block 0 always takes part)
   uint32_t pipe_it = 0;
   eval_init<kPlace>(c, smem);
-  for (;;) {
-    const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
-    GpCurveView cv = curve_view(d.tab, cu);
-    double l, g[FG_MAXP];
-    bool ok;
-    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
-    if (threadIdx.x == 0) {
-      for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
-      for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
-      go = advance_slot(d, slot, -l, g) ? 1 : 0;
-      __threadfence_block();
-    }
+  for (int b = blockIdx.x; b < count; b += gridDim.x) {
+    run_slot_to_end<Kern, kPlace>(c, d, d.list[(size_t)(round & 1) * d.window + b], smem, pipe_it, &go);
     __syncthreads();
-    if (!go) break;   // (thread 0 next writes `go` after the barriers of a whole evaluation: no second barrier needed here)
   }
 }
 
@@ -395,7 +417,7 @@ struct GpFamilyOps {
              double* lml, double* grad, double* gA, size_t gA_stride, long long* marks);
   int (*eval_prepare)(int place, size_t smem);
   int (*eval)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
-  int (*tail)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
+  int (*tail)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round, int tail_below);
   int (*predict)(int place, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a);
 };
 
@@ -436,8 +458,8 @@ struct GpFamilyLaunch {
     GP_PLACE_SWITCH(place, { fit_eval_kernel<Kern, kP><<<grid, threads, smem, st>>>(d, round); })
     return 0;
   }
-  static int tail(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round) {
-    GP_PLACE_SWITCH(place, { fit_tail_kernel<Kern, kP><<<grid, threads, smem, st>>>(d, round); })
+  static int tail(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round, int tail_below) {
+    GP_PLACE_SWITCH(place, { fit_tail_kernel<Kern, kP><<<grid, threads, smem, st>>>(d, round, tail_below); })
     return 0;
   }
   static int predict(int place, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a) {

@@ -198,7 +198,7 @@ __global__ void fit_init_kernel(FitDev d) {
 #endif
 __global__ void fit_step_kernel(FitDev d, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.counts[round]) return;
+  if (*d.ended || i >= d.counts[round]) return;
   const int slot = d.list[(size_t)(round & 1) * d.window + i];
   if (advance_slot(d, slot, d.f_out[slot], d.g_out + slot * FG_MAXP)) {
     const int pos = atomicAdd(&d.counts[round + 1], 1);
@@ -589,6 +589,8 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   d.list = at<int32_t>(workspace, w.list);
   d.counts = at<int32_t>(workspace, w.counts);
   d.next_task = at<unsigned long long>(workspace, w.next_task);
+  d.ended = d.counts + w.max_rounds + 1;   // (the last counter is never a round's: rounds end at max_rounds)
+  d.ended_mark = d.counts + w.max_rounds + 1;
   d.run_f = at<double>(workspace, w.run_f);
   d.run_x = at<double>(workspace, w.run_x);
   d.run_nev = at<int32_t>(workspace, w.run_nev);
@@ -607,42 +609,45 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   if (rc) return rc;
 
   const unsigned step_grid = (unsigned)((w.window + GP_STEP_THREADS - 1) / GP_STEP_THREADS);
-  constexpr int kMaxGroup = 16;
-  const bool prof = opt->profile != nullptr && opt->profile_counts_only == 0;   // per-launch CUDA events
+  const bool prof = opt->profile != nullptr && opt->profile_counts_only == 0;   // per-launch CUDA events (opt-in diagnostics)
   int launches = 3;   // prep, init, select
-  std::vector<cudaEvent_t> ev;   // 3 per round when profiling; read back only after the loop so timing does not perturb it
-  int round = 0, group = 4;
-  bool finished = false;
-  // the tail (and every small fit): once the live slots fit one wave of CTAs, one fused launch finishes them (fit_tail_kernel)
+  std::vector<cudaEvent_t> ev;   // 3 per round when profiling; read back only after the last launch so timing does not perturb it
+  int round = 0;
+  bool finished = false;   // false only for the A/B mode that forbids the fused end (FULU_GP_NO_TAIL=1)
   const bool use_tail = getenv("FULU_GP_NO_TAIL") == nullptr;
-  cudaEvent_t tail_ev[2] = {nullptr, nullptr};   // profiling: the fused launch counts as evaluation time (its optimiser steps are inside)
-  const bool streamed = w.stream_tail && getenv("FULU_GP_NO_TAIL") == nullptr;
-  if ((use_tail && d.n_tasks <= (int64_t)w.grid_eval) || streamed) {
-    const unsigned ctas = (unsigned)(d.n_tasks < (int64_t)w.window ? d.n_tasks : (int64_t)w.window);   // fit_init_kernel filled that many slots at most
+  const bool streamed = w.stream_tail && use_tail;
+  std::vector<cudaEvent_t> tev;   // profiling: two events per fused launch (its time counts as evaluation time: the steps are inside)
+  auto launch_tail = [&](unsigned ctas, int at_round, int tail_below) -> int {
     if (prof) {
-      for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreate(&tail_ev[i]));
-      cudaEventRecord(tail_ev[0], st);
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); tev.push_back(e); }
+      cudaEventRecord(tev[tev.size() - 2], st);
     }
-    ops->tail(w.place, ctas, w.threads_eval, w.smem_eval, st, d, 0);
-    if (prof) cudaEventRecord(tail_ev[1], st);
+    ops->tail(w.place, ctas, w.threads_eval, w.smem_eval, st, d, at_round, tail_below);
+    if (prof) cudaEventRecord(tev[tev.size() - 1], st);
     CU_TRY(cudaGetLastError());
-    finished = true;
     ++launches;
-  }
-  // Rounds are launched in groups, and one group is always queued ahead of the one whose live-slot count the host is waiting for
-  // (the count is read on a second stream behind an event), so the GPU never waits for the host between groups: a late host
-  // thread costs nothing, an early finish costs at most one group of empty launches.
-  cudaStream_t cs = nullptr;
-  cudaEvent_t mark[2] = {nullptr, nullptr};
-  int mark_round[2] = {0, 0};
-  if (!finished) {
-    CU_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreateWithFlags(&mark[i], cudaEventDisableTiming));
-  }
-  auto launch_group = [&](int which) -> int {
-    int upto = round + group;
-    if (upto > w.max_rounds) upto = w.max_rounds;
-    for (; round < upto; ++round) {
+    return 0;
+  };
+  constexpr int kAny = 0x7fffffff;
+  if ((use_tail && d.n_tasks <= (int64_t)w.grid_eval) || streamed) {
+    // a small fit (every task has a CTA of its own) or a streaming class: ONE launch, CTA b owns slot b
+    const unsigned ctas = (unsigned)(d.n_tasks < (int64_t)w.window ? d.n_tasks : (int64_t)w.window);   // fit_init_kernel filled that many slots at most
+    if ((rc = launch_tail(ctas, 0, kAny))) return rc;
+    finished = true;
+  } else {
+    // Rounds of two launches (evaluate every live slot; step every live slot), enqueued WITHOUT the host ever looking at the device:
+    // the call is stream-ordered and returns at once.  How many rounds a fit needs is only known on the device (the longest run of the
+    // batch: ~80-130 evaluations, more when the window is smaller than the task list), so a generous number is enqueued; a round that
+    // finds no live slot costs two empty launches (~2 us each).  Every fourth round is preceded by the fused kernel with "at most one
+    // wave of live slots" as its condition: the first time it holds, that launch finishes the fit and every later round is empty.
+    // Behind the last round one fused launch runs whatever might still be live to the end, so the result never depends on the number
+    // of rounds chosen here.
+    const int64_t waves = (d.n_tasks + w.window - 1) / w.window;
+    int64_t want = use_tail ? 160 + 96 * (waves - 1) : 4096;
+    if (opt->max_rounds > 0 && want > opt->max_rounds) want = opt->max_rounds;
+    if (want > w.max_rounds) want = w.max_rounds;
+    for (; round < (int)want; ++round) {
+      if (use_tail && round > 0 && (round & 3) == 0 && (rc = launch_tail((unsigned)w.grid_eval, round, w.grid_eval))) return rc;
       if (prof) {
         for (int i = 0; i < 3; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); ev.push_back(e); }
         cudaEventRecord(ev[3 * round], st);
@@ -654,60 +659,31 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
       launches += 2;
     }
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaEventRecord(mark[which], st));
-    mark_round[which] = round;
-    return 0;
-  };
-  int cur = 0;
-  if (!finished && (rc = launch_group(cur))) return rc;
-  while (!finished) {
-    const bool more = round < w.max_rounds;
-    if (more && (rc = launch_group(cur ^ 1))) return rc;   // the next group is queued before the host waits
-    int32_t remaining = 0;
-    CU_TRY(cudaStreamWaitEvent(cs, mark[cur], 0));
-    CU_TRY(cudaMemcpyAsync(&remaining, d.counts + mark_round[cur], 4, cudaMemcpyDeviceToHost, cs));
-    CU_TRY(cudaStreamSynchronize(cs));
-    if (remaining == 0) { finished = true; break; }
-    if (use_tail && remaining <= w.grid_eval) {   // (the count can only have gone down since: an upper bound on the CTAs needed)
-      if (prof) {
-        for (int i = 0; i < 2; ++i) CU_TRY(cudaEventCreate(&tail_ev[i]));
-        cudaEventRecord(tail_ev[0], st);
-      }
-      ops->tail(w.place, (unsigned)remaining, w.threads_eval, w.smem_eval, st, d, round);
-      if (prof) cudaEventRecord(tail_ev[1], st);
-      CU_TRY(cudaGetLastError());
+    if (use_tail && opt->max_rounds <= 0) {
+      if ((rc = launch_tail((unsigned)w.grid_eval, round, kAny))) return rc;
       finished = true;
-      ++launches;
-      break;
     }
-    if (!more) break;   // round cap reached with live slots: flushed below
-    if (remaining < 8 * w.grid_eval) group = 4;   // close to the tail: look more often
-    else if (group < kMaxGroup) group *= 2;
-    cur ^= 1;
-  }
-  if (cs) {
-    cudaStreamDestroy(cs);
-    for (int i = 0; i < 2; ++i) cudaEventDestroy(mark[i]);
   }
   if (opt->profile != nullptr) {
     double eval_ms = 0.0, step_ms = 0.0, tail_ms = 0.0;
     if (prof) {
       for (int r = 0; r < round; ++r) {
         float a = 0.f, b = 0.f;
+        cudaEventSynchronize(ev[3 * r + 2]);
         cudaEventElapsedTime(&a, ev[3 * r], ev[3 * r + 1]);
         cudaEventElapsedTime(&b, ev[3 * r + 1], ev[3 * r + 2]);
         eval_ms += a;
         step_ms += b;
       }
       for (cudaEvent_t e : ev) cudaEventDestroy(e);
-      if (tail_ev[0] != nullptr) {
+      for (size_t i = 0; i + 1 < tev.size(); i += 2) {
         float a = 0.f;
-        cudaEventSynchronize(tail_ev[1]);
-        cudaEventElapsedTime(&a, tail_ev[0], tail_ev[1]);
+        cudaEventSynchronize(tev[i + 1]);
+        cudaEventElapsedTime(&a, tev[i], tev[i + 1]);
         eval_ms += a;
-        tail_ms = a;
-        for (int i = 0; i < 2; ++i) cudaEventDestroy(tail_ev[i]);
+        tail_ms += a;
       }
+      for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     double* pr = opt->profile;
     pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = launches + (finished ? 0 : 1); pr[4] = w.window; pr[5] = w.grid_eval;

@@ -11,8 +11,9 @@
  * Conventions
  *   - every pointer in fulu_gp_batch and every in/out array is a DEVICE pointer owned by the caller
  *     (PyTorch tensors); the library allocates nothing and keeps no global state;
- *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), except
- *     fulu_gp_fit_batch which returns after the optimisation loop has finished on the device (see there);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never looks at the device: fulu_gp_fit_batch too
+ *     enqueues its whole optimisation loop and returns (the loop's length is decided on the device, see there); no call creates a
+ *     stream or an event, except fulu_gp_fit_batch's opt-in per-launch timing (fit options `profile`), which also waits for them;
  *   - return value: 0 ok, <0 argument error (FULU_GP_E_*), >0 a cudaError_t;
  *   - per-curve problems never fail the call: they are reported in status[] (FULU_GP_STATUS_* bits).
  *   - batches are ragged CSR: curve i owns observations offsets[i] .. offsets[i+1]-1.
@@ -99,7 +100,8 @@ typedef struct fulu_gp_fit_options {
   int32_t window;            /* optimiser instances resident at once (0 = default: one per task up to 65,536; for curves whose matrix
                                 lives in global memory with one CTA per SM, n_max >= 512, one per CTA - the fit then runs in one fused launch
                                 whose CTAs pull the next run as soon as theirs ends; results do not depend on the window) */
-  int32_t max_rounds;        /* hard cap on evaluation rounds (0 = default) */
+  int32_t max_rounds;        /* 0 (default): the fit always runs to the end on the device.  > 0: hard cap on evaluation rounds - runs still alive
+                                after that many rounds are recorded where they stand, flagged FULU_GP_STATUS_NOT_CONVERGED */
   int32_t starts_per_curve;  /* 0: theta_starts is [S,P], shared by all curves (sklearn's restarts); 1: [B,S,P], indexed by curve id
                                 (e.g. S = 1 continuation runs from each curve's current optimum) */
   int32_t profile_counts_only; /* with `profile`: fill only the counts ([0], [3]..[9]) - no per-launch events, same launches as an
@@ -133,6 +135,11 @@ int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double
 /* Hyperparameter optimisation: S bound-constrained L-BFGS-B runs per curve from theta_starts [S,P], best LML wins.
  * Replaces GaussianProcessRegressor.fit's optimiser loop (_gpr.py:299-340,658-668).
  * theta_starts is read in place (see starts_per_curve); points outside the bounds are clipped (_lbfgsb_py.py:359).
+ * Stream-ordered: rounds of two launches (evaluate every live run's objective; advance every live run's optimiser) are enqueued ahead
+ * of time - ~160 for a batch whose runs all fit the window - and a round that finds nothing left to do costs two empty launches; the
+ * round that finds at most one wave of live runs finishes them in place, and one fused launch behind the last round runs whatever
+ * might still be alive to the end, so the outputs never depend on how many rounds were enqueued.  Small fits and the long-curve
+ * classes are a single fused launch.
  * theta_opt [B,P], lml_opt [B], n_eval [B] (LML+gradient evaluations spent on the curve), status [B] out.
  * scaler [B,4] = (t mean, t scale, loglam mean, loglam scale) and ynorm [B,2] = (flux mean, flux std) out (may be NULL): the fitted
  * StandardScaler (fulu/gp_aug.py:65-66) and sklearn's y normalisation (_gpr.py:275-280), i.e. aug.ss and reg._y_train_mean/_std.

@@ -161,6 +161,15 @@ def main():
             run_case(cls, f"fam_{kn}_ztf_{i}", p2z, t, f, e, bd, use_err=False, n_obs=128, kernel=kn)
         if "--families-only" in sys.argv:
             return
+    if "--flagged" in sys.argv or "--flagged-only" in sys.argv:
+        # BASELINE config #4: the five curves of the 1,000,000-curve run (scripts/ztf_flagged_scan.py, profiles/r02_ztf_flagged.json) whose
+        # best optimiser run ended abnormally on the GPU (status NOT_CONVERGED): what does the reference do on them?
+        p2z = {i: float(np.log10(v)) for i, v in enumerate(datasets.ZTF_LAMBDA)}
+        for idx in (311605, 380955, 945035, 947043, 982192):
+            t, f, e, bd = datasets.ztf_like(1, first=idx).curve(0)
+            run_case(cls, f"ztf_flagged_{idx}", p2z, t, f, e, bd, use_err=False, n_obs=128)
+        if "--flagged-only" in sys.argv:
+            return
     if "--ddf" in sys.argv or "--ddf-only" in sys.argv:
         # BASELINE config #5: one long LSST-DDF-like curve each at N = 1024 and N = 1536 (minutes of CPU per fit); the full-fit parity
         # of the long-curve path is pinned against these (tests/test_gpu_parity.py)

@@ -18,7 +18,7 @@ def _prep(g):
 
 def test_closed_form_scaler_and_norm(golden):
     _, gp = _prep(golden)
-    assert relerr(gp.x_mean, golden["x_mean"]) < 1e-15
+    assert relerr(gp.x_mean, golden["x_mean"]) < 4e-15   # (a few ulp: the summation order of a mean over ~300 values)
     assert relerr(gp.x_scale, golden["x_scale"]) < 1e-13
     assert abs(gp.y_mean - golden["y_mean"]) <= 1e-15 * abs(golden["y_mean"])
     assert abs(gp.y_std - golden["y_std"]) <= 1e-14 * abs(golden["y_std"])
