@@ -55,7 +55,8 @@ class CurveBatch:
         lens = self.lengths()[idx]
         offs = np.zeros(len(idx) + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
-        gather = np.concatenate([np.arange(self.offsets[i], self.offsets[i + 1]) for i in idx]) if len(idx) else np.zeros(0, np.int64)
+        # source position of every gathered observation, without a Python loop over the curves (a shard of 10^5 curves is taken per call)
+        gather = np.repeat(self.offsets[idx] - offs[:-1], lens) + np.arange(offs[-1], dtype=np.int64) if len(idx) else np.zeros(0, np.int64)
         return CurveBatch(offs, self.t[gather], self.flux[gather], self.flux_err[gather], self.band[gather], self.loglam)
 
     @staticmethod

@@ -137,13 +137,14 @@ def gather_fields(local, parts, n_total, dst=0):
 
 
 def fit_augment_sharded(curves, n_obs=128, dst=0, fit_fn=None, t_min=None, t_max=None, use_err=False, spec=None, engine=None, device=None,
-                        window=0, reduce=None):
+                        window=0, reduce=None, out=None):
     """GP fit + augmentation of a ragged batch over all ranks of the default process group (one process per GPU).
 
     Every rank calls this with the same host batch: the curves are split by the LPT partition on the cubic cost model
     (`lpt_partition`), every rank runs the batched path on its own curves on its own GPU - no collective on the data path - and the
     results are gathered ONCE at the end onto rank `dst` (`gather_fields`: device tensors over NCCL), in the original curve order,
     and copied to the host there.  Per-curve arguments (`t_min`, `t_max`, length n_curves) are restricted to each rank's curves.
+    `out` (on `dst`): pinned result buffers (engine.pin_results for the whole batch) - the returned arrays are then views of them.
     Returns an AugmentResult on `dst` (with `lpt_imbalance` = largest / mean modelled load), None elsewhere.
     `fit_fn(batch, n_obs=...)` (tests) replaces the GPU work by a host function returning an AugmentResult."""
     import torch.distributed as dist
@@ -197,7 +198,18 @@ def fit_augment_sharded(curves, n_obs=128, dst=0, fit_fn=None, t_min=None, t_max
     full = gather_fields(local, parts, curves.n_curves, dst=dst)
     if rank != dst:
         return None
-    host = {k: v.cpu().numpy() for k, v in full.items()}
+    names = {"flux_aug": "mean", "flux_err_aug": "std"}
+    if out is not None and all(names.get(k, k) in out for k in full):
+        host = {}
+        for k, v in full.items():
+            dstbuf = out[names.get(k, k)][: curves.n_curves]
+            dstbuf.copy_(v, non_blocking=True)
+            host[k] = dstbuf
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        host = {k: v.numpy() for k, v in host.items()}
+    else:
+        host = {k: v.cpu().numpy() for k, v in full.items()}
     theta = host["theta"] if perm_theta is None else perm_theta.to_sklearn(host["theta"])
     out = AugmentResult(host.get("flux_aug"), host.get("flux_err_aug"), theta, host["lml"], host["n_eval"], host["status"])
     if reduce == "peak":
