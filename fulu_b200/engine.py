@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -285,6 +286,8 @@ class GPEngine:
         self.lib = _capi.load()
         self.device = _require_cuda(device)
         self._ws = None
+        self.lane = 0       # which cached workspace (and side stream) the next call uses
+        self._streams = {}
         self.launches = 0  # kernels this engine has launched through the library (the library reports a fit's count; the other calls are fixed)
 
     # ---- plumbing
@@ -292,12 +295,24 @@ class GPEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _workspace(self, batch, n_params, n_starts, window):
+        """The device workspace of a call, cached per lane (`self.lane`: calls that may run concurrently on different streams -
+        the length classes of fit_augment_device - must not share one)."""
         need = ctypes.c_size_t()
         _capi.check(self.lib.fulu_gp_workspace_bytes(ctypes.byref(batch.c), n_params, n_starts, window, ctypes.byref(need)))
-        if self._ws is None or self._ws.numel() < need.value:
-            self._ws = None
-            self._ws = torch.empty(int(need.value * 1.1) + 4096, dtype=torch.uint8, device=self.device)
-        return self._ws
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(self.lane)
+        if ws is None or ws.numel() < need.value:
+            self._ws[self.lane] = None
+            ws = self._ws[self.lane] = torch.empty(int(need.value * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def side_stream(self, lane):
+        """A CUDA stream per lane (created once, reused): the library is stream-ordered, so independent calls overlap on the GPU."""
+        st = self._streams.get(lane)
+        if st is None:
+            st = self._streams[lane] = torch.cuda.Stream(device=self.device)
+        return st
 
     @staticmethod
     def _p(x):
@@ -600,18 +615,35 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
     fit = dict(theta=new(B, P), lml=new(B), n_eval=new(B, dtype=torch.int32), status=new(B, dtype=torch.int32))
     pred = dict(mean=new(B, nb, n_obs), std=new(B, nb, n_obs), lml=new(B), status=new(B, dtype=torch.int32))
     profiles = []
-    for bound, idx in reversed(groups):   # longest curves first
+    # Every class is a stream-ordered sequence of launches (fit, then prediction) that ends in a tail - the last, longest optimiser
+    # runs on a few CTAs.  The classes therefore go to streams of their own, longest curves first: the tail of one class runs under
+    # the bulk of the next instead of leaving the GPU idle.  (With per-launch timing on, one class at a time on the caller's stream.)
+    concurrent = (profile is not True) and len(groups) > 1 and os.environ.get("FULU_GP_SERIAL_CLASSES") is None
+    main = torch.cuda.current_stream(engine.device)
+    used = []
+    for lane, (bound, idx) in enumerate(reversed(groups)):   # longest curves first
         order = None
         if not single or lengths.min() != lengths.max():
             # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
             order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
-        sub = db.select(order, n_max=bound)
-        with _nvtx(f"fulu_gp.fit n<={bound} x{len(idx)}"):
-            f = engine.fit(sub, spec, window=window, out=fit, profile=profile)
-        with _nvtx(f"fulu_gp.predict n<={bound} x{len(idx)}"):
-            engine.predict_grid(sub, fit["theta"], n_obs, t_min, t_max, out=pred)
+        if concurrent:
+            st = engine.side_stream(lane)
+            st.wait_stream(main)
+            engine.lane = lane
+            used.append(st)
+        else:
+            st = main
+        with torch.cuda.stream(st):
+            sub = db.select(order, n_max=bound)   # (the index list is uploaded on the class's own stream)
+            with _nvtx(f"fulu_gp.fit n<={bound} x{len(idx)}"):
+                f = engine.fit(sub, spec, window=window, out=fit, profile=profile)
+            with _nvtx(f"fulu_gp.predict n<={bound} x{len(idx)}"):
+                engine.predict_grid(sub, fit["theta"], n_obs, t_min, t_max, out=pred)
         if profile:
             profiles.append(dict(f["profile"], bound=bound, curves=len(idx)))
+    engine.lane = 0
+    for st in used:
+        main.wait_stream(st)
     out = dict(mean=pred["mean"], std=pred["std"], theta=fit["theta"], lml=fit["lml"], n_eval=fit["n_eval"], status=fit["status"] | pred["status"])
     if profile:
         out["profile"] = profiles

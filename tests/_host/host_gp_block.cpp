@@ -1,6 +1,7 @@
 // TEST HARNESS ONLY: runs fulu_b200/csrc/gp_block.cuh (the code a CUDA thread block executes) on host threads.  A block barrier
 // stands in for __syncthreads, a per-warp barrier for __syncwarp, and the warp-collective DMMA / shuffle instructions are
 // emulated through a per-warp scratch area, so the block algorithm can be checked against the oracle without a GPU.
+#include <atomic>
 #include <barrier>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +13,9 @@
 
 #include "../../fulu_b200/csrc/gp_block.cuh"
 #include "../../fulu_b200/csrc/gp_tiled.cuh"
+
+static std::atomic<long long> g_mma_count{0};   // DMMA instructions issued (one per warp-wide call), for work accounting
+extern "C" long long host_gp_mma_count() { return g_mma_count.exchange(0); }
 
 struct WarpShared {
   std::barrier<> bar{32};
@@ -42,6 +46,7 @@ struct HostCtx {
   void warp_sync() { ws->bar.arrive_and_wait(); }
   // D = A(8x4, row) * B(4x8, col) + C; lane (g,t): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
   void mma(double& c0, double& c1, double a, double b) {
+    if (lane == 0) g_mma_count.fetch_add(1, std::memory_order_relaxed);
     ws->a[lane] = a;
     ws->b[lane] = b;
     ws->bar.arrive_and_wait();
