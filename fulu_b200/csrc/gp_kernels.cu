@@ -64,10 +64,15 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.globalA = full > kMaxSmem;
   // Residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation of a curve that fits shared memory is latency
   // bound, so as many curves per SM as fit, and the 512 threads the register file allows are split between them.
-  // Longer curves (matrix in a global slab, streamed through shared-memory stages - gp_tiled.cuh): two 256-thread CTAs per SM up to
-  // np = 512 (the serial 64 x 64 diagonal blocks of one overlap the streamed products of the other), one 512-thread CTA above.
+  // Longer curves keep the matrix in a per-CTA slab in global memory: up to N = 303 two 256-thread CTAs per SM run the 8x8 block code
+  // on it (the slabs of a wave stay in L2), above that one 512-thread CTA per SM streams it through shared-memory stages (gp_tiled.cuh).
   int occ;
-  w.place = !w.globalA ? GP_PLACE_SMEM : (np <= 512 ? GP_PLACE_SLAB : GP_PLACE_TILED);
+  // Boundary between the slab and the tiled placement, measured on B200 with 296 evaluations in flight (algorithmic TFLOP/s, slab /
+  // tiled): N = 240: 7.9 / 6.1, 300: 10.3 / 8.2, 400: 8.2 / 10.9, 500: 6.9 / 14.5 - the class N <= 303 (config #4's longest) stays on
+  // the slab, everything above streams.  (FULU_GP_TILED_ABOVE=<np>: A/B switch.)
+  const char* tiled_above = getenv("FULU_GP_TILED_ABOVE");
+  const size_t np_slab_max = tiled_above ? (size_t)atoi(tiled_above) : 304;
+  w.place = !w.globalA ? GP_PLACE_SMEM : (np <= np_slab_max ? GP_PLACE_SLAB : GP_PLACE_TILED);
   if (w.place == GP_PLACE_TILED) {
     occ = 1;
     w.smem_eval = gp_tiled_smem_doubles<TiledCfg>(nmax, kEvalMaxThreads / 32) * sizeof(double) + 16;

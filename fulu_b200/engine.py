@@ -245,7 +245,7 @@ class DeviceBatch:
         sub = DeviceBatch(self.offsets, self.t, self.flux, self.flux_err, self.band, self.loglam, self.n_max if n_max is None else n_max,
                           self.use_err, self.alpha0, self.family)
         if order is not None:
-            sub.order = torch.as_tensor(order, dtype=torch.int32).to(self.device).contiguous()
+            sub.order = (order if torch.is_tensor(order) else torch.as_tensor(order, dtype=torch.int32)).to(self.device, torch.int32).contiguous()
             sub.c.order, sub.c.n_order = sub.order.data_ptr(), int(sub.order.numel())
         return sub
 
@@ -480,8 +480,9 @@ class GPEngine:
     def ingest_table(self, object_id, t, flux, flux_err, passband, passband2lam, use_err=False, family=KERNEL_RBF_WHITE):
         """A survey table grouped by object (columns as in notebook_examples/object_34299.csv plus an object id) -> a DeviceBatch,
         built on the device: CSR offsets from the id column, band indices through a lookup table of the (integer) passband ids
-        (fulu/_base_aug.py:9-11).  The t / flux / flux_err columns are used where they lie.  Returns (batch, lengths, object_ids):
-        lengths (host int64 [B]) for the length-class launches, object_ids (host) = the id of each curve.
+        (fulu/_base_aug.py:9-11).  The t / flux / flux_err columns are used where they lie.  Returns (batch, None, object_ids):
+        the lengths are not read back (None tells fit_augment_device to build the length classes on the device),
+        object_ids (host) = the id of each curve.
         Raises KeyError for a passband that is not in passband2lam, like the reference."""
         with torch.cuda.device(self.device):
             dev = self.device
@@ -511,11 +512,12 @@ class GPEngine:
                 bad = pb[band < 0][0].item()
                 raise KeyError(bad)
             offsets = offsets[: B + 1].contiguous()
-            off_h = offsets.cpu().numpy()
-            lengths = np.diff(off_h)
             ids = oid[offsets[:-1]].cpu().numpy() if B else np.zeros(0, np.int64)
-            batch = DeviceBatch(offsets, cols[0], cols[1], cols[2], band, loglam, int(lengths.max()) if B else 0, use_err, family=family)
-            return batch, lengths, ids
+            # the offsets stay on the device: fit_augment_device builds the length classes and their index lists there
+            # (class_orders_device); n_max of the batch itself = its longest curve, one integer
+            n_max = int((offsets[1:] - offsets[:-1]).max().item()) if B else 0
+            batch = DeviceBatch(offsets, cols[0], cols[1], cols[2], band, loglam, n_max, use_err, family=family)
+            return batch, None, ids
 
     def fp64_peak(self, mode=0, iters=20000, reps=4):
         """Measured FP64 TFLOP/s of a register-resident DFMA (mode 0) or DMMA (mode 1) loop on this GPU: the library enqueues
@@ -570,7 +572,7 @@ class AugmentResult:
         return out
 
 
-MERGE_ABOVE = 511     # classes above this bound share one launch geometry (one 512-thread CTA per SM, the matrix in a global slab streamed
+MERGE_ABOVE = 303     # classes above this bound share one launch geometry (one 512-thread CTA per SM, the matrix in a global slab streamed
                       # through shared-memory stages) and are merged into ONE class, run longest curves first: a fit there is one fused
                       # launch fed by a task queue, and every class run on its own would end in its own tail of a few long optimiser runs
 
@@ -593,6 +595,33 @@ def bucket_curves(lengths, buckets=N_BUCKETS):
     return [(b, i) for b, i in out]
 
 
+def class_orders_device(offsets, buckets=N_BUCKETS):
+    """bucket_curves for a batch whose offsets live on the device (an ingested table): the curve ids sorted by (length class,
+    longest first) stay on the device as ONE int32 index array; only the class sizes and the longest length - a dozen integers - come
+    back to the host, which needs them to size the launches.  Returns [(bound, count, order slice)] in ascending bounds, the
+    long-curve classes (bound > MERGE_ABOVE) merged into one, like bucket_curves."""
+    dev = offsets.device
+    lengths = offsets[1:] - offsets[:-1]
+    bounds = torch.tensor(buckets, dtype=torch.int64, device=dev)
+    cls = torch.bucketize(lengths, bounds, right=False)              # first class whose bound >= length
+    first_long = int(np.searchsorted(np.asarray(buckets), MERGE_ABOVE, side="right"))
+    grp = torch.clamp(cls, max=first_long)                          # every class above MERGE_ABOVE is one group
+    key = grp * (1 << 32) - lengths                                  # group ascending, longest first inside a group
+    order = torch.argsort(key, stable=True).to(torch.int32)
+    summary = torch.cat([torch.bincount(grp, minlength=first_long + 1), lengths.max().reshape(1) if lengths.numel() else lengths.new_zeros(1)]).cpu().numpy()
+    counts, longest = summary[:-1], int(summary[-1])
+    out, start = [], 0
+    for g, c in enumerate(counts):
+        c = int(c)
+        if c:
+            bound = int(buckets[g]) if g < first_long else max((longest + 8) // 8 * 8 - 1, int(buckets[min(g, len(buckets) - 1)]))
+            if g == first_long:   # the merged long class is bounded by its own longest curve, in 8k - 1 steps like the table
+                bound = next((int(b) for b in buckets if b >= longest), (longest + 8) // 8 * 8 - 1)
+            out.append((bound, c, order[start:start + c]))
+        start += c
+    return out
+
+
 def pin_results(n_curves, n_bands, n_obs, n_params=4):  # n_params: KernelSpec.n_params of the family that will be fitted
     """Pinned host buffers for the results of fit_augment_batch (reusable across calls: what a production loop double-buffers)."""
     mk = lambda *shape, dtype=torch.float64: torch.empty(shape, dtype=dtype, pin_memory=True)
@@ -607,9 +636,14 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
     Returns device tensors dict(mean, std [B,n_bands,n_obs], theta [B,P], lml, n_eval, status [B]) (+ "profile": per-class list)."""
     spec = spec or KernelSpec(db.family)
     db = db.with_family(spec.family)
-    lengths = np.asarray(lengths)
     B, nb, P = db.n_curves, db.n_bands, spec.n_params
-    groups = bucket_curves(lengths)
+    if lengths is None:   # offsets on the device only (an ingested table): classes and index lists are built there
+        groups = [(bound, count, order) for bound, count, order in class_orders_device(db.offsets)]
+        on_device = True
+    else:
+        lengths = np.asarray(lengths)
+        groups = [(bound, len(idx), idx) for bound, idx in bucket_curves(lengths)]
+        on_device = False
     single = len(groups) == 1
     new = engine._new
     fit = dict(theta=new(B, P), lml=new(B), n_eval=new(B, dtype=torch.int32), status=new(B, dtype=torch.int32))
@@ -621,9 +655,11 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
     concurrent = (profile is not True) and len(groups) > 1 and os.environ.get("FULU_GP_SERIAL_CLASSES") is None
     main = torch.cuda.current_stream(engine.device)
     used = []
-    for lane, (bound, idx) in enumerate(reversed(groups)):   # longest curves first
+    for lane, (bound, count, idx) in enumerate(reversed(groups)):   # longest curves first
         order = None
-        if not single or lengths.min() != lengths.max():
+        if on_device:
+            order = idx     # (already longest first, already on the device)
+        elif not single or lengths.min() != lengths.max():
             # within a class, longest first too: the tail of the optimiser's task queue is then made of the cheapest curves
             order = idx[np.argsort(-lengths[idx], kind="stable")].astype(np.int32)
         if concurrent:
@@ -635,12 +671,12 @@ def fit_augment_device(engine: "GPEngine", db: DeviceBatch, lengths, n_obs=128, 
             st = main
         with torch.cuda.stream(st):
             sub = db.select(order, n_max=bound)   # (the index list is uploaded on the class's own stream)
-            with _nvtx(f"fulu_gp.fit n<={bound} x{len(idx)}"):
+            with _nvtx(f"fulu_gp.fit n<={bound} x{count}"):
                 f = engine.fit(sub, spec, window=window, out=fit, profile=profile)
-            with _nvtx(f"fulu_gp.predict n<={bound} x{len(idx)}"):
+            with _nvtx(f"fulu_gp.predict n<={bound} x{count}"):
                 engine.predict_grid(sub, fit["theta"], n_obs, t_min, t_max, out=pred)
         if profile:
-            profiles.append(dict(f["profile"], bound=bound, curves=len(idx)))
+            profiles.append(dict(f["profile"], bound=bound, curves=count))
     engine.lane = 0
     for st in used:
         main.wait_stream(st)

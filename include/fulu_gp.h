@@ -98,7 +98,7 @@ typedef struct fulu_gp_fit_options {
   int32_t maxfun;            /* 15000 */
   int32_t maxls;             /* 20 */
   int32_t window;            /* optimiser instances resident at once (0 = default: one per task up to 65,536; for curves whose matrix
-                                lives in global memory with one CTA per SM, n_max >= 512, one per CTA - the fit then runs in one fused launch
+                                streams from global memory with one CTA per SM, n_max >= 304, one per CTA - the fit then runs in one fused launch
                                 whose CTAs pull the next run as soon as theirs ends; results do not depend on the window) */
   int32_t max_rounds;        /* 0 (default): the fit always runs to the end on the device.  > 0: hard cap on evaluation rounds - runs still alive
                                 after that many rounds are recorded where they stand, flagged FULU_GP_STATUS_NOT_CONVERGED */

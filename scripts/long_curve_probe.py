@@ -12,7 +12,7 @@ from fulu_b200 import DeviceBatch, GPEngine, datasets  # noqa: E402
 
 eng = GPEngine()
 for n in [int(a) for a in sys.argv[1:]] or [1024, 2048]:
-    hb = datasets.ddf_like(148, n_points=n)
+    hb = datasets.ddf_like(int(os.environ.get("PROBE_CURVES", "148")), n_points=n)
     db = DeviceBatch.from_host(hb, eng.device)
     theta = torch.zeros(hb.n_curves, 4, dtype=torch.float64, device=eng.device)
     theta[:, 3] = -2.0
@@ -25,5 +25,5 @@ for n in [int(a) for a in sys.argv[1:]] or [1024, 2048]:
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1])
     flops = hb.n_curves * (float(n) ** 3 + 12.0 * n * n)
-    print(f"N={n}: 148 evaluations (one per CTA) in {ms:.2f} ms incl. prep = {flops / ms / 1e9:.2f} TFLOP/s algorithmic; "
+    print(f"N={n}: {hb.n_curves} evaluations (one per CTA per wave) in {ms:.2f} ms incl. prep = {flops / ms / 1e9:.2f} TFLOP/s algorithmic; "
           f"lml[0]={float(out['lml'][0]):.6f} finite={bool(torch.isfinite(out['lml']).all())}", flush=True)

@@ -255,7 +255,7 @@ def test_config5_fit_reaches_oracle_lml(engine):
 
 
 def test_long_curve_fit_streams_runs_through_one_launch(engine, monkeypatch):
-    """Curves whose matrix lives in global memory with one CTA per SM (n_max >= 512): by default the fit runs in one fused launch
+    """Curves whose matrix lives in global memory with one CTA per SM (n_max >= 304): by default the fit runs in one fused launch
     whose CTAs pull the next (curve, start) run as soon as theirs ends (window = CTAs < tasks).  Same runs, same numbers as on
     rounds of two launches (FULU_GP_NO_TAIL=1), bit for bit; mixed lengths, more tasks than CTAs, one unusable curve in the queue."""
     from fulu_b200 import CurveBatch, DeviceBatch, datasets

@@ -35,7 +35,15 @@ def test_ingest_matches_numpy_groupby(engine):
     off_ref, ids_ref = O.table_to_csr(oid)
     np.testing.assert_array_equal(batch.offsets.cpu().numpy(), off_ref)
     np.testing.assert_array_equal(got_ids, ids_ref)
-    np.testing.assert_array_equal(lengths, hb.lengths())
+    assert lengths is None       # not read back: the length classes are built on the device (engine.class_orders_device)
+    from fulu_b200.engine import bucket_curves, class_orders_device
+
+    dev_classes = class_orders_device(batch.offsets)
+    ref_classes = bucket_curves(hb.lengths())
+    assert [(b_, c_) for b_, c_, _ in dev_classes] == [(b_, len(i_)) for b_, i_ in ref_classes]
+    for (_, _, order), (_, idx) in zip(dev_classes, ref_classes):
+        o = order.cpu().numpy()
+        assert sorted(o.tolist()) == sorted(idx.tolist()) and np.all(np.diff(hb.lengths()[o]) <= 0)    # same curves, longest first
     np.testing.assert_array_equal(batch.band.cpu().numpy(), hb.band)
     assert batch.n_curves == hb.n_curves and batch.n_max == int(hb.lengths().max())
     # sizes around the chunk size, a single object, a single row, an empty table
