@@ -66,6 +66,8 @@ struct DevCtx {
       }
     }
   }
+  // (the producer's wait for a stage to be released; a name of its own so that the host harness can drop it in its self-test)
+  __device__ __forceinline__ void mbar_wait_reuse(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
   // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the barrier
   __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),

@@ -149,7 +149,7 @@ GP_DEV void gp_stream_issue(Ctx& c, GpTiled& g, const GpStreamJob& job, int chun
   const int BM = c.nwarp * Cfg::RW, NS = g.ns;
   const uint32_t st = it % NS, use = it / NS;
   uint64_t* full = gp_bar_full(g, st);
-  if (use > 0) c.mbar_wait(gp_bar_empty(g, st), (use - 1) & 1);   // every warp has released the previous contents of this stage
+  if (use > 0) c.mbar_wait_reuse(gp_bar_empty(g, st), (use - 1) & 1);   // every warp has released the previous contents of this stage
   double* dst = g.stage + (size_t)st * gp_tiled_stage_doubles<Cfg>(c.nwarp);
   const int kc = job.k0 + chunk * KC;
   const int kn = (job.k1 - kc < KC) ? job.k1 - kc : KC;

@@ -20,7 +20,7 @@ def contiguous_shard(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def lpt_partition(lengths, world, n_eval=135, m=768, exact_below=4096):
+def lpt_partition(lengths, world, n_eval=135, m=768, exact_below=1024):
     """Longest-processing-time partition of ragged curves over `world` GPUs; returns one sorted index array per rank.
 
     Curves in decreasing cost order; the greedy rule (next curve to the least loaded rank) is applied one by one to the last

@@ -97,11 +97,29 @@ struct HostCtx {
   void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { mb_update(mb(bar), (uint64_t)bytes - (1ull << 48)); }
   void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     if (bytes == 0 || (bytes & 15) || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) abort();
+#ifdef SAN_SKIP_SYNC
+    if (late_bar != nullptr) {
+      std::memcpy(dst, src, bytes);   // too early: the slower warps may still be reading this stage
+      mbar_wait(late_bar, late_parity);
+      late_bar = nullptr;
+    }
+#endif
     std::memcpy(dst, src, bytes);
     mb_update(mb(bar), (uint64_t)0 - (uint64_t)bytes);
   }
   void mbar_wait(uint64_t* bar, uint32_t parity) {
     while ((mb(bar)->phase.load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
+  }
+#ifdef SAN_SKIP_SYNC   // self-test of the sanitizer run: the producer writes into a stage BEFORE waiting for its release (the wait
+  uint64_t* late_bar = nullptr;   // itself still happens, right after that premature write, so the barriers' phases stay in step)
+  uint32_t late_parity = 0;
+#endif
+  void mbar_wait_reuse(uint64_t* bar, uint32_t parity) {
+#ifdef SAN_SKIP_SYNC
+    static const bool skip = getenv("SAN_SKIP_REUSE_WAIT") != nullptr;
+    if (skip) { late_bar = bar; late_parity = parity; return; }
+#endif
+    mbar_wait(bar, parity);
   }
   void fence_async() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 };

@@ -177,6 +177,42 @@ def test_batched_entry_point_against_live_sklearn(engine, kname):
     assert np.count_nonzero(deficits2 > 1e-6) <= np.count_nonzero(deficits > 1e-6)
 
 
+@pytest.mark.parametrize("kname,n", [("rbf_matern", 400), ("notebook", 330), ("rbf_rq", 520)])
+def test_families_on_the_tiled_long_curve_path(engine, kname, n):
+    """The non-default kernels where the matrix is streamed from a global slab (N >= 304, gp_tiled.cuh): K and dK/dtheta are
+    assembled / recomputed inside the streamed products' epilogues there.  LML, gradient, mean and std at fixed hyperparameters
+    against the closed-form oracle, and against live sklearn with the same kernel object."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+
+    from fulu_b200 import DeviceBatch, datasets
+    from fulu_b200.engine import kernel_spec_from_sklearn
+    from oracle import gp_oracle as O
+
+    spec = kernel_spec_from_sklearn(family_kernel(kname))
+    hb = datasets.ddf_like(2, n_points=n, first=31)
+    db = DeviceBatch.from_host(hb, engine.device, family=spec.family)
+    assert db.n_max >= 304
+    rng = np.random.default_rng(n)
+    th = rng.uniform(-1.0, 1.0, (2, spec.n_params))
+    th[:, -1] = -3.0
+    out = engine.lml(db, torch.tensor(th))
+    pred = engine.predict_grid(db, torch.tensor(th), 16)
+    p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
+    for i in range(2):
+        t, f, e, b = hb.curve(i)
+        gp = O.ClosedFormGP(p2l, kind=spec.family).prepare(t, f, e, b)
+        l, g, gs = O.lml_and_grad(gp.X, gp.y, gp.alpha, th[i], spec.family, return_scale=True)
+        assert abs(float(out["lml"][i]) - l) <= 1e-9 * max(1.0, abs(l)), (kname, i)
+        assert np.max(np.abs(out["grad"][i].cpu().numpy() - g) / np.maximum(np.maximum(np.abs(g), 1e-1 * gs), 1e-30)) < 1e-9, (kname, i)
+        X = (np.c_[t, hb.loglam[b]] - gp.x_mean) / gp.x_scale
+        reg = GaussianProcessRegressor(kernel=family_kernel(kname).clone_with_theta(spec.to_sklearn(th[i])), optimizer=None, normalize_y=True).fit(X, f)
+        assert abs(reg.log_marginal_likelihood_value_ - float(out["lml"][i])) <= 1e-9 * max(1.0, abs(l))
+        tq = np.tile(np.linspace(t.min(), t.max(), 16), hb.n_bands)
+        fr, er = reg.predict((np.c_[tq, np.repeat(hb.loglam, 16)] - gp.x_mean) / gp.x_scale, return_std=True)
+        assert relerr(pred["mean"][i].cpu().numpy().reshape(-1), fr, floor=1e-3 * gp.y_std) < 1e-9, (kname, i)
+        assert relerr(pred["std"][i].cpu().numpy().reshape(-1), er, floor=1e-6 * gp.y_std) < 1e-9, (kname, i)
+
+
 def test_unsupported_family_and_parameter_count_are_refused(engine):
     from fulu_b200 import CurveBatch, DeviceBatch, _capi
     from fulu_b200.engine import family_code

@@ -14,7 +14,8 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "_host", "sanitize_main.cpp")
-DEPS = [SRC, os.path.join(HERE, "_host", "host_gp_block.cpp"), os.path.join(os.path.dirname(HERE), "fulu_b200", "csrc", "gp_block.cuh")]
+DEPS = [SRC, os.path.join(HERE, "_host", "host_gp_block.cpp"), os.path.join(os.path.dirname(HERE), "fulu_b200", "csrc", "gp_block.cuh"),
+        os.path.join(os.path.dirname(HERE), "fulu_b200", "csrc", "gp_tiled.cuh")]
 BUILD = os.path.join(HERE, "_build")
 FLAGS = {
     "asan": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"],
@@ -33,8 +34,8 @@ def _exe(kind):
     return exe
 
 
-def _run(kind, n, nthr, family, kslab, n_obs=8, env=None):
-    r = subprocess.run([_exe(kind), str(n), str(nthr), str(family), str(kslab), str(n_obs)], capture_output=True, text=True,
+def _run(kind, n, nthr, family, kslab, n_obs=8, env=None, tiled=0):
+    r = subprocess.run([_exe(kind), str(n), str(nthr), str(family), str(kslab), str(n_obs), str(tiled)], capture_output=True, text=True,
                        env=dict(os.environ, **(env or {})), timeout=600)
     return r.returncode, r.stdout + r.stderr
 
@@ -51,6 +52,30 @@ CASES = [(100, 128, 0, 1), (104, 256, 0, 0), (8, 32, 0, 1), (2, 128, 0, 0), (100
 def test_block_code_is_clean(kind, case):
     rc, out = _run(kind, *case)
     assert rc == 0 and "Sanitizer" not in out and "runtime error" not in out, out[-3000:]
+
+
+# the long-curve path (gp_tiled.cuh): (n, threads per block, family): several panels with a narrow last one, a row block with fewer
+# rows than warps, 2 / 4 / 8 warps, the notebook family
+TILED_CASES = [(100, 128, 0), (130, 256, 0), (72, 64, 34)]
+
+
+@pytest.mark.parametrize("kind", ["asan", "tsan"])
+@pytest.mark.parametrize("case", TILED_CASES, ids=lambda c: "n%d_t%d_f%d" % c)
+def test_tiled_path_is_clean(kind, case):
+    """Slab, stages and barriers allocated at exactly their sizes (ASan); the emulated copy engine's writes into a stage against the
+    warps' reads of it, ordered only by the full / empty barriers (TSan)."""
+    n, nthr, fam = case
+    rc, out = _run(kind, n, nthr, fam, 0, tiled=1)
+    assert rc == 0 and "Sanitizer" not in out and "runtime error" not in out, out[-3000:]
+
+
+def test_tsan_reports_a_stage_refilled_before_its_release():
+    """Self-test of the pipeline protocol: with the producer's wait on the stage's `empty` barrier removed, the copy into a stage
+    races with the slower warps still reading it - ThreadSanitizer must say so; with the wait in place it is silent."""
+    rc, out = _run("tsan_skip", 130, 256, 0, 0, env={"SAN_SKIP_REUSE_WAIT": "1", "SAN_SKIP_SYNC": "0"}, tiled=1)
+    assert "ThreadSanitizer: data race" in out
+    rc, out = _run("tsan_skip", 130, 256, 0, 0, env={"SAN_SKIP_SYNC": "0"}, tiled=1)
+    assert rc == 0 and "Sanitizer" not in out, out[-3000:]
 
 
 @pytest.mark.parametrize("dropped", [1, 3, 5])
