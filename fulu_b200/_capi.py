@@ -64,7 +64,7 @@ def load():
     lib.fulu_gp_strerror.argtypes = [ctypes.c_int]
     lib.fulu_gp_workspace_bytes.argtypes = [ctypes.POINTER(Batch), i32, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
     lib.fulu_gp_lml_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
-    lib.fulu_gp_fit_batch.argtypes = [ctypes.POINTER(Batch), ctypes.POINTER(FitOptions), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.fulu_gp_fit_batch.argtypes = [ctypes.POINTER(Batch), ctypes.POINTER(FitOptions), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_predict_grid_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_predict_points_batch.argtypes = [ctypes.POINTER(Batch), i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.fulu_gp_fp64_probe.argtypes = [i32, i32, vp, ctypes.c_size_t, c_double_p, vp]

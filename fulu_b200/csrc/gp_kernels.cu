@@ -233,7 +233,7 @@ struct SelectArgs {
   const int32_t *run_nev, *run_end, *pstatus;
   double lo[FG_MAXP], hi[FG_MAXP];
   double *theta_opt, *lml_opt, *run_lml, *run_theta;
-  int32_t *n_eval, *status;
+  int32_t *n_eval, *status, *run_n_eval;
 };
 
 __global__ void fit_select_kernel(SelectArgs a) {
@@ -247,6 +247,7 @@ __global__ void fit_select_kernel(SelectArgs a) {
     if (f < fb) { fb = f; best = s; }   // np.argmin: first minimum (_gpr.py:336-340)
     nev += a.run_nev[k * a.S + s];
     if (a.run_lml) a.run_lml[cu * a.S + s] = (f < 1.0e99) ? -f : -INFINITY;
+    if (a.run_n_eval) a.run_n_eval[cu * a.S + s] = a.run_nev[k * a.S + s];
     if (a.run_theta)
       for (int q = 0; q < a.P; ++q) a.run_theta[(cu * a.S + s) * a.P + q] = a.run_x[(k * a.S + s) * FG_MAXP + q];
   }
@@ -561,7 +562,7 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
 
 int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,
                       double* lml_opt, double* scaler, double* ynorm, int32_t* n_eval, int32_t* status, double* run_lml, double* run_theta,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      int32_t* run_n_eval, void* workspace, size_t workspace_bytes, void* stream) {
   if (!opt) return FULU_GP_E_BADARG;
   int rc = check_batch(batch, opt->n_params);
   if (rc) return rc;
@@ -702,7 +703,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   sa.B = n_active(*batch); sa.order = batch->order; sa.S = S; sa.P = P;
   sa.run_f = d.run_f; sa.run_x = d.run_x; sa.run_nev = d.run_nev; sa.run_end = d.run_end; sa.pstatus = tab.pstatus;
   for (int k = 0; k < FG_MAXP; ++k) { sa.lo[k] = d.opt.lo[k]; sa.hi[k] = d.opt.hi[k]; }
-  sa.theta_opt = theta_opt; sa.lml_opt = lml_opt; sa.run_lml = run_lml; sa.run_theta = run_theta; sa.n_eval = n_eval; sa.status = status;
+  sa.theta_opt = theta_opt; sa.lml_opt = lml_opt; sa.run_lml = run_lml; sa.run_theta = run_theta; sa.n_eval = n_eval; sa.status = status; sa.run_n_eval = run_n_eval;
   fit_select_kernel<<<(unsigned)((sa.B + 127) / 128), 128, 0, st>>>(sa);
   if (scaler || ynorm) export_stats_kernel<<<(unsigned)((sa.B + 255) / 256), 256, 0, st>>>(sa.B, tab.order, tab.stats, scaler, ynorm);
   CU_TRY(cudaGetLastError());

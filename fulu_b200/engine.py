@@ -382,6 +382,7 @@ class GPEngine:
             if return_runs:
                 out["run_lml"] = self._new(B, S)
                 out["run_theta"] = self._new(B, S, P)
+                out["run_n_eval"] = self._new(B, S, dtype=torch.int32)
             # True: per-launch CUDA events (eval_ms, step_ms); "counts" (and by default, for the launch counter): only rounds / launches /
             # geometry, no events - the same launches as an unprofiled call
             prof = (ctypes.c_double * 12)()
@@ -391,8 +392,8 @@ class GPEngine:
             _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts), self._p(out["theta"]),
                                                    self._p(out["lml"]), self._p(out.get("scaler")), self._p(out.get("ynorm")),
                                                    self._p(out["n_eval"]), self._p(out["status"]),
-                                                   self._p(out.get("run_lml")), self._p(out.get("run_theta")), self._p(ws), ws.numel(),
-                                                   self._stream()))
+                                                   self._p(out.get("run_lml")), self._p(out.get("run_theta")), self._p(out.get("run_n_eval")),
+                                                   self._p(ws), ws.numel(), self._stream()))
             self.launches += int(prof[3])
             if profile:
                 keys = ("rounds", "eval_ms", "step_ms", "launches", "window", "grid_eval", "smem_eval", "global_a", "threads_eval", "ctas_per_sm",
@@ -407,7 +408,7 @@ class GPEngine:
                 o.profile, o.profile_counts_only = ctypes.cast(prof2, ctypes.POINTER(ctypes.c_double)), 1
                 _capi.check(self.lib.fulu_gp_fit_batch(ctypes.byref(batch.c), ctypes.byref(o), self._p(starts2), self._p(cont["theta"]),
                                                        self._p(cont["lml"]), None, None, self._p(cont["n_eval"]), self._p(cont["status"]),
-                                                       None, None, self._p(ws), ws.numel(), self._stream()))
+                                                       None, None, None, self._p(ws), ws.numel(), self._stream()))
                 self.launches += int(prof2[3])
                 better = cont["lml"] > out["lml"]
                 out["theta"].copy_(torch.where(better[:, None], cont["theta"], out["theta"]))

@@ -143,12 +143,12 @@ int fulu_gp_lml_batch(const fulu_gp_batch* batch, int32_t n_params, const double
  * theta_opt [B,P], lml_opt [B], n_eval [B] (LML+gradient evaluations spent on the curve), status [B] out.
  * scaler [B,4] = (t mean, t scale, loglam mean, loglam scale) and ynorm [B,2] = (flux mean, flux std) out (may be NULL): the fitted
  * StandardScaler (fulu/gp_aug.py:65-66) and sklearn's y normalisation (_gpr.py:275-280), i.e. aug.ss and reg._y_train_mean/_std.
- * run_lml [B,S] (final LML of every run) and run_theta [B,S,P] may be NULL.
+ * run_lml [B,S] (final LML of every run), run_theta [B,S,P] and run_n_eval [B,S] (evaluations of every run) may be NULL.
  * A curve whose covariance was never positive definite along its best run gets lml_opt = -inf and FULU_GP_STATUS_NOT_PD
  * (sklearn: log_marginal_likelihood_value_ = -inf, then LinAlgError in fit, _gpr.py:349-361). */
 int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt, const double* theta_starts, double* theta_opt,
                       double* lml_opt, double* scaler, double* ynorm, int32_t* n_eval, int32_t* status, double* run_lml,
-                      double* run_theta, void* workspace, size_t workspace_bytes, void* stream);
+                      double* run_theta, int32_t* run_n_eval, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Augmentation: predictive mean / std on the band-major grid linspace(t_min[i], t_max[i], n_obs) x n_bands.
  * Replaces BaseAugmentation.augmentation -> predict -> reg.predict(return_std=True)

@@ -236,3 +236,44 @@ def test_invariances_at_full_size():
         dn = eng.lml(base, theta - d)["lml"].cpu().numpy()
         fd = (up - dn) / (2 * h)
         np.testing.assert_allclose(a["grad"].cpu().numpy()[:, k], fd, rtol=2e-5, atol=2e-5)
+
+
+def test_more_long_curves_than_sms_in_one_class():
+    """a class of long curves (matrix in a per-CTA global slab) holding more curves than the GPU has SMs.  The
+    prediction kernel runs up to two CTAs per SM, each with a slab of its own: the workspace must hold one slab per CTA that can be at
+    work, whichever kernel asks for more.  2.5 curves per SM of N = 310 (tiled placement) and of N = 250 (slab placement) through the
+    batched entry point: every curve finite, and a sample of them bit-identical to the same curve fitted alone."""
+    import fulu_b200
+    from fulu_b200 import datasets
+
+    eng = fulu_b200.GPEngine()
+    sms = torch.cuda.get_device_properties(eng.device).multi_processor_count
+    for n in (310, 250):
+        hb = datasets.ddf_like(int(2.5 * sms), n_points=n, first=500)
+        res = fulu_b200.fit_augment_batch(hb, n_obs=8, engine=eng)
+        assert np.all(np.isfinite(res.lml)) and np.all(np.isfinite(res.flux_aug)) and np.all(np.isfinite(res.flux_err_aug))
+        assert not np.any(res.status & ~8)
+        for i in (0, sms - 1, sms, 2 * sms + 3, hb.n_curves - 1):
+            one = fulu_b200.fit_augment_batch(hb.slice(i, i + 1), n_obs=8, engine=eng)
+            assert one.lml[0] == res.lml[i] and np.array_equal(one.flux_aug[0], res.flux_aug[i]) and np.array_equal(one.theta[0], res.theta[i]), (n, i)
+
+
+def test_query_band_outside_the_table_is_flagged_not_indexed():
+    """ADVICE r1 (low): fulu_gp_predict_points_batch validates the query bands (the header promises per-curve problems in status[]);
+    an empty curve at the end of the CSR arrays is flagged without its first observation being read."""
+    import fulu_b200
+    from fulu_b200 import CurveBatch, DeviceBatch, datasets
+
+    eng = fulu_b200.GPEngine()
+    hb = datasets.plasticc_like(2, n_points=40, first=9)
+    db = DeviceBatch.from_host(hb, eng.device)
+    theta = torch.zeros(2, 4, dtype=torch.float64)
+    qt = np.array([59010.0, 59020.0, 59030.0, 59040.0])
+    out = eng.predict_points(db, theta, np.array([0, 2, 4], np.int64), qt, np.array([0, 5, 1, 6], np.int32))   # band 6 of 6: out of range
+    st = out["status"].cpu().numpy()
+    assert st[0] == 0 and st[1] & 1
+    assert np.all(np.isfinite(out["mean"].cpu().numpy()[:2]))
+    curves = [hb.curve(0), (np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, np.int32))]          # the last curve is empty
+    db2 = DeviceBatch.from_host(CurveBatch.from_curves(curves, hb.loglam), eng.device, n_max=40)
+    g = eng.predict_grid(db2, theta, 4)
+    assert int(g["status"][0]) == 0 and int(g["status"][1]) & 1 and bool(torch.isnan(g["mean"][1]).all())
