@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#ifdef GP_FUSED_STATS
+#include <stdio.h>
+#endif
 
 #include "../../include/fulu_gp.h"
 #include "gp_block.cuh"
@@ -233,9 +236,25 @@ __device__ __forceinline__ bool acquire_task(const FitDev& d, int slot, FgState&
 #ifndef GP_STEP_LOCAL
 #define GP_STEP_LOCAL 1
 #endif
+// (the state travels as 16-byte words, 23 in flight at a time, in a rolled loop: a member-wise struct copy is ~1,200 instructions in and out)
+static_assert(sizeof(FgState) % (16 * 23) == 0, "FgState is copied as 4 x 23 16-byte words");
+__device__ __forceinline__ void fg_state_copy(FgState* dst, const FgState* src) {
+  double2* o = reinterpret_cast<double2*>(dst);
+  const double2* i = reinterpret_cast<const double2*>(src);
+#pragma unroll 1
+  for (int k0 = 0; k0 < (int)(sizeof(FgState) / 16); k0 += 23) {
+    double2 v[23];
+#pragma unroll
+    for (int k = 0; k < 23; ++k) v[k] = i[k0 + k];
+#pragma unroll
+    for (int k = 0; k < 23; ++k) o[k0 + k] = v[k];
+  }
+}
+
 __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f, const double* g) {
 #if GP_STEP_LOCAL
-  FgState st = d.slots[slot];
+  FgState st;
+  fg_state_copy(&st, &d.slots[slot]);
 #else
   FgState& st = d.slots[slot];
 #endif
@@ -251,7 +270,7 @@ __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f
     live = acquire_task(d, slot, st);
   }
 #if GP_STEP_LOCAL
-  d.slots[slot] = st;
+  fg_state_copy(&d.slots[slot], &st);
 #endif
   return live;
 }
@@ -329,6 +348,226 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, 
     run_slot_to_end<Kern, kPlace>(c, d, d.list[(size_t)(round & 1) * d.window + b], smem, pipe_it, &go);
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------ the fused fit (round 2)
+// ONE persistent CTA per SM runs a whole fit: no rounds, no optimiser-step kernel, no host in the loop.
+//   G evaluation groups   what the rounds path runs as G co-resident CTAs: the same threads per group, the same block code (a named
+//                         barrier per group stands in for __syncthreads), the same shared-memory layout per group - a run's numbers are
+//                         bit-identical to the rounds path;
+//   one stepper warp      lane i owns optimiser slot i of this SM: it advances the L-BFGS-B state machine of its slot whenever an
+//                         evaluation of that slot has come back, concurrently with the groups evaluating other slots (an optimiser
+//                         step is a ~75 us serial chain: as a kernel of its own it cost 4.6 % of the fit and a grid-wide barrier per
+//                         round; here it runs in issue slots the evaluation leaves idle).  A finished run pulls the next
+//                         (curve, start) task from the global queue into its slot.
+// Slot hand-over goes through shared memory: the stepper publishes theta and the curve id and marks the slot READY; a group's leader
+// claims the READY slot whose run has gone on longest (long runs are what a fit's tail is made of), the group evaluates, publishes
+// (-LML, -gradient) and marks the slot DONE; the stepper picks it up.  No CTA ever waits for another CTA, so the kernel needs no
+// co-residency guarantee; inside a CTA every wait is on a thread of the same CTA.  A wait that lasts ~10 s traps instead of hanging.
+constexpr int kFusedMaxSlots = 32;
+constexpr int kFusedMaxGroups = 16;
+constexpr int kFusedDefaultSlots = 32;
+constexpr int kFusedDefaultSteppers = 1;
+constexpr int kFusedMaxSteppers = 4;   // (warps are allocated four at a time: up to four stepper warps cost no registers)
+constexpr int kFusedThreads = kEvalMaxThreads + 32 * kFusedMaxSteppers;
+
+enum { FS_IDLE = 0, FS_READY = 1, FS_BUSY = 2, FS_DONE = 3 };
+
+struct FusedShared {
+  double theta[kFusedMaxSlots][FG_MAXP];
+  double g[kFusedMaxSlots][FG_MAXP];
+  double f[kFusedMaxSlots];
+  long long curve[kFusedMaxSlots];
+  int state[kFusedMaxSlots];
+  int age[kFusedMaxSlots];     // evaluations of the slot's current run so far: the claim priority
+  int pick[kFusedMaxGroups];
+  int live;                    // slots that still have something to do
+};
+
+struct FusedGeom {
+  int groups;         // evaluation groups per CTA (= CTAs per SM of the rounds path)
+  int group_threads;  // threads per group
+  int slots;          // optimiser slots per CTA (<= 32)
+  int steppers;       // stepper warps (1 .. 4); each owns slots / steppers slots, one per lane
+  int rotate;         // 1: the groups' warp 0 (the serial diagonal chain) on different schedulers
+  size_t group_smem;  // doubles of dynamic shared memory per group
+};
+
+// block context of one evaluation group: threads [base, base + nthr) of the CTA, barrier `bar` (1 .. 15; warp-sized groups need none)
+struct GroupCtx : DevCtx {
+  int bar;
+  __device__ __forceinline__ GroupCtx(int group, int group_threads, int rotate) : DevCtx() {
+    const int hw = (int)threadIdx.x - group * group_threads;   // thread index inside the group
+    nthr = group_threads;
+    nwarp = group_threads >> 5;
+    // which hardware warp of the group plays warp 0: hardware warp h sits on scheduler h % 4
+    int j0 = 0;
+    if (rotate) {
+      if (nwarp >= 4) j0 = (((group * (1 - nwarp)) % 4) + 4) % 4;
+      else if (nwarp == 2) j0 = (group >> 1) & 1;
+    }
+    // (through a shuffle, like DevCtx: the compiler then knows the warp index is warp-uniform and keeps the branches on it convergent)
+    const int hwarp = hw >> 5;
+    warp = __shfl_sync(0xffffffffu, hwarp - j0 < 0 ? hwarp - j0 + nwarp : hwarp - j0, 0);
+    tid = warp * 32 + lane;
+    bar = 1 + group;
+  }
+  __device__ __forceinline__ void sync() {
+    if (nthr != 32) asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory");
+    __syncwarp();   // (also tells the compiler that the warp is converged here, as __syncthreads does: plain SHFL / DMMA follow)
+  }
+};
+
+__device__ __forceinline__ void fused_watchdog(unsigned& spins, long long& t0) {
+  if (++spins > 4096u) {
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 20000000000LL) __trap();
+  }
+  __nanosleep(64);
+}
+
+// the stepper hands slot `slot` (lane `lane` of this CTA) to the groups: its next evaluation point, its curve, its age
+__device__ __forceinline__ void fused_publish(FusedShared& sh, const FitDev& d, int slot, int lane) {
+  const FgState& st = d.slots[slot];
+  for (int k = 0; k < FG_MAXP; ++k) sh.theta[lane][k] = st.x[k];
+  sh.curve[lane] = (long long)curve_of(d.tab, d.slot_task[slot] / d.S);
+  sh.age[lane] = d.slot_nev[slot];
+  __threadfence_block();
+  *(volatile int*)&sh.state[lane] = FS_READY;
+}
+
+template <class Kern, int kPlace>
+__global__ void __launch_bounds__(kFusedThreads, 1) fit_fused_kernel(FitDev d, FusedGeom geo) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ FusedShared sh;
+  const int n_eval_threads = geo.groups * geo.group_threads;
+  // (roles and loop exits go through shuffles so that the compiler knows they are warp-uniform: the block code's warp-level
+  // exchanges then compile to plain SHFL / DMMA, as in the rounds kernels)
+  const bool stepper = __shfl_sync(0xffffffffu, (int)threadIdx.x >= n_eval_threads ? 1 : 0, 0) != 0;
+  const int lane = (int)threadIdx.x & 31;
+  if (threadIdx.x == 0) sh.live = 0;
+  if ((int)threadIdx.x < kFusedMaxSlots) { sh.state[threadIdx.x] = FS_IDLE; sh.age[threadIdx.x] = 0; }
+  __syncthreads();
+  // ---------------------------------------------------------------- the stepper warps: warp s, lane i <-> slot s * spw + i of this CTA
+  const int spw = (geo.slots + geo.steppers - 1) / geo.steppers;   // slots per stepper warp
+  const int sw = stepper ? __shfl_sync(0xffffffffu, ((int)threadIdx.x - n_eval_threads) >> 5, 0) : 0;
+  const int ls = sw * spw + lane;                                   // this lane's slot (local index)
+  const bool has_slot = stepper && lane < spw && ls < geo.slots;
+  if (stepper) {
+    const int slot = (int)blockIdx.x * kFusedMaxSlots + ls;
+    if (has_slot && acquire_task(d, slot, d.slots[slot])) {
+      atomicAdd(&sh.live, 1);
+      fused_publish(sh, d, slot, ls);
+    }
+  }
+  __syncthreads();   // (the last block-wide barrier: from here on the groups and the stepper meet through shared memory only)
+  if (stepper) {
+    const int slot = (int)blockIdx.x * kFusedMaxSlots + ls;
+    unsigned spins = 0;
+    long long t0 = 0;
+#ifdef GP_FUSED_STATS
+    long long st_begin = clock64(), st_busy = 0, st_pass = 0, st_lanes = 0;
+#endif
+    for (;;) {
+      __syncwarp();
+      const bool mine = has_slot && *(volatile int*)&sh.state[ls] == FS_DONE;
+#ifdef GP_FUSED_STATS
+      const long long tp = clock64();
+#endif
+      if (mine) {
+        __threadfence_block();
+        double g[FG_MAXP];
+        for (int k = 0; k < FG_MAXP; ++k) g[k] = sh.g[ls][k];
+        if (advance_slot(d, slot, sh.f[ls], g)) fused_publish(sh, d, slot, ls);
+        else {
+          *(volatile int*)&sh.state[ls] = FS_IDLE;
+          __threadfence_block();
+          atomicSub(&sh.live, 1);
+        }
+      }
+      __syncwarp();
+#ifdef GP_FUSED_STATS
+      { const unsigned bal = __ballot_sync(0xffffffffu, mine); if (bal) { st_busy += clock64() - tp; ++st_pass; st_lanes += __popc(bal); } }
+#endif
+      if (__any_sync(0xffffffffu, mine)) { spins = 0; t0 = 0; continue; }
+      const int live = __shfl_sync(0xffffffffu, *(volatile int*)&sh.live, 0);
+      if (live == 0) break;
+      fused_watchdog(spins, t0);
+    }
+#ifdef GP_FUSED_STATS
+    if (lane == 0 && blockIdx.x < 2)
+      printf("cta %d stepper %d: total %lld kcyc, stepping %lld kcyc (%.1f %%), passes %lld, lanes/pass %.2f, kcyc/pass %.1f\n", (int)blockIdx.x, sw,
+             (clock64() - st_begin) / 1000, st_busy / 1000, 100.0 * st_busy / (double)(clock64() - st_begin), st_pass,
+             (double)st_lanes / (double)(st_pass ? st_pass : 1), (double)st_busy / 1000.0 / (double)(st_pass ? st_pass : 1));
+#endif
+    return;
+  }
+  // ------------------------------------------------------------------ an evaluation group
+  const int group = __shfl_sync(0xffffffffu, (int)threadIdx.x / geo.group_threads, 0);
+  GroupCtx c(group, geo.group_threads, geo.rotate);
+  double* gsm = smem + (size_t)group * geo.group_smem;
+  double* slab = (d.gA != nullptr && d.gA_stride > 0) ? d.gA + ((size_t)blockIdx.x * geo.groups + group) * d.gA_stride : nullptr;
+#ifdef GP_FUSED_STATS
+  long long gs_begin = clock64(), gs_wait = 0, gs_n = 0;
+#endif
+  for (;;) {
+    if (c.tid == 0) {
+      int pick = -1;
+      unsigned spins = 0;
+      long long t0 = 0;
+#ifdef GP_FUSED_STATS
+      const long long tw = clock64();
+#endif
+      for (;;) {
+        int best = -1, best_age = -1;
+        for (int s = 0; s < geo.slots; ++s) {
+          if (*(volatile int*)&sh.state[s] == FS_READY) {
+            const int a = *(volatile int*)&sh.age[s];
+            if (a > best_age) { best_age = a; best = s; }
+          }
+        }
+        if (best >= 0) {
+          if (atomicCAS(&sh.state[best], FS_READY, FS_BUSY) == FS_READY) { pick = best; break; }
+          continue;   // another group was faster: look again
+        }
+        if (*(volatile int*)&sh.live == 0) break;
+        fused_watchdog(spins, t0);
+      }
+      *(volatile int*)&sh.pick[group] = pick;
+      __threadfence_block();
+#ifdef GP_FUSED_STATS
+      gs_wait += clock64() - tw; ++gs_n;
+#endif
+    }
+    c.sync();
+    const int pick = __shfl_sync(0xffffffffu, *(volatile int*)&sh.pick[group], 0);
+    if (pick < 0) break;
+    __threadfence_block();
+    GpCurveView cv = curve_view(d.tab, (int64_t)sh.curve[pick]);
+    double theta[FG_MAXP];
+    for (int k = 0; k < FG_MAXP; ++k) theta[k] = sh.theta[pick][k];
+    double l, g[FG_MAXP];
+    bool ok;
+    {
+      GpSmem s = (kPlace == GP_PLACE_SMEM) ? gp_carve(gsm, gsm + gp_mat_doubles(gp_pad(cv.n)), cv.n) : gp_carve(slab, gsm, cv.n);
+      if (kPlace == GP_PLACE_SMEM && slab != nullptr) s.kslab = slab;
+      gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
+    }
+    if (c.tid == 0) {
+      sh.f[pick] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
+      for (int k = 0; k < Kern::P; ++k) sh.g[pick][k] = -g[k];
+      for (int k = Kern::P; k < FG_MAXP; ++k) sh.g[pick][k] = 0.0;
+      __threadfence_block();
+      *(volatile int*)&sh.state[pick] = FS_DONE;
+    }
+    c.sync();   // (the group's shared memory is free for the next evaluation; pick[group] may be rewritten)
+  }
+#ifdef GP_FUSED_STATS
+  if (c.tid == 0 && blockIdx.x < 2)
+    printf("cta %d group %d: total %lld kcyc, waiting for a slot %lld kcyc (%.1f %%), evaluations %lld, kcyc/evaluation %.1f\n", (int)blockIdx.x, group,
+           (clock64() - gs_begin) / 1000, gs_wait / 1000, 100.0 * gs_wait / (double)(clock64() - gs_begin), gs_n - 1,
+           (double)(clock64() - gs_begin - gs_wait) / 1000.0 / (double)(gs_n > 1 ? gs_n - 1 : 1));
+#endif
 }
 
 struct PredictArgs {
@@ -420,6 +659,7 @@ struct GpFamilyOps {
   int (*eval_prepare)(int place, size_t smem);
   int (*eval)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
   int (*tail)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round, int tail_below);
+  int (*fused)(int place, unsigned grid, size_t smem, cudaStream_t st, const FitDev& d, const FusedGeom& geo);   // shared-memory and slab placements
   int (*predict)(int place, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a);
 };
 
@@ -464,6 +704,20 @@ struct GpFamilyLaunch {
     GP_PLACE_SWITCH(place, { fit_tail_kernel<Kern, kP><<<grid, threads, smem, st>>>(d, round, tail_below); })
     return 0;
   }
+  static int fused(int place, unsigned grid, size_t smem, cudaStream_t st, const FitDev& d, const FusedGeom& geo) {
+    const int threads = geo.groups * geo.group_threads + 32 * geo.steppers;
+    int rc = 0;
+    if (place == GP_PLACE_SMEM) {
+      if ((rc = gp_set_smem(fit_fused_kernel<Kern, GP_PLACE_SMEM>, smem))) return rc;
+      fit_fused_kernel<Kern, GP_PLACE_SMEM><<<grid, threads, smem, st>>>(d, geo);
+    } else if (place == GP_PLACE_SLAB) {
+      if ((rc = gp_set_smem(fit_fused_kernel<Kern, GP_PLACE_SLAB>, smem))) return rc;
+      fit_fused_kernel<Kern, GP_PLACE_SLAB><<<grid, threads, smem, st>>>(d, geo);
+    } else {
+      return FULU_GP_E_UNSUPPORTED;
+    }
+    return (int)cudaGetLastError();
+  }
   static int predict(int place, unsigned grid, size_t smem, cudaStream_t st, const PredictArgs& a) {
     int rc = 0;
     GP_PLACE_SWITCH(place, {
@@ -473,7 +727,7 @@ struct GpFamilyLaunch {
     return (int)cudaGetLastError();
   }
   static const GpFamilyOps* ops() {
-    static const GpFamilyOps o = {Kern::P, &lml, &eval_prepare, &eval, &tail, &predict};
+    static const GpFamilyOps o = {Kern::P, &lml, &eval_prepare, &eval, &tail, &fused, &predict};
     return &o;
   }
 };

@@ -119,9 +119,11 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   w.lam = take(B * (size_t)b.n_bands * 8);
   w.stats = take(B * 6 * 8);
   w.pstatus = take(B * 4);
-  w.slots = take((size_t)window * sizeof(FgState));
-  w.slot_task = take((size_t)window * 8);
-  w.slot_nev = take((size_t)window * 4);
+  // (the fused fit addresses its slots as CTA x lane of the stepper warp, whatever the window)
+  const size_t nslot = (size_t)window > (size_t)sms * kFusedMaxSlots ? (size_t)window : (size_t)sms * kFusedMaxSlots;
+  w.slots = take(nslot * sizeof(FgState));
+  w.slot_task = take(nslot * 8);
+  w.slot_nev = take(nslot * 4);
   w.f_out = take((size_t)window * 8);
   w.g_out = take((size_t)window * FG_MAXP * 8);
   w.list = take((size_t)window * 2 * 4);
@@ -606,13 +608,46 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   d.gA = at<double>(workspace, w.gA);
   d.gA_stride = w.gA_stride;
 
+  const GpFamilyOps* ops = family_ops(batch->kernel);
+  const bool use_tail = getenv("FULU_GP_NO_TAIL") == nullptr;
+  const bool streamed = w.stream_tail && use_tail;
+  // The fused fit (fit_fused_kernel: one persistent CTA per SM, evaluation groups + stepper warps; no rounds, no optimiser-step kernel,
+  // one launch per fit) is OPT-IN (FULU_GP_FUSED=1): bit-identical results, but measured 9-10 % slower than the rounds on B200 at
+  // N = 100 (197 ms against 180 ms for the 10,000-curve fit) and on the ragged config #4 - the stepper warps' long branchy code and
+  // its local-memory state slow the co-resident evaluation warps by more than the step kernel costs as a launch of its own
+  // (DESIGN.md section 6).  It takes fits with more runs than one wave of evaluation CTAs whose matrix is worked on by the 8x8 block
+  // code (shared-memory or slab placement); an explicit window or round cap always means the rounds.
+  FusedGeom geo;
+  geo.groups = w.occ_eval;
+  geo.group_threads = w.threads_eval;
+  geo.group_smem = (w.smem_eval + 15) / 16 * 2;   // doubles, 16-byte granules
+  {
+    const char* e = getenv("FULU_GP_FUSED_SLOTS");
+    geo.slots = e ? atoi(e) : kFusedDefaultSlots;   // (32 slots, one stepper warp: the best of the sweep in profiles/r02_fused_fit.md)
+    if (geo.slots < 1) geo.slots = 1;
+    if (geo.slots > kFusedMaxSlots) geo.slots = kFusedMaxSlots;
+    e = getenv("FULU_GP_FUSED_ROTATE");
+    geo.rotate = e ? atoi(e) : 1;
+    e = getenv("FULU_GP_FUSED_STEPPERS");
+    geo.steppers = e ? atoi(e) : kFusedDefaultSteppers;
+    if (geo.steppers < 1) geo.steppers = 1;
+    if (geo.steppers > kFusedMaxSteppers) geo.steppers = kFusedMaxSteppers;
+    if (geo.steppers > geo.slots) geo.steppers = geo.slots;
+  }
+  const size_t fused_smem = (size_t)geo.groups * geo.group_smem * sizeof(double);
+  const char* fused_env = getenv("FULU_GP_FUSED");
+  const bool fused = use_tail && !streamed && fused_env != nullptr && atoi(fused_env) != 0 && opt->window <= 0 && opt->max_rounds <= 0 &&
+                     w.place != GP_PLACE_TILED && d.n_tasks > (int64_t)w.grid_eval && geo.groups <= kFusedMaxGroups &&
+                     geo.groups * geo.group_threads <= kEvalMaxThreads && fused_smem + sizeof(FusedShared) + 64 <= kMaxSmem;
+
   CU_TRY(cudaMemsetAsync(d.counts, 0, ((size_t)w.max_rounds + 2) * 4, st));
   CU_TRY(cudaMemsetAsync(d.next_task, 0, 8, st));
-  fit_init_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
-  CU_TRY(cudaGetLastError());
-  const GpFamilyOps* ops = family_ops(batch->kernel);
-  rc = ops->eval_prepare(w.place, w.smem_eval);
-  if (rc) return rc;
+  if (!fused) {
+    fit_init_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);
+    CU_TRY(cudaGetLastError());
+    rc = ops->eval_prepare(w.place, w.smem_eval);
+    if (rc) return rc;
+  }
 
   const unsigned step_grid = (unsigned)((w.window + GP_STEP_THREADS - 1) / GP_STEP_THREADS);
   const bool prof = opt->profile != nullptr && opt->profile_counts_only == 0;   // per-launch CUDA events (opt-in diagnostics)
@@ -620,8 +655,6 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   std::vector<cudaEvent_t> ev;   // 3 per round when profiling; read back only after the last launch so timing does not perturb it
   int round = 0;
   bool finished = false;   // false only for the A/B mode that forbids the fused end (FULU_GP_NO_TAIL=1)
-  const bool use_tail = getenv("FULU_GP_NO_TAIL") == nullptr;
-  const bool streamed = w.stream_tail && use_tail;
   std::vector<cudaEvent_t> tev;   // profiling: two events per fused launch (its time counts as evaluation time: the steps are inside)
   auto launch_tail = [&](unsigned ctas, int at_round, int tail_below) -> int {
     if (prof) {
@@ -635,7 +668,19 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     return 0;
   };
   constexpr int kAny = 0x7fffffff;
-  if ((use_tail && d.n_tasks <= (int64_t)w.grid_eval) || streamed) {
+  if (fused) {
+    if (prof) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); tev.push_back(e); }
+      cudaEventRecord(tev[0], st);
+    }
+    const int64_t want_ctas = (d.n_tasks + geo.slots - 1) / geo.slots;   // (a CTA without a task would exit at once)
+    const unsigned ctas = (unsigned)(want_ctas < (int64_t)di.sms ? want_ctas : (int64_t)di.sms);
+    if ((rc = ops->fused(w.place, ctas, fused_smem, st, d, geo))) return rc;
+    if (prof) cudaEventRecord(tev[1], st);
+    --launches;   // (no init kernel)
+    ++launches;
+    finished = true;
+  } else if ((use_tail && d.n_tasks <= (int64_t)w.grid_eval) || streamed) {
     // a small fit (every task has a CTA of its own) or a streaming class: ONE launch, CTA b owns slot b
     const unsigned ctas = (unsigned)(d.n_tasks < (int64_t)w.window ? d.n_tasks : (int64_t)w.window);   // fit_init_kernel filled that many slots at most
     if ((rc = launch_tail(ctas, 0, kAny))) return rc;
@@ -694,6 +739,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     double* pr = opt->profile;
     pr[0] = round; pr[1] = eval_ms; pr[2] = step_ms; pr[3] = launches + (finished ? 0 : 1); pr[4] = w.window; pr[5] = w.grid_eval;
     pr[6] = (double)w.smem_eval; pr[7] = w.globalA ? 1.0 : 0.0; pr[8] = w.threads_eval; pr[9] = w.occ_eval; pr[10] = tail_ms; pr[11] = w.place;
+    if (fused) { pr[4] = (double)geo.slots * di.sms; pr[5] = di.sms; pr[6] = (double)fused_smem; }
   }
   if (!finished) {
     fit_flush_kernel<<<(w.window + 255) / 256, 256, 0, st>>>(d);

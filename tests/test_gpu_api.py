@@ -277,3 +277,37 @@ def test_query_band_outside_the_table_is_flagged_not_indexed():
     db2 = DeviceBatch.from_host(CurveBatch.from_curves(curves, hb.loglam), eng.device, n_max=40)
     g = eng.predict_grid(db2, theta, 4)
     assert int(g["status"][0]) == 0 and int(g["status"][1]) & 1 and bool(torch.isnan(g["mean"][1]).all())
+
+
+def test_fused_fit_is_bit_identical_to_the_rounds(monkeypatch):
+    """FULU_GP_FUSED=1 runs a fit as ONE persistent launch (evaluation groups + stepper warps per SM, csrc/gp_device.cuh
+    fit_fused_kernel) instead of rounds of two kernels: same block code, same geometry per group - the same bits, whatever the number
+    of slots and stepper warps, for shared-memory classes of several residencies and the slab class."""
+    import fulu_b200
+    from fulu_b200 import datasets
+
+    eng = fulu_b200.GPEngine()
+    hb = datasets.ztf_like(700, first=5000, n_lo=20, n_hi=300)   # every length class of config #4: the short ones stay below one wave of CTAs (not fused), the others fuse
+    monkeypatch.setenv("FULU_GP_FUSED", "0")
+    ref = fulu_b200.fit_augment_batch(hb, n_obs=16, engine=eng)
+    for slots, steppers in (("32", "1"), ("12", "3"), ("5", "4")):
+        monkeypatch.setenv("FULU_GP_FUSED", "1")
+        monkeypatch.setenv("FULU_GP_FUSED_SLOTS", slots)
+        monkeypatch.setenv("FULU_GP_FUSED_STEPPERS", steppers)
+        res = fulu_b200.fit_augment_batch(hb, n_obs=16, engine=eng)
+        np.testing.assert_array_equal(res.theta, ref.theta)
+        np.testing.assert_array_equal(res.lml, ref.lml)
+        np.testing.assert_array_equal(res.n_eval, ref.n_eval)
+        np.testing.assert_array_equal(res.status, ref.status)
+        np.testing.assert_array_equal(res.flux_aug, ref.flux_aug)
+    # the headline class (four groups per SM) with more runs than slots: continuous batching inside the CTAs
+    hp = datasets.plasticc_like(1200, first=300)
+    monkeypatch.setenv("FULU_GP_FUSED", "0")
+    ref = fulu_b200.fit_augment_batch(hp, n_obs=8, engine=eng)
+    monkeypatch.setenv("FULU_GP_FUSED", "1")
+    monkeypatch.delenv("FULU_GP_FUSED_SLOTS")
+    monkeypatch.delenv("FULU_GP_FUSED_STEPPERS")
+    res = fulu_b200.fit_augment_batch(hp, n_obs=8, engine=eng)
+    np.testing.assert_array_equal(res.theta, ref.theta)
+    np.testing.assert_array_equal(res.lml, ref.lml)
+    np.testing.assert_array_equal(res.n_eval, ref.n_eval)
