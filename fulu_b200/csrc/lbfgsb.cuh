@@ -37,6 +37,7 @@
 #else
 #define FG_HD inline
 #define FG_NI inline
+#define FG_ROLLED
 #define FG_ROLLED_IN
 #endif
 
