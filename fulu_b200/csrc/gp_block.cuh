@@ -46,6 +46,17 @@
 #define GP_HD inline
 #endif
 
+// The inner DMMA loops run 1 .. T times (mean ~T/3).  Left to the compiler each became a 16/8/4/2/1 unrolling cascade whose branchy
+// remainder logic ran once per tile - as many instructions as the products themselves in a kernel whose warps are bound by their own
+// instruction stream (63k warp-instructions per evaluation, 55 % of them integer and control).  Rolled: 178.6 -> 169.7 ms for the
+// 10,000-curve fit (+5.3 %); unroll 2 / 4: 170.0 / 170.6; rolling the loops over tiles as well: no change; fetching the next tile's
+// fragments by hand before issuing the products: 175.1 (profiles/r02_unroll_sweep.md).
+#define GP_PRAGMA_(x) _Pragma(#x)
+#define GP_PRAGMA(x) GP_PRAGMA_(x)
+#ifndef GP_UNROLL_INNER
+#define GP_UNROLL_INNER 1
+#endif
+#define GP_UNROLL_K GP_PRAGMA(unroll GP_UNROLL_INNER)
 #define GP_NB 8
 #define GP_LOG_2PI 1.8378770664093453
 #define GP_RED 192
@@ -515,6 +526,7 @@ GP_DEV void gp_chol_accumulate(Ctx& c, const GpSmem& s, const GpFrag& f, int k, 
   acc[0][0] = P1[64 * k + f.a0]; acc[0][1] = P1[64 * k + f.a1];
   P1 += 64 * J0;
   if (I2 < 0) {
+    GP_UNROLL_K
     for (int J = J0; J < J1; ++J) {
       c.mma(acc[0][0], acc[0][1], -P1[f.a0], Pb[f.b0]);
       c.mma(d10, d11, -P1[f.a1], Pb[f.b1]);
@@ -525,6 +537,7 @@ GP_DEV void gp_chol_accumulate(Ctx& c, const GpSmem& s, const GpFrag& f, int k, 
     double d20 = 0.0, d21 = 0.0;
     acc[1][0] = P2[64 * k + f.a0]; acc[1][1] = P2[64 * k + f.a1];
     P2 += 64 * J0;
+    GP_UNROLL_K
     for (int J = J0; J < J1; ++J) {
       const double b0 = Pb[f.b0], b1 = Pb[f.b1];
       c.mma(acc[0][0], acc[0][1], -P1[f.a0], b0);
@@ -636,6 +649,7 @@ GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
       double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
       const double* Xr = A + gp_tile(I, kb + 1);   // X_I,K for K = kb + 1 .. I
       const double* Wk = W + 64 * (kb + 1);
+      GP_UNROLL_K
       for (int K = kb + 1; K <= I; ++K) {
         c.mma(p0, p1, Xr[f.a0], Wk[f.p0]);
         c.mma(q0, q1, Xr[f.a1], Wk[f.p1]);
@@ -675,6 +689,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
     const double* Xi = A + gp_tile(I, I);
     const double* Xj = A + gp_tile(I, J);
+    GP_UNROLL_K
     for (int K = I; K < T - 1; ++K) {
       c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
       c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
@@ -844,6 +859,7 @@ GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, con
     double r0 = 0.0, r1 = 0.0;
     const double* L = A + gp_tile(I, 0);
     const double* Vj = Vw;
+    GP_UNROLL_K
     for (int J = 0; J < I; ++J) {
       c.mma(p0, p1, -L[f.a0], Vj[ob0]);
       c.mma(r0, r1, -L[f.a1], Vj[ob1]);
