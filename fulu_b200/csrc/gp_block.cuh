@@ -57,9 +57,40 @@
 #define GP_UNROLL_INNER 1
 #endif
 #define GP_UNROLL_K GP_PRAGMA(unroll GP_UNROLL_INNER)
+// Three more instruction savers of the same kind (A/B switches; all on): the trace pass takes PAIRS of neighbouring tiles that share
+// their A fragments (-0.6 %), tiles of real observations left of the diagonal skip every mask of the assembly (-1.7 %) and of the trace
+// epilogue (-0.7 %): 169.7 -> 164.0 ms.  Dealing the rows of the triangular inverse to the warps in serpentine order: +0.6 %, dropped.
+#ifndef GP_TRACE_PAIRS
+#define GP_TRACE_PAIRS 1
+#endif
+#ifndef GP_ASM_FAST
+#define GP_ASM_FAST 1
+#endif
+#ifndef GP_TRACE_FAST
+#define GP_TRACE_FAST 1
+#endif
 #define GP_NB 8
 #define GP_LOG_2PI 1.8378770664093453
 #define GP_RED 192
+
+// Rolled where the operands come from shared memory; where they come from a slab in global memory (GP_PLACE_SLAB, and the forward
+// substitution of the tiled path) the compiler's unrolling keeps a dozen loads in flight and stays: the N <= 303 class of config #4
+// ran 610 ms unrolled, 717 ms rolled.  A block context may say which it wants (kRolled: factorisation / inverse / traces,
+// kRolledPredict: forward substitution); contexts that say nothing (the host harness) get the rolled loops.
+template <class Ctx, class = void>
+struct GpLoops { static constexpr bool rolled = true, rolled_predict = true; };
+template <class Ctx>
+struct GpLoops<Ctx, decltype((void)Ctx::kRolled, void())> { static constexpr bool rolled = Ctx::kRolled, rolled_predict = Ctx::kRolledPredict; };
+
+template <bool kRolled, class F>
+GP_DEV void gp_kloop(int a, int b, F&& body) {
+  if constexpr (kRolled) {
+    GP_UNROLL_K
+    for (int k = a; k < b; ++k) body(k);
+  } else {
+    for (int k = a; k < b; ++k) body(k);
+  }
+}
 
 struct GpCurveView {
   int n;               // observations
@@ -385,6 +416,21 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Ke
     const double du0 = ui - s.u[j0], dv0 = vi - s.v[j0], du1 = ui - s.u[j1], dv1 = vi - s.v[j1];
     double v0 = kn.value(du0 * du0, dv0 * dv0);
     double v1 = kn.value(du1 * du1, dv1 * dv1);
+#if GP_ASM_FAST
+    // tiles above the last tile-row and left of the diagonal hold nothing but K_ij of real observations (the border row n and the
+    // padding live in tile-row T - 1): no masks, no diagonal, no border
+    if (I < T - 1 && J < I) {
+      tp[f.a0] = v0;
+      tp[f.a1] = v1;
+      if (Kern::kKeepK && s.kslab != nullptr) {
+        s.kslab[64 * q + 8 * g + t] = v0;
+        s.kslab[64 * q + 8 * g + 4 + t] = v1;
+      }
+      J += c.nwarp;
+      while (J > I) { J -= I + 1; ++I; }
+      continue;
+    }
+#endif
     if (i >= n || j0 >= n) v0 = 0.0;
     if (i >= n || j1 >= n) v1 = 0.0;
     // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding; the border's own diagonal entry
@@ -526,26 +572,24 @@ GP_DEV void gp_chol_accumulate(Ctx& c, const GpSmem& s, const GpFrag& f, int k, 
   acc[0][0] = P1[64 * k + f.a0]; acc[0][1] = P1[64 * k + f.a1];
   P1 += 64 * J0;
   if (I2 < 0) {
-    GP_UNROLL_K
-    for (int J = J0; J < J1; ++J) {
+    gp_kloop<GpLoops<Ctx>::rolled>(J0, J1, [&](int) {
       c.mma(acc[0][0], acc[0][1], -P1[f.a0], Pb[f.b0]);
       c.mma(d10, d11, -P1[f.a1], Pb[f.b1]);
       P1 += 64; Pb += 64;
-    }
+    });
   } else {
     const double* P2 = s.A + gp_tile(I2, 0);
     double d20 = 0.0, d21 = 0.0;
     acc[1][0] = P2[64 * k + f.a0]; acc[1][1] = P2[64 * k + f.a1];
     P2 += 64 * J0;
-    GP_UNROLL_K
-    for (int J = J0; J < J1; ++J) {
+    gp_kloop<GpLoops<Ctx>::rolled>(J0, J1, [&](int) {
       const double b0 = Pb[f.b0], b1 = Pb[f.b1];
       c.mma(acc[0][0], acc[0][1], -P1[f.a0], b0);
       c.mma(d10, d11, -P1[f.a1], b1);
       c.mma(acc[1][0], acc[1][1], -P2[f.a0], b0);
       c.mma(d20, d21, -P2[f.a1], b1);
       P1 += 64; P2 += 64; Pb += 64;
-    }
+    });
     acc[1][0] += d20; acc[1][1] += d21;
   }
   acc[0][0] += d10; acc[0][1] += d11;
@@ -649,13 +693,12 @@ GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
       double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
       const double* Xr = A + gp_tile(I, kb + 1);   // X_I,K for K = kb + 1 .. I
       const double* Wk = W + 64 * (kb + 1);
-      GP_UNROLL_K
-      for (int K = kb + 1; K <= I; ++K) {
+      gp_kloop<GpLoops<Ctx>::rolled>(kb + 1, I + 1, [&](int) {
         c.mma(p0, p1, Xr[f.a0], Wk[f.p0]);
         c.mma(q0, q1, Xr[f.a1], Wk[f.p1]);
         Xr += 64;
         Wk += 64;
-      }
+      });
       double* O = A + gp_tile(I, kb);
       O[f.a0] = p0 + q0;
       O[f.a1] = p1 + q1;
@@ -678,35 +721,29 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
 #pragma unroll
   for (int k = 0; k < Kern::NTR; ++k) tr[k] = 0.0;
   trd = 0.0;
-  int I = 0, J = c.warp;
-  while (J > I) { J -= I + 1; ++I; }
   const bool stored = Kern::kKeepK && s.kslab != nullptr;
-  for (int q = c.warp; q < ntile; q += c.nwarp) {
-    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-    GpPair kst = {0.0, 0.0};
-    if (stored) kst = *reinterpret_cast<const GpPair*>(s.kslab + 64 * q + 8 * g + 2 * t);   // K[i][j], K[i][j + 1]: in flight during the products
-    // K^-1[i][j] = sum_{k >= i, k != n} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
-    // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
-    const double* Xi = A + gp_tile(I, I);
-    const double* Xj = A + gp_tile(I, J);
-    GP_UNROLL_K
-    for (int K = I; K < T - 1; ++K) {
-      c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
-      c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
-      Xi += 64 * (K + 1);
-      Xj += 64 * (K + 1);
-    }
-    c.mma(p0, p1, brow0 ? 0.0 : Xi[f.t0], Xj[f.t0]);
-    c.mma(q0, q1, brow1 ? 0.0 : Xi[f.t1], Xj[f.t1]);
-    // epilogue: lane (g, t) owns (i, j) = (i0 + g, j0 + 2t) and (i0 + g, j0 + 2t + 1)
+  // epilogue of one tile (I, J) given its K^-1 entries: lane (g, t) owns (i, j) = (i0 + g, j0 + 2t) and (i0 + g, j0 + 2t + 1)
+  auto finish = [&](int I, int J, double k0, double k1, const GpPair& kst) {
     const int i = 8 * I + g, j = 8 * J + 2 * t;
     const double ai = bord[64 * I + ob_g], ui = s.u[i], vi = s.v[i];                 // (the border row holds -alpha)
-    const double w0 = ai * bord[64 * J + ob_0] - (p0 + q0), w1 = ai * bord[64 * J + ob_1] - (p1 + q1);
+    const double w0 = ai * bord[64 * J + ob_0] - k0, w1 = ai * bord[64 * J + ob_1] - k1;
     const GpPair uj = *reinterpret_cast<const GpPair*>(s.u + j), vj = *reinterpret_cast<const GpPair*>(s.v + j);   // j is even
     const double du0 = ui - uj.x, dv0 = vi - vj.x, du1 = ui - uj.y, dv1 = vi - vj.y;
     const double du0s = du0 * du0, dv0s = dv0 * dv0, du1s = du1 * du1, dv1s = dv1 * dv1;
     // strictly-lower entries inside the curve count (K_ij and its derivatives are recomputed, not stored); on a diagonal tile
     // the diagonal feeds trd
+#if GP_TRACE_FAST
+    if (I < T - 1 && J < I) {   // a tile of real observations left of the diagonal: every entry counts, nothing feeds trd
+      if (stored) {
+        kn.accumulate_stored(w0, kst.x, du0s, dv0s, tr);
+        kn.accumulate_stored(w1, kst.y, du1s, dv1s, tr);
+      } else {
+        kn.accumulate(w0, du0s, dv0s, tr);
+        kn.accumulate(w1, du1s, dv1s, tr);
+      }
+      return;
+    }
+#endif
     const bool in = i < n;
     if (stored) {
       kn.accumulate_stored((in && i > j) ? w0 : 0.0, kst.x, du0s, dv0s, tr);
@@ -716,9 +753,82 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
       kn.accumulate((in && i > j + 1) ? w1 : 0.0, du1s, dv1s, tr);
     }
     if (I == J) trd += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
+  };
+#if GP_TRACE_PAIRS
+  // Work items are PAIRS of neighbouring tiles (I, J), (I, J + 1) of a tile-row (a single tile where the row's count is odd): the two
+  // share the A fragments (X_K,I), the second tile's fragments sit at a fixed offset from the first's - 6 loads and one set of
+  // address / loop instructions for 4 products instead of 8 and two, and four independent DMMA chains per warp instead of two.
+  int I = 0, Jp = c.warp;   // Jp: item index inside tile-row I, which holds (I + 2) / 2 items
+  while (Jp >= (I + 2) / 2) { Jp -= (I + 2) / 2; ++I; }
+  while (I < T) {
+    const int J = 2 * Jp;
+    const bool two = J + 1 <= I;
+    const int q = I * (I + 1) / 2 + J;
+    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0, r0 = 0.0, r1 = 0.0, s0 = 0.0, s1 = 0.0;
+    GpPair kst = {0.0, 0.0}, kst2 = {0.0, 0.0};
+    if (stored) {   // K[i][j], K[i][j + 1]: in flight during the products
+      kst = *reinterpret_cast<const GpPair*>(s.kslab + 64 * q + 8 * g + 2 * t);
+      if (two) kst2 = *reinterpret_cast<const GpPair*>(s.kslab + 64 * (q + 1) + 8 * g + 2 * t);
+    }
+    // K^-1[i][j] = sum_{k >= i, k != n} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
+    // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
+    const double* Xi = A + gp_tile(I, I);
+    const double* Xj = A + gp_tile(I, J);
+    if (two) {
+      gp_kloop<GpLoops<Ctx>::rolled>(I, T - 1, [&](int K) {
+        const double a0 = Xi[f.t0], a1 = Xi[f.t1];
+        c.mma(p0, p1, a0, Xj[f.t0]);
+        c.mma(q0, q1, a1, Xj[f.t1]);
+        c.mma(r0, r1, a0, Xj[64 + f.t0]);
+        c.mma(s0, s1, a1, Xj[64 + f.t1]);
+        Xi += 64 * (K + 1);
+        Xj += 64 * (K + 1);
+      });
+      const double a0 = brow0 ? 0.0 : Xi[f.t0], a1 = brow1 ? 0.0 : Xi[f.t1];
+      c.mma(p0, p1, a0, Xj[f.t0]);
+      c.mma(q0, q1, a1, Xj[f.t1]);
+      c.mma(r0, r1, a0, Xj[64 + f.t0]);
+      c.mma(s0, s1, a1, Xj[64 + f.t1]);
+      finish(I, J, p0 + q0, p1 + q1, kst);
+      finish(I, J + 1, r0 + s0, r1 + s1, kst2);
+    } else {
+      gp_kloop<GpLoops<Ctx>::rolled>(I, T - 1, [&](int K) {
+        c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
+        c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
+        Xi += 64 * (K + 1);
+        Xj += 64 * (K + 1);
+      });
+      c.mma(p0, p1, brow0 ? 0.0 : Xi[f.t0], Xj[f.t0]);
+      c.mma(q0, q1, brow1 ? 0.0 : Xi[f.t1], Xj[f.t1]);
+      finish(I, J, p0 + q0, p1 + q1, kst);
+    }
+    Jp += c.nwarp;
+    while (I < T && Jp >= (I + 2) / 2) { Jp -= (I + 2) / 2; ++I; }
+  }
+#else
+  int I = 0, J = c.warp;
+  while (J > I) { J -= I + 1; ++I; }
+  for (int q = c.warp; q < ntile; q += c.nwarp) {
+    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+    GpPair kst = {0.0, 0.0};
+    if (stored) kst = *reinterpret_cast<const GpPair*>(s.kslab + 64 * q + 8 * g + 2 * t);   // K[i][j], K[i][j + 1]: in flight during the products
+    // K^-1[i][j] = sum_{k >= i, k != n} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
+    // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
+    const double* Xi = A + gp_tile(I, I);
+    const double* Xj = A + gp_tile(I, J);
+    gp_kloop<GpLoops<Ctx>::rolled>(I, T - 1, [&](int K) {
+      c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
+      c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
+      Xi += 64 * (K + 1);
+      Xj += 64 * (K + 1);
+    });
+    c.mma(p0, p1, brow0 ? 0.0 : Xi[f.t0], Xj[f.t0]);
+    c.mma(q0, q1, brow1 ? 0.0 : Xi[f.t1], Xj[f.t1]);
+    finish(I, J, p0 + q0, p1 + q1, kst);
     J += c.nwarp;
     while (J > I) { J -= I + 1; ++I; }
   }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- one LML + gradient evaluation
@@ -859,13 +969,12 @@ GP_DEV double gp_predict_tile(Ctx& c, const GpCurveView& cv, const Kern& kn, con
     double r0 = 0.0, r1 = 0.0;
     const double* L = A + gp_tile(I, 0);
     const double* Vj = Vw;
-    GP_UNROLL_K
-    for (int J = 0; J < I; ++J) {
+    gp_kloop<GpLoops<Ctx>::rolled_predict>(0, I, [&](int) {
       c.mma(p0, p1, -L[f.a0], Vj[ob0]);
       c.mma(r0, r1, -L[f.a1], Vj[ob1]);
       L += 64;
       Vj += 64;
-    }
+    });
     // right-hand side through the warp's own tile I (accumulator layout -> B layout), then V_I = X_II rhs
     double* Vi = Vw + 64 * I;
     *reinterpret_cast<GpPair*>(Vi + oc) = GpPair{p0 + r0, p1 + r1};   // (one 16-byte store: oc is even)

@@ -83,6 +83,15 @@ struct DevCtx {
 
 using TiledCfg = GpTiledCfgDefault;
 
+// The block context of a kernel whose matrix lives in placement kPlace (the GP_PLACE_* values below): it also tells the block code
+// whether its inner product loops run rolled (operands in shared memory) or as the compiler unrolls them (operands in a global slab:
+// gp_block.cuh, GpLoops).
+template <int kPlace>
+struct DevCtxP : DevCtx {
+  static constexpr bool kRolled = kPlace != 1;          // factorisation, inverse, traces: shared memory, or the 64 x 64 blocks of the tiled path
+  static constexpr bool kRolledPredict = kPlace == 0;   // forward substitution against the factor
+};
+
 // Threads per SM given to the evaluation kernel, split evenly between the resident CTAs; it also fixes the register budget
 // (65536 / threads).  Measured on B200 at N = 100 (4 CTAs per SM), 10,000 curves: 1024 threads (64 registers) 229 ms,
 // 768 (80) 213 ms, 640 (96) 206 ms, 512 (128) 203 ms, 384 (168) 216 ms, 256 (255) 255 ms per fit - with few registers the
@@ -140,7 +149,7 @@ __device__ __forceinline__ void attach_kslab(GpSmem& s, double* gA, size_t gA_st
 // as a slab in global memory streamed through shared-memory stages (gp_tiled.cuh).  pipe_it: the CTA's position in its ring of
 // stages (tiled path; carried from evaluation to evaluation).
 template <class Kern, int kPlace>
-__device__ __forceinline__ void eval_curve(DevCtx& c, const GpCurveView& cv, const double* theta, double* smem, double* gA, size_t gA_stride,
+__device__ __forceinline__ void eval_curve(DevCtxP<kPlace>& c, const GpCurveView& cv, const double* theta, double* smem, double* gA, size_t gA_stride,
                                            uint32_t& pipe_it, double& l, double* g, bool& ok) {
   if constexpr (kPlace == GP_PLACE_TILED) {
     GpTiled tl = gp_tiled_carve<TiledCfg>(gA + (size_t)blockIdx.x * gA_stride, smem, cv.n, c.nwarp, pipe_it);
@@ -154,7 +163,7 @@ __device__ __forceinline__ void eval_curve(DevCtx& c, const GpCurveView& cv, con
 }
 
 template <int kPlace>
-__device__ __forceinline__ void eval_init(DevCtx& c, double* smem) {
+__device__ __forceinline__ void eval_init(DevCtxP<kPlace>& c, double* smem) {
   if constexpr (kPlace == GP_PLACE_TILED) {
     GpTiled tl = gp_tiled_carve<TiledCfg>(smem, smem, 1, c.nwarp, 0);   // (only the shared-memory part is used)
     gp_tiled_init<TiledCfg>(c, tl);
@@ -166,7 +175,7 @@ template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
                                                             double* gA, size_t gA_stride, long long* marks) {
   extern __shared__ __align__(16) double smem[];
-  DevCtx c;
+  DevCtxP<kPlace> c;
   if (blockIdx.x == 0) c.marks = marks;
   uint32_t pipe_it = 0;
   eval_init<kPlace>(c, smem);
@@ -278,7 +287,7 @@ __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f
 // One slot run to the end by this CTA: evaluation (all warps) and optimiser step (thread 0) in turn until the slot has nothing left
 // to do (a finished run pulls the next task of the queue into the slot).
 template <class Kern, int kPlace>
-__device__ __forceinline__ void run_slot_to_end(DevCtx& c, const FitDev& d, int slot, double* smem, uint32_t& pipe_it, int* go) {
+__device__ __forceinline__ void run_slot_to_end(DevCtxP<kPlace>& c, const FitDev& d, int slot, double* smem, uint32_t& pipe_it, int* go) {
   for (;;) {
     const int64_t cu = curve_of(d.tab, d.slot_task[slot] / d.S);
     GpCurveView cv = curve_view(d.tab, cu);
@@ -302,7 +311,7 @@ __device__ __forceinline__ void run_slot_to_end(DevCtx& c, const FitDev& d, int 
 template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, int round) {
   extern __shared__ __align__(16) double smem[];
-  DevCtx c;
+  DevCtxP<kPlace> c;
   const int count = *d.ended ? 0 : d.counts[round];
   if ((int)blockIdx.x >= count) return;
   const int32_t* list = d.list + (size_t)(round & 1) * d.window;
@@ -335,7 +344,7 @@ template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, int round, int tail_below) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int go;
-  DevCtx c;
+  DevCtxP<kPlace> c;
   // the mark is this launch's own stamp (round + 1): CTAs of this launch that start after block 0 has set it must not mistake it for
   // an earlier launch's
   const int seen = *d.ended;
@@ -394,9 +403,11 @@ struct FusedGeom {
 };
 
 // block context of one evaluation group: threads [base, base + nthr) of the CTA, barrier `bar` (1 .. 15; warp-sized groups need none)
-struct GroupCtx : DevCtx {
+template <int kPlace>
+struct GroupCtx : DevCtxP<kPlace> {
+  using DevCtx::tid; using DevCtx::nthr; using DevCtx::lane; using DevCtx::warp; using DevCtx::nwarp;
   int bar;
-  __device__ __forceinline__ GroupCtx(int group, int group_threads, int rotate) : DevCtx() {
+  __device__ __forceinline__ GroupCtx(int group, int group_threads, int rotate) : DevCtxP<kPlace>() {
     const int hw = (int)threadIdx.x - group * group_threads;   // thread index inside the group
     nthr = group_threads;
     nwarp = group_threads >> 5;
@@ -504,7 +515,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fit_fused_kernel(FitDev d, F
   }
   // ------------------------------------------------------------------ an evaluation group
   const int group = __shfl_sync(0xffffffffu, (int)threadIdx.x / geo.group_threads, 0);
-  GroupCtx c(group, geo.group_threads, geo.rotate);
+  GroupCtx<kPlace> c(group, geo.group_threads, geo.rotate);
   double* gsm = smem + (size_t)group * geo.group_smem;
   double* slab = (d.gA != nullptr && d.gA_stride > 0) ? d.gA + ((size_t)blockIdx.x * geo.groups + group) * d.gA_stride : nullptr;
 #ifdef GP_FUSED_STATS
@@ -591,7 +602,7 @@ template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double tlim[2];
-  DevCtx c;
+  DevCtxP<kPlace> c;
   // the warps' V tiles: behind the matrix and vectors in shared memory, or this CTA's global slab for long curves
   double* Vglobal = a.gV + (size_t)blockIdx.x * a.gV_stride;
   uint32_t pipe_it = 0;

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/s3_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/s3_pytest_gpu.log
+timeout 600 python bench.py --workload ztf > gpurun_out/s3_bench_ztf.log 2>&1; echo "ztf rc=$?"; tail -1 gpurun_out/s3_bench_ztf.log | cut -c1-230
+timeout 900 python bench.py --workload ddf > gpurun_out/s3_bench_ddf.log 2>&1; echo "ddf rc=$?"; tail -1 gpurun_out/s3_bench_ddf.log | cut -c1-230
+timeout 600 python bench.py > gpurun_out/s3_bench.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/s3_bench.log | cut -c1-230

@@ -1,0 +1,6 @@
+#!/bin/bash
+P="python scripts/fused_probe.py 10000 3"
+echo "== default"; timeout 200 $P 2>&1 | tail -1
+for v in tp af tpaf; do echo "== $v"; FULU_GP_LIB=$PWD/fulu_b200/_lib/libfulu_gp_$v.so timeout 200 $P 2>&1 | tail -1; done
+echo "== default again"; timeout 200 $P 2>&1 | tail -1
+FULU_GP_LIB=$PWD/fulu_b200/_lib/libfulu_gp_tpaf.so timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -2
