@@ -260,6 +260,8 @@ __device__ __forceinline__ void fg_state_copy(FgState* dst, const FgState* src) 
   }
 }
 
+// NV = the family's number of hyperparameters (compile time), 0 = taken from the options
+template <int NV>
 __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f, const double* g) {
 #if GP_STEP_LOCAL
   FgState st;
@@ -267,7 +269,11 @@ __device__ __forceinline__ bool advance_slot(const FitDev& d, int slot, double f
 #else
   FgState& st = d.slots[slot];
 #endif
-  lbfgsb_advance(st, d.opt, f, g);
+#ifdef FG_RUNTIME_N   // (A/B: the number of variables read from the options, loops with run-time bounds)
+  lbfgsb_advance<0>(st, d.opt, f, g);
+#else
+  lbfgsb_advance<NV>(st, d.opt, f, g);
+#endif
   d.slot_nev[slot] += 1;
   bool live = true;
   if (fg_task_done(st.task)) {
@@ -297,7 +303,7 @@ __device__ __forceinline__ void run_slot_to_end(DevCtxP<kPlace>& c, const FitDev
     if (threadIdx.x == 0) {
       for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
-      *go = advance_slot(d, slot, -l, g) ? 1 : 0;
+      *go = advance_slot<Kern::P>(d, slot, -l, g) ? 1 : 0;
       __threadfence_block();
     }
     __syncthreads();
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fit_fused_kernel(FitDev d, F
         __threadfence_block();
         double g[FG_MAXP];
         for (int k = 0; k < FG_MAXP; ++k) g[k] = sh.g[ls][k];
-        if (advance_slot(d, slot, sh.f[ls], g)) fused_publish(sh, d, slot, ls);
+        if (advance_slot<Kern::P>(d, slot, sh.f[ls], g)) fused_publish(sh, d, slot, ls);
         else {
           *(volatile int*)&sh.state[ls] = FS_IDLE;
           __threadfence_block();

@@ -203,11 +203,12 @@ __global__ void fit_init_kernel(FitDev d) {
 #ifndef GP_STEP_THREADS
 #define GP_STEP_THREADS 64
 #endif
+template <int NV>
 __global__ void fit_step_kernel(FitDev d, int round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (*d.ended || i >= d.counts[round]) return;
   const int slot = d.list[(size_t)(round & 1) * d.window + i];
-  if (advance_slot(d, slot, d.f_out[slot], d.g_out + slot * FG_MAXP)) {
+  if (advance_slot<NV>(d, slot, d.f_out[slot], d.g_out + slot * FG_MAXP)) {
     const int pos = atomicAdd(&d.counts[round + 1], 1);
     d.list[(size_t)((round + 1) & 1) * d.window + pos] = slot;
   }
@@ -705,7 +706,13 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
       }
       ops->eval(w.place, w.grid_eval, w.threads_eval, w.smem_eval, st, d, round);
       if (prof) cudaEventRecord(ev[3 * round + 1], st);
-      fit_step_kernel<<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round);
+      // (one instantiation per number of hyperparameters: its loops over the variables unroll exactly, the dense B lives in registers)
+      switch (P) {
+        case 4: fit_step_kernel<4><<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round); break;
+        case 5: fit_step_kernel<5><<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round); break;
+        case 6: fit_step_kernel<6><<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round); break;
+        default: fit_step_kernel<0><<<step_grid, GP_STEP_THREADS, 0, st>>>(d, round); break;
+      }
       if (prof) cudaEventRecord(ev[3 * round + 2], st);
       launches += 2;
     }

@@ -97,10 +97,12 @@ FG_HD double fg_dot(const double* a, const double* b, int n) {
 }
 
 // Infinity norm of the projected gradient (projgr).
+template <int NV = 0>
 FG_HD double fg_projgr(const FgState& s, const FgOptions& o) {
+  const int n = NV > 0 ? NV : o.n;
   double nrm = 0.0;
   FG_ROLLED_IN
-  for (int i = 0; i < o.n; ++i) {
+  for (int i = 0; i < n; ++i) {
     double gi = s.g[i];
     if (gi < 0.0) gi = fmax(s.x[i] - o.hi[i], gi);
     else gi = fmin(s.x[i] - o.lo[i], gi);
@@ -141,8 +143,9 @@ FG_HD void fg_form_B(const FgState& s, int n, int m, double B[FG_MAXP][FG_MAXP])
 
 // Generalised Cauchy point (Algorithm CP).  Returns xcp in s.z and the free set (vars not fixed at a bound
 // along the projected steepest-descent path) in freev[]; returns false if the model is not convex.
+template <int NV = 0>
 FG_HD bool fg_cauchy(FgState& s, const FgOptions& o, const double B[FG_MAXP][FG_MAXP], bool freev[FG_MAXP]) {
-  const int n = o.n;
+  const int n = NV > 0 ? NV : o.n;
   const double epsmch = 2.220446049250313e-16;
   double d[FG_MAXP], tb[FG_MAXP], zz[FG_MAXP];
   bool moving[FG_MAXP];
@@ -227,8 +230,9 @@ FG_HD bool fg_cauchy(FgState& s, const FgOptions& o, const double B[FG_MAXP][FG_
 
 // Subspace minimisation over the free variables at the Cauchy point (direct primal method with the
 // projection step of L-BFGS-B 3.0).  s.z holds xcp on entry, the subspace minimiser on exit.
+template <int NV = 0>
 FG_HD bool fg_subsm(FgState& s, const FgOptions& o, const double B[FG_MAXP][FG_MAXP], const bool freev[FG_MAXP]) {
-  const int n = o.n;
+  const int n = NV > 0 ? NV : o.n;
   int idx[FG_MAXP];
   int nf = 0;
   FG_ROLLED_IN
@@ -485,16 +489,17 @@ FG_HD void lbfgsb_init(FgState& s, const FgOptions& o, const double* x0) {
 
 // Starts an iteration at the current (x, f, g): Cauchy point, subspace minimisation, line-search set-up.
 // Leaves s.x at the first trial point and s.task = FG_TASK_LNSRCH, or a terminal task.
+template <int NV = 0>
 FG_NI void fg_begin_iteration(FgState& s, const FgOptions& o) {
-  const int n = o.n;
+  const int n = NV > 0 ? NV : o.n;
   FG_ROLLED
   for (int attempt = 0; attempt < 3; ++attempt) {
     double B[FG_MAXP][FG_MAXP];
     bool freev[FG_MAXP];
     fg_form_B(s, n, o.m, B);
-    if (!fg_cauchy(s, o, B, freev)) { fg_reset_memory(s); continue; }
+    if (!fg_cauchy<NV>(s, o, B, freev)) { fg_reset_memory(s); continue; }
     if (s.col > 0) {
-      if (!fg_subsm(s, o, B, freev)) { fg_reset_memory(s); continue; }
+      if (!fg_subsm<NV>(s, o, B, freev)) { fg_reset_memory(s); continue; }
     }
     // line search set-up (lnsrlb)
     double dtd = 0.0;
@@ -538,8 +543,11 @@ FG_NI void fg_begin_iteration(FgState& s, const FgOptions& o) {
 
 // Consume (f, g) evaluated at s.x.  On return either s.task is FG_TASK_LNSRCH (evaluate at the new s.x) or terminal
 // (then s.x / s.f / s.g hold the result).
+// NV: the number of variables as a compile-time constant (the loops over the variables then unroll exactly and the small vectors and the
+// dense B stay in registers), or 0 to take it from the options.
+template <int NV = 0>
 FG_HD void lbfgsb_advance(FgState& s, const FgOptions& o, double f, const double* g) {
-  const int n = o.n;
+  const int n = NV > 0 ? NV : o.n;
   const double epsmch = 2.220446049250313e-16;
   if (!(f == f) || fabs(f) > 1e100) {  // -inf LML (non-PD K, _gpr.py:592-593) or NaN: treat as a very bad trial point
     f = 1e100;
@@ -552,9 +560,9 @@ FG_HD void lbfgsb_advance(FgState& s, const FgOptions& o, double f, const double
   s.f = f;
   if (s.task == FG_TASK_START) {
     s.nfgv = 1;
-    s.sbgnrm = fg_projgr(s, o);
+    s.sbgnrm = fg_projgr<NV>(s, o);
     if (s.sbgnrm <= o.pgtol) { s.task = FG_TASK_CONV_PG; return; }
-    fg_begin_iteration(s, o);
+    fg_begin_iteration<NV>(s, o);
     return;
   }
   if (s.task != FG_TASK_LNSRCH) return;
@@ -571,7 +579,7 @@ FG_HD void lbfgsb_advance(FgState& s, const FgOptions& o, double f, const double
       s.nfgv -= 1;
       if (s.col == 0) { s.ifun -= 1; s.iback -= 1; s.iter += 1; s.task = FG_TASK_ABNORMAL; return; }
       fg_reset_memory(s);
-      fg_begin_iteration(s, o);
+      fg_begin_iteration<NV>(s, o);
       return;
     }
     if (s.nfgv > o.maxfun) {  // evaluation budget (checked by SciPy's driver at NEW_X; here also mid-search as a safety net)
@@ -587,7 +595,7 @@ FG_HD void lbfgsb_advance(FgState& s, const FgOptions& o, double f, const double
   }
   // ---- new iterate accepted (CONVERGENCE or WARNING from dcsrch)
   s.iter += 1;
-  s.sbgnrm = fg_projgr(s, o);
+  s.sbgnrm = fg_projgr<NV>(s, o);
   if (s.sbgnrm <= o.pgtol) { s.task = FG_TASK_CONV_PG; return; }
   double ddum = fmax(fmax(fabs(s.fold), fabs(s.f)), 1.0);
   if ((s.fold - s.f) <= epsmch * o.factr * ddum) { s.task = FG_TASK_CONV_F; return; }
@@ -613,7 +621,7 @@ FG_HD void lbfgsb_advance(FgState& s, const FgOptions& o, double f, const double
     s.theta = rr / dr;
   }
   if (s.iter >= o.maxiter || s.nfgv > o.maxfun) { s.task = FG_TASK_MAXITER; return; }
-  fg_begin_iteration(s, o);
+  fg_begin_iteration<NV>(s, o);
 }
 
 FG_HD bool fg_task_done(int32_t task) { return task != FG_TASK_START && task != FG_TASK_LNSRCH; }
