@@ -498,11 +498,17 @@ GP_DEV void gp_logprod_mul(GpLogProd& lp, double x) {   // x in (1e-300, 1e300)
 }
 GP_DEV double gp_logprod_value(const GpLogProd& lp) { return log(lp.m) + (double)lp.e * 0.6931471805599453; }
 
-// jb: local index of the border row when this block holds it, 8 otherwise.  The border's pivot is taken as 1; what has
+// jb: local index of the border row when this block holds it (kBorder), 8 otherwise.  The border's pivot is taken as 1; what has
 // accumulated in its diagonal entry by then is -z.z (it starts at 0), returned in bq.
-template <class Ctx>
+// This warp is the critical path of the factorisation (the other warps of the block have a third of its instructions per block
+// column), and it is bound by its own instruction count - ~57 instructions per pivot in the first version, ~45 now: the column entry
+// of the lane's own row comes by a width-4 shuffle with an immediate lane index, the other lane indices are formed once per block,
+// the pivots are tested four at a time through the product of their reciprocal roots (a non-positive or non-finite pivot makes it
+// NaN, infinite or non-positive), and only the block that holds the border row carries the border's selects.
+template <bool kBorder, class Ctx>
 GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, GpLogProd& rdet, int jb, double& bq) {
   const int g = c.lane >> 2, t = c.lane & 3;
+  const int s0 = 4 * t, s1 = 4 * t + 16;   // lanes that hold rows t and 4 + t (column offsets are added per pivot)
   z0 = (g == t) ? 1.0 : 0.0;
   z1 = (g == 4 + t) ? 1.0 : 0.0;
   bool ok = true;
@@ -512,18 +518,17 @@ GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, 
     const int jt = j & 3;
     const double aj = (j < 4) ? a0 : a1;           // this lane's entry of block column (j & 3) / (4 + (j & 3))
     const double dj = c.shfl(aj, 4 * j + jt);       // A[j][j]
-    const double d = (j == jb) ? 1.0 : dj;
-    if (j == jb) bq = dj;
-    const double cg = c.shfl(aj, 4 * g + jt);       // A[g][j]
-    const double c0 = c.shfl(aj, 4 * t + jt);       // A[t][j]
-    const double c1 = c.shfl(aj, 4 * (4 + t) + jt); // A[4 + t][j]
+    double d = dj;
+    if (kBorder) {
+      if (j == jb) { bq = dj; d = 1.0; }
+    }
+    const double cg = c.shfl4(aj, jt);              // A[g][j]
+    const double c0 = c.shfl(aj, s0 + jt);          // A[t][j]
+    const double c1 = c.shfl(aj, s1 + jt);          // A[4 + t][j]
     const double zj0 = c.shfl(z0, 4 * j + t);       // Z[j][t]
     const double zj1 = c.shfl(z1, 4 * j + t);       // Z[j][4 + t]
-    // a bad pivot is only recorded (the evaluation is discarded as "not positive definite"); nothing waits for the test
-    const bool good = (d > 1.0e-300) && (d < 1.0e300);
-    ok = ok && good;
     const double r = gp_rsqrt(d);
-    rprod *= good ? r : 1.0;
+    rprod *= r;
     const double lg = cg * r, l0 = c0 * r, l1 = c1 * r, x0 = zj0 * r, x1 = zj1 * r;
     if (g > j) {
       a0 -= lg * l0;
@@ -535,6 +540,8 @@ GP_DEV bool gp_chol8_warp(Ctx& c, double a0, double a1, double& z0, double& z1, 
       z1 = x1;
     }
     if ((j & 3) == 3) {
+      // a bad pivot is only recorded (the evaluation is discarded as "not positive definite"); nothing waits for the test
+      ok = ok && (rprod > 0.0) && (rprod < 1.0e300);
       gp_logprod_mul(rdet, rprod);
       rprod = 1.0;
     }
@@ -642,7 +649,9 @@ GP_DEV void gp_cholesky(Ctx& c, const GpSmem& s, int n, double& logdet, double& 
       double acc[2][2], z0, z1;
       const long long t0 = c.clock();
       gp_chol_accumulate(c, s, f, kb, kb, -1, Jlast, kb, acc);
-      if (!gp_chol8_warp(c, acc[0][0], acc[0][1], z0, z1, rdet, (border && kb == T - 1) ? (n & 7) : 8, bq) && c.lane == 0) s.flag[0] = 1;
+      const bool pd = (border && kb == T - 1) ? gp_chol8_warp<true>(c, acc[0][0], acc[0][1], z0, z1, rdet, n & 7, bq)
+                                              : gp_chol8_warp<false>(c, acc[0][0], acc[0][1], z0, z1, rdet, 8, bq);
+      if (!pd && c.lane == 0) s.flag[0] = 1;
       double* D = s.A + gp_tile(kb, kb);
       D[f.a0] = z0;
       D[f.a1] = z1;

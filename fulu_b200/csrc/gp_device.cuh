@@ -39,6 +39,7 @@ struct DevCtx {
   }
   __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ double shfl4(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 4); }   // from lane `src` of this lane's group of four
   // ---- bulk-asynchronous copies and their barriers (gp_tiled.cuh): SASS UBLKCP / SYNCS
   static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
   __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -239,11 +240,13 @@ __device__ __forceinline__ bool acquire_task(const FitDev& d, int slot, FgState&
   }
 }
 
-// One optimiser step of `slot` after its objective evaluation (f, g): advances the L-BFGS-B state machine on a thread-local copy of
-// the 1.5 KB state (local memory is interleaved per thread and L1-resident: one pipelined copy in, one out); a finished run records
-// its result and pulls the next task into the slot.  Returns false when the slot has nothing left to do.
+// One optimiser step of `slot` after its objective evaluation (f, g): advances the L-BFGS-B state machine where the 1.5 KB state
+// lies in global memory; a finished run records its result and pulls the next task into the slot.  Returns false when the slot has
+// nothing left to do.  (GP_STEP_LOCAL=1: on a thread-local copy, one pipelined copy in and one out.  With run-time loop bounds the
+// copy was the faster way, 14.0 against 14.2 ms per fit in round 1; with the number of variables a compile-time constant the small
+// vectors are registers anyway and only the stored pairs are touched where they lie: 160.7 -> 159.2 ms.)
 #ifndef GP_STEP_LOCAL
-#define GP_STEP_LOCAL 1
+#define GP_STEP_LOCAL 0
 #endif
 // (the state travels as 16-byte words, 23 in flight at a time, in a rolled loop: a member-wise struct copy is ~1,200 instructions in and out)
 static_assert(sizeof(FgState) % (16 * 23) == 0, "FgState is copied as 4 x 23 16-byte words");

@@ -64,6 +64,7 @@ struct HostCtx {
     ws->bar.arrive_and_wait();
     return r;
   }
+  double shfl4(double v, int src) { return shfl(v, (lane & ~3) | (src & 3)); }   // __shfl_sync(.., width = 4)
   double shfl_xor(double v, int m) {
     ws->x[lane] = v;
     ws->bar.arrive_and_wait();
