@@ -67,14 +67,20 @@ def _cpu_worker(args):
     workload, first, count, n_obs, kernel = args
     import warnings
 
+    from oracle import ref_arm
     from oracle.fulu_sklearn_port import SklearnGPAugmentation, count_evals
 
+    ref_cls = ref_arm.load()   # the reference's own class where its files were staged (oracle/_ref/), else the re-typed port
     hb = cpu_sample_curves(workload, first, count)
     p2l = {i: float(v) for i, v in enumerate(hb.loglam)}
     out = []
     for i in range(hb.n_curves):
         t, f, e, b = hb.curve(i)
-        aug = SklearnGPAugmentation(p2l, kernel=make_kernel(kernel))
+        k = make_kernel(kernel)
+        if ref_cls is not None:
+            aug = ref_cls(p2l) if k is None else ref_cls(p2l, kernel=k)
+        else:
+            aug = SklearnGPAugmentation(p2l, kernel=k)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             n_eval = count_evals(aug, t, f, e, b)   # aug.fit(...) with the LML+gradient evaluations counted (E of SURVEY 8d)
@@ -100,6 +106,17 @@ def cpu_reference_throughput(n_curves, cores=None, first=0, chunk=4, workload="p
         lml = [v for part in ex.map(_cpu_worker, tasks) for v in part]
         dt = time.perf_counter() - t0
     return n_curves / dt, dt, cores, lml   # lml: [(final LML, evaluations)] per curve, in curve order
+
+
+def cpu_arm_kind():
+    """("reference", text) when the CPU arm runs the reference's own files (staged under oracle/_ref/ by __graft_entry__.build() in
+    the build container), ("port", text) when it runs the re-typed adapter - decided the way the worker processes decide."""
+    from oracle import ref_arm
+
+    if ref_arm.staged():
+        return "reference", ("the reference's own fulu/gp_aug.py + fulu/_base_aug.py (unmodified files staged under oracle/_ref/, imported "
+                             "through matplotlib stubs) on the box's scikit-learn")
+    return "port", "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py)"
 
 
 def cpu_sample_size(workload, cores, ref_curves):
@@ -132,7 +149,8 @@ def run_reference(args):
             vals.append(v)
             times.append(dt)
     value = per_step * len(times) / sum(times)
-    sample = f"{per_step} {CPU_SAMPLE_TEXT[args.workload]} per step, {cores} processes x 1 BLAS thread"
+    kind, kind_text = cpu_arm_kind()
+    sample = f"{per_step} {CPU_SAMPLE_TEXT[args.workload]} per step, {cores} processes x 1 BLAS thread, {kind_text}"
     headline = args.workload == "plasticc" and args.kernel == "default"
     metric = METRIC if headline else f"light curves/sec GP fit+augment ({args.workload} workload, {args.kernel} kernel)"
     line = {
@@ -141,7 +159,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][0], "curves_per_step": per_step, "n_bands": 2 if args.workload == "ztf" else N_BANDS,
                    "n_obs": N_OBS, "kernel": args.kernel},
-        "cpu_baseline": {"value": value, "unit": "curves/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "curves/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "curves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -455,9 +473,10 @@ def run_gpu(args):
         cores = os.cpu_count() or 1
         sample_n = cpu_sample_size(args.workload, cores, args.ref_curves)
         v, dt, cores, cpu_curves = cpu_reference_throughput(sample_n, cores, workload=args.workload)
-        cpu_base = {"value": v, "unit": "curves/s", "cores": cores, "kind": "port",
+        kind, kind_text = cpu_arm_kind()
+        cpu_base = {"value": v, "unit": "curves/s", "cores": cores, "kind": kind,
                     "sample": f"{sample_n} {CPU_SAMPLE_TEXT[args.workload]} in {dt:.1f} s, {cores} processes x 1 BLAS thread, "
-                              "fulu adapter on scikit-learn (oracle/fulu_sklearn_port.py); the same curves as the head of the GPU batch"}
+                              f"{kind_text}; the same curves as the head of the GPU batch"}
 
     engine = fulu_b200.GPEngine(torch.device("cuda", local))
     sampler = ClockSampler(local)

@@ -113,3 +113,29 @@ def test_pipeline_checkers():
     t = np.tile(np.linspace(0.0, 3.0, 4), 2)
     tt, ss, peak = O.band_sum_peak(t, np.array([0.0, 1.0, 5.0, 2.0, 1.0, 1.0, -3.0, 4.0]), np.repeat([0, 1], 4))
     assert ss.tolist() == [1.0, 2.0, 2.0, 6.0] and peak == 3.0
+
+
+def test_staged_reference_class_is_the_cpu_arm_and_agrees_with_the_port():
+    """oracle/ref_arm.py: where __graft_entry__.build() staged the reference's own files (oracle/_ref/, build container), bench.py's CPU
+    arm runs the real class; it must give the port's numbers bit for bit (both drive the same scikit-learn calls)."""
+    import warnings
+
+    from fulu_b200 import datasets
+    from oracle import ref_arm
+    from oracle.fulu_sklearn_port import SklearnGPAugmentation
+
+    if not ref_arm.staged() and not ref_arm.stage():
+        pytest.skip("reference files not staged (no /root/reference here)")
+    cls = ref_arm.load()
+    assert cls is not None and cls.__module__ == "fulu.gp_aug"
+    p2l, t, flux, err, pb = datasets.readme_example()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = cls(p2l).fit(t, flux, err, pb)
+        b = SklearnGPAugmentation(p2l).fit(t, flux, err, pb)
+        ra = a.augmentation(t.min(), t.max(), 50)
+        rb = b.augmentation(t.min(), t.max(), 50)
+    assert a.reg.log_marginal_likelihood_value_ == b.reg.log_marginal_likelihood_value_
+    np.testing.assert_array_equal(a.reg.kernel_.theta, b.reg.kernel_.theta)
+    np.testing.assert_array_equal(ra[1], rb[1])
+    np.testing.assert_array_equal(ra[2], rb[2])
