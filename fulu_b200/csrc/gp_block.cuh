@@ -60,6 +60,10 @@
 // Three more instruction savers of the same kind (A/B switches; all on): the trace pass takes PAIRS of neighbouring tiles that share
 // their A fragments (-0.6 %), tiles of real observations left of the diagonal skip every mask of the assembly (-1.7 %) and of the trace
 // epilogue (-0.7 %): 169.7 -> 164.0 ms.  Dealing the rows of the triangular inverse to the warps in serpentine order: +0.6 %, dropped.
+#ifndef GP_TRACE_GROUP
+#define GP_TRACE_GROUP 2   // tiles of a tile-row taken together in the trace pass: 2, or 4 (measured: 209 ms against 158 - the sixteen
+                           // accumulators and four K pairs of a group of four no longer fit the registers of a 128-thread CTA at 4 CTAs per SM)
+#endif
 #ifndef GP_TRACE_PAIRS
 #define GP_TRACE_PAIRS 1
 #endif
@@ -81,6 +85,9 @@ template <class Ctx, class = void>
 struct GpLoops { static constexpr bool rolled = true, rolled_predict = true; };
 template <class Ctx>
 struct GpLoops<Ctx, decltype((void)Ctx::kRolled, void())> { static constexpr bool rolled = Ctx::kRolled, rolled_predict = Ctx::kRolledPredict; };
+
+template <int N>
+struct GpInt { static constexpr int value = N; };
 
 template <bool kRolled, class F>
 GP_DEV void gp_kloop(int a, int b, F&& body) {
@@ -764,55 +771,57 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     if (I == J) trd += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
   };
 #if GP_TRACE_PAIRS
-  // Work items are PAIRS of neighbouring tiles (I, J), (I, J + 1) of a tile-row (a single tile where the row's count is odd): the two
-  // share the A fragments (X_K,I), the second tile's fragments sit at a fixed offset from the first's - 6 loads and one set of
-  // address / loop instructions for 4 products instead of 8 and two, and four independent DMMA chains per warp instead of two.
-  int I = 0, Jp = c.warp;   // Jp: item index inside tile-row I, which holds (I + 2) / 2 items
-  while (Jp >= (I + 2) / 2) { Jp -= (I + 2) / 2; ++I; }
-  while (I < T) {
-    const int J = 2 * Jp;
-    const bool two = J + 1 <= I;
+  // Work items are GROUPS of up to GP_TRACE_GROUP neighbouring tiles (I, J), (I, J + 1), ... of a tile-row: they share the A fragments
+  // (X_K,I), the later tiles' fragments sit at fixed offsets from the first's - per k-tile 2 + 2 n loads and one set of address / loop
+  // instructions for 2 n products, and 2 n independent DMMA chains per warp.
+  constexpr int NG = GP_TRACE_GROUP;
+  auto run = [&](auto cnt_c, int I, int J) {
+    constexpr int N = decltype(cnt_c)::value;
     const int q = I * (I + 1) / 2 + J;
-    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0, r0 = 0.0, r1 = 0.0, s0 = 0.0, s1 = 0.0;
-    GpPair kst = {0.0, 0.0}, kst2 = {0.0, 0.0};
-    if (stored) {   // K[i][j], K[i][j + 1]: in flight during the products
-      kst = *reinterpret_cast<const GpPair*>(s.kslab + 64 * q + 8 * g + 2 * t);
-      if (two) kst2 = *reinterpret_cast<const GpPair*>(s.kslab + 64 * (q + 1) + 8 * g + 2 * t);
+    double acc[N][4];
+    GpPair kst[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.0;
+      kst[e] = GpPair{0.0, 0.0};
+      if (stored) kst[e] = *reinterpret_cast<const GpPair*>(s.kslab + 64 * (q + e) + 8 * g + 2 * t);   // K[i][j], K[i][j + 1]: in flight during the products
     }
     // K^-1[i][j] = sum_{k >= i, k != n} X[k][i] X[k][j]:  A-fragment (m = g, k = t) = X_K,I[t][g], B (k = t, n = g) = X_K,J[t][g];
     // the diagonal tiles of X carry explicit zeros above the diagonal; the border row (in the last tile-row) is left out
     const double* Xi = A + gp_tile(I, I);
     const double* Xj = A + gp_tile(I, J);
-    if (two) {
-      gp_kloop<GpLoops<Ctx>::rolled>(I, T - 1, [&](int K) {
-        const double a0 = Xi[f.t0], a1 = Xi[f.t1];
-        c.mma(p0, p1, a0, Xj[f.t0]);
-        c.mma(q0, q1, a1, Xj[f.t1]);
-        c.mma(r0, r1, a0, Xj[64 + f.t0]);
-        c.mma(s0, s1, a1, Xj[64 + f.t1]);
-        Xi += 64 * (K + 1);
-        Xj += 64 * (K + 1);
-      });
-      const double a0 = brow0 ? 0.0 : Xi[f.t0], a1 = brow1 ? 0.0 : Xi[f.t1];
-      c.mma(p0, p1, a0, Xj[f.t0]);
-      c.mma(q0, q1, a1, Xj[f.t1]);
-      c.mma(r0, r1, a0, Xj[64 + f.t0]);
-      c.mma(s0, s1, a1, Xj[64 + f.t1]);
-      finish(I, J, p0 + q0, p1 + q1, kst);
-      finish(I, J + 1, r0 + s0, r1 + s1, kst2);
-    } else {
-      gp_kloop<GpLoops<Ctx>::rolled>(I, T - 1, [&](int K) {
-        c.mma(p0, p1, Xi[f.t0], Xj[f.t0]);
-        c.mma(q0, q1, Xi[f.t1], Xj[f.t1]);
-        Xi += 64 * (K + 1);
-        Xj += 64 * (K + 1);
-      });
-      c.mma(p0, p1, brow0 ? 0.0 : Xi[f.t0], Xj[f.t0]);
-      c.mma(q0, q1, brow1 ? 0.0 : Xi[f.t1], Xj[f.t1]);
-      finish(I, J, p0 + q0, p1 + q1, kst);
+    gp_kloop<GpLoops<Ctx>::rolled>(I, T - 1, [&](int K) {
+      const double a0 = Xi[f.t0], a1 = Xi[f.t1];
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        c.mma(acc[e][0], acc[e][1], a0, Xj[64 * e + f.t0]);
+        c.mma(acc[e][2], acc[e][3], a1, Xj[64 * e + f.t1]);
+      }
+      Xi += 64 * (K + 1);
+      Xj += 64 * (K + 1);
+    });
+    const double a0 = brow0 ? 0.0 : Xi[f.t0], a1 = brow1 ? 0.0 : Xi[f.t1];
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      c.mma(acc[e][0], acc[e][1], a0, Xj[64 * e + f.t0]);
+      c.mma(acc[e][2], acc[e][3], a1, Xj[64 * e + f.t1]);
     }
+#pragma unroll
+    for (int e = 0; e < N; ++e) finish(I, J + e, acc[e][0] + acc[e][2], acc[e][1] + acc[e][3], kst[e]);
+  };
+  int I = 0, Jp = c.warp;   // Jp: item index inside tile-row I, which holds (I + NG) / NG items
+  while (Jp >= (I + NG) / NG) { Jp -= (I + NG) / NG; ++I; }
+  while (I < T) {
+    const int J = NG * Jp;
+    const int cnt = I + 1 - J < NG ? I + 1 - J : NG;
+    if (cnt == 1) run(GpInt<1>{}, I, J);
+    else if (cnt == 2) run(GpInt<2>{}, I, J);
+#if GP_TRACE_GROUP > 2
+    else if (cnt == 3) run(GpInt<3>{}, I, J);
+    else run(GpInt<4>{}, I, J);
+#endif
     Jp += c.nwarp;
-    while (I < T && Jp >= (I + 2) / 2) { Jp -= (I + 2) / 2; ++I; }
+    while (I < T && Jp >= (I + NG) / NG) { Jp -= (I + NG) / NG; ++I; }
   }
 #else
   int I = 0, J = c.warp;
