@@ -17,9 +17,11 @@
  *   - return value: 0 ok, <0 argument error (FULU_GP_E_*), >0 a cudaError_t;
  *   - per-curve problems never fail the call: they are reported in status[] (FULU_GP_STATUS_* bits).
  *   - batches are ragged CSR: curve i owns observations offsets[i] .. offsets[i+1]-1.
- *   - two environment variables exist for A/B measurements only (read per call, defaults are the fast paths): FULU_GP_NO_TAIL=1 keeps
+ *   - a few environment variables exist for A/B measurements only (read per call, defaults are the fast paths): FULU_GP_NO_TAIL=1 keeps
  *     the fit on rounds of two launches to the end, FULU_GP_NO_KSLAB=1 recomputes K in the gradient pass instead of reading it back
- *     from the L2 slab; neither changes which curves are processed or the meaning of any output;
+ *     from the L2 slab, FULU_GP_FUSED=1 runs a fit as ONE persistent launch (evaluation groups + optimiser-stepping warps per SM,
+ *     with FULU_GP_FUSED_SLOTS / _STEPPERS / _ROTATE as its geometry; same bits, measured slower: DESIGN.md section 6),
+ *     FULU_GP_TILED_ABOVE=<np> moves the slab / tiled boundary; none changes which curves are processed or the meaning of any output;
  *   - results are bitwise reproducible for a given curve and launch geometry; the geometry (shared memory, CTAs per SM, threads
  *     per CTA) is a function of n_max only.
  */
