@@ -12,7 +12,8 @@ GPU) every rank owns its own 10,000 curves (weak scaling); there is no collectiv
   roofline      the evaluation kernel (fit_eval_kernel: assemble K, Cholesky, inverse, LML+gradient) against the FP64 pipe:
                 algorithmic flops N^3+12N^2 per evaluation / CUDA-event time of its launches (library-side events on
                 the launching stream); peak = DFMA rate measured in this run by fulu_gp_fp64_peak (MEASURED_PEAKS.json has no FP64)
-  cpu_baseline  the reference path (fulu adapter on scikit-learn, oracle/fulu_sklearn_port.py) on all host cores, bounded sample
+  cpu_baseline  the reference path on all host cores, bounded sample: the reference's own fulu/gp_aug.py where __graft_entry__.build() staged
+                it (oracle/_ref/, kind "reference"), else the same calls re-typed (oracle/fulu_sklearn_port.py, kind "port")
   parity        curves with a status other than "theta on a bound"; vs_cpu_pass: the CPU sample is the first curves of the GPU batch, so
                 the final LMLs are compared curve by curve (max deficit against sklearn, fraction within 1e-6) together with both
                 evaluation counts; roofline.frac_at_sklearn_evals rescales the roofline fraction to sklearn's count
