@@ -59,6 +59,8 @@ def cpu_sample_curves(workload, first, count):
 
     if workload == "plasticc":
         return datasets.plasticc_like(count, n_points=N_POINTS, first=first)
+    if workload == "plasticc_ragged":
+        return datasets.plasticc_like(count, n_points=N_POINTS, first=first, ragged=True)
     if workload == "ztf":
         return datasets.ztf_like(count, first=first)
     return datasets.ddf_like(count, n_points=1024, first=first)
@@ -132,6 +134,7 @@ def cpu_sample_size(workload, cores, ref_curves):
 
 CPU_SAMPLE_TEXT = {
     "plasticc": "curves of config #3 (N=100, 6 bands, M=768)",
+    "plasticc_ragged": "curves of config #3's ragged variant (N = clip(Poisson(100), 64, 160), 6 bands, M=768)",
     "ztf": "curves of config #4 (ZTF-like, 2 bands, ragged N = 20..300, M=256)",
     "ddf": "curves of config #5 at N = 1024 (6 bands, M=768; the N = 1536 / 2048 curves of the GPU batch are not in the CPU sample)",
 }
@@ -264,6 +267,8 @@ class ClockSampler:
 WORKLOADS = {
     # name: (description, default curves per GPU per step, n_obs)
     "plasticc": ("BASELINE config #3 (PLAsTiCC-like, 6 bands, N=100, 128-point grid x 6 bands), one batch per GPU per step", 10000, N_OBS),
+    "plasticc_ragged": ("BASELINE config #3, the survey's ragged variant (PLAsTiCC-like, 6 bands, N = clip(Poisson(100), 64, 160), 128-point grid "
+                        "x 6 bands): three length classes (N <= 103 / 127 / 159) as index-list launches over the resident batch", 10000, N_OBS),
     "ztf": ("BASELINE config #4 sample (ZTF-like, 2 bands g/r, ragged N = round(exp(U(ln 20, ln 300))), 128-point grid x 2 bands), "
             "one batch per GPU per step, length classes run as index-list launches over the resident batch", 20000, N_OBS),
     "ddf": ("BASELINE config #5 (LSST-DDF-like, 6 bands, N in {1024, 1536, 2048} in equal parts, 128-point grid x 6 bands), "
@@ -277,6 +282,8 @@ def make_workload(name, B, rank):
 
     if name == "plasticc":
         return datasets.plasticc_like(B, n_points=N_POINTS, first=rank * B)   # each rank: its own B curves (weak scaling)
+    if name == "plasticc_ragged":
+        return datasets.plasticc_like(B, n_points=N_POINTS, first=rank * B, ragged=True)
     if name == "ztf":
         return datasets.ztf_like(B, first=rank * B)
     parts = [datasets.ddf_like((B + 2 - k) // 3, n_points=n, first=rank * B + k * B) for k, n in enumerate((1024, 1536, 2048))]

@@ -29,7 +29,10 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "curves/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 0 and d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    from oracle import ref_arm
+
+    # "reference" where the reference's own files are staged for the CPU arm (oracle/_ref/: build container and what it ships), else "port"
+    assert cb["kind"] == ("reference" if ref_arm.staged() else "port") and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["curves_per_step"] == 2 * cb["cores"]   # the bounded sample: never fewer than two curves per core
 
