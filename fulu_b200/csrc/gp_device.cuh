@@ -369,15 +369,17 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_tail_kernel(FitDev d, 
 }
 
 // ------------------------------------------------------------------------------------------------ the fused fit (round 2)
+// OPT-IN (FULU_GP_FUSED=1): bit-identical to the rounds, measured 9-10 % slower on B200 (profiles/r02_fused_fit.md).
 // ONE persistent CTA per SM runs a whole fit: no rounds, no optimiser-step kernel, no host in the loop.
 //   G evaluation groups   what the rounds path runs as G co-resident CTAs: the same threads per group, the same block code (a named
 //                         barrier per group stands in for __syncthreads), the same shared-memory layout per group - a run's numbers are
 //                         bit-identical to the rounds path;
-//   one stepper warp      lane i owns optimiser slot i of this SM: it advances the L-BFGS-B state machine of its slot whenever an
+//   1-4 stepper warps     each lane owns one optimiser slot of this SM: it advances the L-BFGS-B state machine of its slot whenever an
 //                         evaluation of that slot has come back, concurrently with the groups evaluating other slots (an optimiser
-//                         step is a ~75 us serial chain: as a kernel of its own it cost 4.6 % of the fit and a grid-wide barrier per
-//                         round; here it runs in issue slots the evaluation leaves idle).  A finished run pulls the next
-//                         (curve, start) task from the global queue into its slot.
+//                         step is a 40-75 us serial chain: as a kernel of its own it costs 3-5 % of the fit and a grid-wide barrier
+//                         per round; here it was meant to run in issue slots the evaluation leaves idle - what it takes instead is
+//                         L1 and instruction cache, and the evaluations around it slow down by more than that).  A finished run
+//                         pulls the next (curve, start) task from the global queue into its slot.
 // Slot hand-over goes through shared memory: the stepper publishes theta and the curve id and marks the slot READY; a group's leader
 // claims the READY slot whose run has gone on longest (long runs are what a fit's tail is made of), the group evaluates, publishes
 // (-LML, -gradient) and marks the slot DONE; the stepper picks it up.  No CTA ever waits for another CTA, so the kernel needs no
