@@ -695,7 +695,10 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
     // Behind the last round one fused launch runs whatever might still be live to the end, so the result never depends on the number
     // of rounds chosen here.
     const int64_t waves = (d.n_tasks + w.window - 1) / w.window;
-    int64_t want = use_tail ? 160 + 96 * (waves - 1) : 4096;
+    // (the 5- and 6-parameter families run longer: their longest runs of the 10,000-curve fit take 250-270 evaluations against ~125
+    // for the default kernel; with only 160 rounds enqueued a third of the rbf_rq fit ended in the one-CTA-per-slot launch behind the
+    // last round: 866 ms instead of 650)
+    int64_t want = use_tail ? 160 + 100 * (P > 4 ? P - 4 : 0) + 96 * (waves - 1) : 4096;
     if (opt->max_rounds > 0 && want > opt->max_rounds) want = opt->max_rounds;
     if (want > w.max_rounds) want = w.max_rounds;
     for (; round < (int)want; ++round) {
