@@ -313,6 +313,7 @@ struct GpKern {
   static constexpr int P = 4 + NF1 + NEX;   // hyperparameters
   static constexpr int NTR = P - 1;         // traces over the strictly-lower pairs: every parameter but the noise level
   static constexpr bool kKeepK = (F1 == GP_F_NONE && EX == GP_F_NONE);   // every off-diagonal derivative is K_ij times a weight
+  static constexpr bool kLeanPaths = (P <= 5);   // mask-free / grouped code paths in the assembly and the trace pass (gp_assemble, gp_inverse_traces)
   double cst, s2, lt, ll;
   double xminc;        // arguments of the amplitude-scaled exponential below this give 0
   const double* tabc;  // c 2^(j/16) (GpSmem::tab)
@@ -423,10 +424,11 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Ke
     const double du0 = ui - s.u[j0], dv0 = vi - s.v[j0], du1 = ui - s.u[j1], dv1 = vi - s.v[j1];
     double v0 = kn.value(du0 * du0, dv0 * dv0);
     double v1 = kn.value(du1 * du1, dv1 * dv1);
-#if GP_ASM_FAST
     // tiles above the last tile-row and left of the diagonal hold nothing but K_ij of real observations (the border row n and the
-    // padding live in tile-row T - 1): no masks, no diagonal, no border
-    if (I < T - 1 && J < I) {
+    // padding live in tile-row T - 1): no masks, no diagonal, no border.  (Only for the 4- and 5-parameter families: every extra
+    // path repeats the covariance function's code, and at six parameters the evaluation kernel outgrows the instruction cache -
+    // rbf_rq ran 865 ms with the extra paths against 650 ms without, 99 KB of SASS against the default kernel's 53 KB.)
+    if (GP_ASM_FAST && Kern::kLeanPaths && I < T - 1 && J < I) {
       tp[f.a0] = v0;
       tp[f.a1] = v1;
       if (Kern::kKeepK && s.kslab != nullptr) {
@@ -437,7 +439,6 @@ GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Ke
       while (J > I) { J -= I + 1; ++I; }
       continue;
     }
-#endif
     if (i >= n || j0 >= n) v0 = 0.0;
     if (i >= n || j1 >= n) v1 = 0.0;
     // White on the diagonal, then K[diag] += alpha (_gpr.py:589); identity on the padding; the border's own diagonal entry
@@ -750,8 +751,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     const double du0s = du0 * du0, dv0s = dv0 * dv0, du1s = du1 * du1, dv1s = dv1 * dv1;
     // strictly-lower entries inside the curve count (K_ij and its derivatives are recomputed, not stored); on a diagonal tile
     // the diagonal feeds trd
-#if GP_TRACE_FAST
-    if (I < T - 1 && J < I) {   // a tile of real observations left of the diagonal: every entry counts, nothing feeds trd
+    if (GP_TRACE_FAST && Kern::kLeanPaths && I < T - 1 && J < I) {   // a tile of real observations left of the diagonal: every entry counts, nothing feeds trd
       if (stored) {
         kn.accumulate_stored(w0, kst.x, du0s, dv0s, tr);
         kn.accumulate_stored(w1, kst.y, du1s, dv1s, tr);
@@ -761,7 +761,6 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
       }
       return;
     }
-#endif
     const bool in = i < n;
     if (stored) {
       kn.accumulate_stored((in && i > j) ? w0 : 0.0, kst.x, du0s, dv0s, tr);
@@ -772,7 +771,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     }
     if (I == J) trd += (in && i == j) ? w0 : ((in && i == j + 1) ? w1 : 0.0);
   };
-#if GP_TRACE_PAIRS
+  if constexpr (GP_TRACE_PAIRS && Kern::kLeanPaths) {
   // Work items are GROUPS of up to GP_TRACE_GROUP neighbouring tiles (I, J), (I, J + 1), ... of a tile-row: they share the A fragments
   // (X_K,I), the later tiles' fragments sit at fixed offsets from the first's - per k-tile 2 + 2 n loads and one set of address / loop
   // instructions for 2 n products, and 2 n independent DMMA chains per warp.
@@ -825,7 +824,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     Jp += c.nwarp;
     while (I < T && Jp >= (I + NG) / NG) { Jp -= (I + NG) / NG; ++I; }
   }
-#else
+  } else {
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
   for (int q = c.warp; q < ntile; q += c.nwarp) {
@@ -848,7 +847,7 @@ GP_DEV void gp_inverse_traces(Ctx& c, const GpSmem& s, int n, const Kern& kn, do
     J += c.nwarp;
     while (J > I) { J -= I + 1; ++I; }
   }
-#endif
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- one LML + gradient evaluation
