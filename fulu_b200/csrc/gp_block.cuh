@@ -60,6 +60,9 @@
 // Three more instruction savers of the same kind (A/B switches; all on): the trace pass takes PAIRS of neighbouring tiles that share
 // their A fragments (-0.6 %), tiles of real observations left of the diagonal skip every mask of the assembly (-1.7 %) and of the trace
 // epilogue (-0.7 %): 169.7 -> 164.0 ms.  Dealing the rows of the triangular inverse to the warps in serpentine order: +0.6 %, dropped.
+#ifndef GP_LEAN_MAX_P
+#define GP_LEAN_MAX_P 5   // families with up to this many hyperparameters get the grouped / mask-free paths (GpKern::kLeanPaths)
+#endif
 #ifndef GP_TRACE_GROUP
 #define GP_TRACE_GROUP 2   // tiles of a tile-row taken together in the trace pass: 2, or 4 (measured: 209 ms against 158 - the sixteen
                            // accumulators and four K pairs of a group of four no longer fit the registers of a 128-thread CTA at 4 CTAs per SM)
@@ -313,7 +316,7 @@ struct GpKern {
   static constexpr int P = 4 + NF1 + NEX;   // hyperparameters
   static constexpr int NTR = P - 1;         // traces over the strictly-lower pairs: every parameter but the noise level
   static constexpr bool kKeepK = (F1 == GP_F_NONE && EX == GP_F_NONE);   // every off-diagonal derivative is K_ij times a weight
-  static constexpr bool kLeanPaths = (P <= 5);   // mask-free / grouped code paths in the assembly and the trace pass (gp_assemble, gp_inverse_traces)
+  static constexpr bool kLeanPaths = (P <= GP_LEAN_MAX_P);   // mask-free / grouped code paths in the assembly and the trace pass (gp_assemble, gp_inverse_traces)
   double cst, s2, lt, ll;
   double xminc;        // arguments of the amplitude-scaled exponential below this give 0
   const double* tabc;  // c 2^(j/16) (GpSmem::tab)
