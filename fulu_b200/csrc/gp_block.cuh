@@ -116,7 +116,9 @@ struct alignas(16) GpPair {
 };
 
 struct GpSmem {
-  double* A;      // packed tiles: T (T + 1) / 2 lower tiles, then T scratch tiles
+  double* A;      // packed tiles: T (T + 1) / 2 lower tiles, then (scratch layout) T scratch tiles
+  double* W;      // the scratch column (the triangular inverse's W tiles), or null: the scratch-free layout (gp_carve)
+  double* stage;  // 2 np doubles where gp_load_curve stages the noise diagonal and y for the assembly: the scratch column, or behind the vectors
   double* u;      // np   x_i0 / l_t
   double* v;      // np   x_i1 / l_lambda
   double* red;    // reduction scratch, GP_RED doubles (32 warps x 6 values)
@@ -130,6 +132,11 @@ struct GpSmem {
 GP_HD int gp_pad(int n) { return (n + GP_NB) / GP_NB * GP_NB; }   // order of the bordered matrix (n + 1), padded to a multiple of 8
 GP_HD size_t gp_mat_doubles(int np) { const size_t T = (size_t)np / GP_NB; return 64 * (T * (T + 1) / 2 + T); }
 GP_HD size_t gp_vec_doubles(int np) { return 2 * (size_t)np + GP_RED + 32 + 2; }
+// The scratch-free layout (length classes where it buys one more resident CTA per SM: N = 104 .. 127, 136 .. 159): no scratch column -
+// the triangular inverse forms its W tiles in place and holds a block column's rows in registers across a barrier (gp_trtri) - and the
+// staging of the noise diagonal and y moves behind the vectors.
+GP_HD size_t gp_mat_doubles_ns(int np) { const size_t T = (size_t)np / GP_NB; return 64 * (T * (T + 1) / 2); }
+GP_HD size_t gp_vec_doubles_ns(int np) { return gp_vec_doubles(np) + 2 * (size_t)np; }
 // doubles of shared memory needed for a curve of n observations (matrix + vectors)
 GP_HD size_t gp_smem_doubles(int n) {
   const int np = gp_pad(n);
@@ -137,7 +144,7 @@ GP_HD size_t gp_smem_doubles(int n) {
 }
 
 // vectors at `vec`, matrix at `mat` (shared memory, or a per-CTA global slab for long curves)
-GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
+GP_HD GpSmem gp_carve(double* mat, double* vec, int n, bool scratch = true) {
   GpSmem s;
   s.np = gp_pad(n);
   s.T = s.np / GP_NB;
@@ -149,6 +156,8 @@ GP_HD GpSmem gp_carve(double* mat, double* vec, int n) {
   s.tab = p; p += 32;
   s.kslab = nullptr;
   s.flag = (int*)p;
+  s.W = scratch ? mat + 64 * (s.T * (s.T + 1) / 2) : nullptr;   // (= gp_tile(T, 0))
+  s.stage = scratch ? s.W : p + 2;
   return s;
 }
 
@@ -394,7 +403,7 @@ GP_DEV void gp_load_curve(Ctx& c, const GpCurveView& cv, const GpSmem& s, Kern& 
   if (c.tid < 32) s.tab[c.tid] = (c.tid < 16 ? kn.cst : 1.0) * gp_exp2_tab[c.tid & 15];
   // the noise diagonal and y ride in the scratch column until the triangular inverse needs it: the assembly then reads them from
   // shared memory instead of waiting on global loads in its diagonal and border tiles
-  double* sc = s.A + gp_tile(s.T, 0);
+  double* sc = s.stage;
   for (int i = c.tid; i < s.np; i += c.nthr) {
     if (i < cv.n) {
       s.u[i] = cv.xs[i] * ilt;
@@ -415,7 +424,7 @@ template <class Ctx, class Kern>
 GP_DEV void gp_assemble(Ctx& c, const GpCurveView& cv, const GpSmem& s, const Kern& kn) {
   const int T = s.T, n = cv.n, ntile = T * (T + 1) / 2, g = c.lane >> 2, t = c.lane & 3;
   const GpFrag f = gp_frag(c.lane);
-  const double* al = s.A + gp_tile(T, 0);   // staged by gp_load_curve in the scratch column
+  const double* al = s.stage;   // staged by gp_load_curve (in the scratch column, or behind the vectors in the scratch-free layout)
   const double* yv = al + s.np;
   int I = 0, J = c.warp;
   while (J > I) { J -= I + 1; ++I; }
@@ -692,9 +701,65 @@ template <class Ctx>
 GP_DEV void gp_trtri(Ctx& c, const GpSmem& s) {
   const int T = s.T;
   double* A = s.A;
-  double* W = A + gp_tile(T, 0);   // scratch column: W_I at 64 I
+  double* W = s.W;   // scratch column: W_I at 64 I
   const GpFrag f = gp_frag(c.lane);
   // (the diagonal tiles already hold the inverted diagonal blocks: gp_cholesky)
+  if (W == nullptr) {
+    // The scratch-free layout (every warp takes at most four rows of a block column: plan() in gp_kernels.cu).  ALL the W_I,kb =
+    // -M_I,kb X_kb,kb are formed first, in place, in one pass without barriers between them (the factor itself is not needed any
+    // more); a block column then is: every warp computes its rows into registers, reading W where it lies - barrier - the rows are
+    // written - barrier.  The same products in the same order as the scratch version (bit-identical); at equal residency it is 2 %
+    // slower - it exists for the classes where giving up the scratch column buys a resident CTA.
+    {
+      int I = 1, J = c.warp;   // strictly-lower tiles (I, J), J < I: tile-row I holds I of them
+      while (I < T && J >= I) { J -= I; ++I; }
+      while (I < T) {
+        const double* X11 = A + gp_tile(J, J);
+        double* tp = A + gp_tile(I, J);
+        double w0 = 0.0, w1 = 0.0;
+        c.mma(w0, w1, -tp[f.a0], X11[f.p0]);
+        c.mma(w0, w1, -tp[f.a1], X11[f.p1]);
+        tp[f.a0] = w0;   // (every lane's operands were consumed by the warp-wide products above)
+        tp[f.a1] = w1;
+        J += c.nwarp;
+        while (I < T && J >= I) { J -= I; ++I; }
+      }
+    }
+    c.sync();
+    for (int kb = T - 2; kb >= 0; --kb) {
+      double res[4][2];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int I = T - 1 - c.warp - r * c.nwarp;
+        res[r][0] = 0.0; res[r][1] = 0.0;
+        if (I > kb) {
+          double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+          const double* Xr = A + gp_tile(I, kb + 1);     // X_I,K for K = kb + 1 .. I
+          const double* Wk = A + gp_tile(kb + 1, kb);    // W_K,kb down block column kb
+          gp_kloop<GpLoops<Ctx>::rolled>(kb + 1, I + 1, [&](int K) {
+            c.mma(p0, p1, Xr[f.a0], Wk[f.p0]);
+            c.mma(q0, q1, Xr[f.a1], Wk[f.p1]);
+            Xr += 64;
+            Wk += 64 * (K + 1);
+          });
+          res[r][0] = p0 + q0;
+          res[r][1] = p1 + q1;
+        }
+      }
+      c.sync();   // every W of this block column has been read
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int I = T - 1 - c.warp - r * c.nwarp;
+        if (I > kb) {
+          double* O = A + gp_tile(I, kb);
+          O[f.a0] = res[r][0];
+          O[f.a1] = res[r][1];
+        }
+      }
+      c.sync();
+    }
+    return;
+  }
   for (int kb = T - 2; kb >= 0; --kb) {
     // (1) W_I = -(M_I,kb X11)
     {

@@ -132,8 +132,10 @@ __device__ __forceinline__ GpCurveView curve_view(const CurveTable& t, int64_t c
 enum { GP_PLACE_SMEM = 0, GP_PLACE_SLAB = 1, GP_PLACE_TILED = 2 };
 
 template <bool kGlobalA>
-__device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n) {
+__device__ __forceinline__ GpSmem carve(double* smem, double* gA, size_t gA_stride, int n, bool noscratch = false) {
   if (!kGlobalA) {
+    // (noscratch: the scratch-free layout of the classes where it buys a resident CTA - plan() in gp_kernels.cu, gp_block.cuh)
+    if (noscratch) return gp_carve(smem, smem + gp_mat_doubles_ns(gp_pad(n)), n, false);
     return gp_carve(smem, smem + gp_mat_doubles(gp_pad(n)), n);
   }
   // vectors in shared memory, the matrix in this CTA's global slab (stays in L2)
@@ -151,13 +153,13 @@ __device__ __forceinline__ void attach_kslab(GpSmem& s, double* gA, size_t gA_st
 // stages (tiled path; carried from evaluation to evaluation).
 template <class Kern, int kPlace>
 __device__ __forceinline__ void eval_curve(DevCtxP<kPlace>& c, const GpCurveView& cv, const double* theta, double* smem, double* gA, size_t gA_stride,
-                                           uint32_t& pipe_it, double& l, double* g, bool& ok) {
+                                           uint32_t& pipe_it, double& l, double* g, bool& ok, bool noscratch = false) {
   if constexpr (kPlace == GP_PLACE_TILED) {
     GpTiled tl = gp_tiled_carve<TiledCfg>(gA + (size_t)blockIdx.x * gA_stride, smem, cv.n, c.nwarp, pipe_it);
     gp_tiled_eval_lml_grad<Kern, TiledCfg>(c, cv, theta, tl, l, g, ok);
     pipe_it = tl.it;
   } else {
-    GpSmem s = carve<kPlace != GP_PLACE_SMEM>(smem, gA, gA_stride, cv.n);
+    GpSmem s = carve<kPlace != GP_PLACE_SMEM>(smem, gA, gA_stride, cv.n, noscratch);
     attach_kslab<kPlace != GP_PLACE_SMEM>(s, gA, gA_stride);
     gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
   }
@@ -174,7 +176,7 @@ __device__ __forceinline__ void eval_init(DevCtxP<kPlace>& c, double* smem) {
 // LML + gradient at one theta per curve (fixed-theta parity entry point)
 template <class Kern, int kPlace>
 __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab, int64_t B, int P, const double* theta, double* lml, double* grad,
-                                                            double* gA, size_t gA_stride, long long* marks) {
+                                                            double* gA, size_t gA_stride, long long* marks, int noscratch) {
   extern __shared__ __align__(16) double smem[];
   DevCtxP<kPlace> c;
   if (blockIdx.x == 0) c.marks = marks;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) lml_kernel(CurveTable tab,
     GpCurveView cv = curve_view(tab, cu);
     double l, g[Kern::P];
     bool ok;
-    eval_curve<Kern, kPlace>(c, cv, theta + cu * P, smem, gA, gA_stride, pipe_it, l, g, ok);
+    eval_curve<Kern, kPlace>(c, cv, theta + cu * P, smem, gA, gA_stride, pipe_it, l, g, ok, noscratch != 0);
     if (threadIdx.x == 0) { lml[cu] = l; for (int k = 0; k < Kern::P; ++k) grad[cu * P + k] = g[k]; }
     __syncthreads();
   }
@@ -215,6 +217,7 @@ struct FitDev {
   bool starts_per_curve;
   double* gA;
   size_t gA_stride;
+  int noscratch;   // 1: the scratch-free shared-memory layout (plan() in gp_kernels.cu)
 };
 
 // pulls the next runnable task into `slot` (whose optimiser state is `state`); returns false when the queue is empty
@@ -302,7 +305,7 @@ __device__ __forceinline__ void run_slot_to_end(DevCtxP<kPlace>& c, const FitDev
     GpCurveView cv = curve_view(d.tab, cu);
     double l, g[FG_MAXP];
     bool ok;
-    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
+    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok, d.noscratch != 0);
     if (threadIdx.x == 0) {
       for (int k = 0; k < Kern::P; ++k) g[k] = -g[k];     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = Kern::P; k < FG_MAXP; ++k) g[k] = 0.0;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kEvalMaxThreads, 1) fit_eval_kernel(FitDev d, 
     GpCurveView cv = curve_view(d.tab, cu);
     double l, g[Kern::P];
     bool ok;
-    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok);
+    eval_curve<Kern, kPlace>(c, cv, d.slots[slot].x, smem, d.gA, d.gA_stride, pipe_it, l, g, ok, d.noscratch != 0);
     if (threadIdx.x == 0) {
       d.f_out[slot] = -l;     // obj_func returns (-lml, -grad)  (_gpr.py:302-309)
       for (int k = 0; k < Kern::P; ++k) d.g_out[slot * FG_MAXP + k] = -g[k];
@@ -571,7 +574,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fit_fused_kernel(FitDev d, F
     double l, g[FG_MAXP];
     bool ok;
     {
-      GpSmem s = (kPlace == GP_PLACE_SMEM) ? gp_carve(gsm, gsm + gp_mat_doubles(gp_pad(cv.n)), cv.n) : gp_carve(slab, gsm, cv.n);
+      GpSmem s = (kPlace != GP_PLACE_SMEM) ? gp_carve(slab, gsm, cv.n)
+                 : d.noscratch   ? gp_carve(gsm, gsm + gp_mat_doubles_ns(gp_pad(cv.n)), cv.n, false)
+                                 : gp_carve(gsm, gsm + gp_mat_doubles(gp_pad(cv.n)), cv.n);
       if (kPlace == GP_PLACE_SMEM && slab != nullptr) s.kslab = slab;
       gp_eval_lml_grad<Kern>(c, cv, theta, s, l, g, ok);
     }
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__(kPredictThreads, 2) predict_kernel(PredictArgs
 struct GpFamilyOps {
   int n_params;
   int (*lml)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P, const double* theta,
-             double* lml, double* grad, double* gA, size_t gA_stride, long long* marks);
+             double* lml, double* grad, double* gA, size_t gA_stride, long long* marks, int noscratch);
   int (*eval_prepare)(int place, size_t smem);
   int (*eval)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round);
   int (*tail)(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const FitDev& d, int round, int tail_below);
@@ -702,11 +707,11 @@ inline int gp_set_smem(K kernel, size_t bytes) {
 template <class Kern>
 struct GpFamilyLaunch {
   static int lml(int place, unsigned grid, int threads, size_t smem, cudaStream_t st, const CurveTable& tab, int64_t B, int P,
-                 const double* theta, double* lml, double* grad, double* gA, size_t gA_stride, long long* marks) {
+                 const double* theta, double* lml, double* grad, double* gA, size_t gA_stride, long long* marks, int noscratch) {
     int rc = 0;
     GP_PLACE_SWITCH(place, {
       if ((rc = gp_set_smem(lml_kernel<Kern, kP>, smem))) return rc;
-      lml_kernel<Kern, kP><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks);
+      lml_kernel<Kern, kP><<<grid, threads, smem, st>>>(tab, B, P, theta, lml, grad, gA, gA_stride, marks, noscratch);
     })
     return (int)cudaGetLastError();
   }

@@ -35,6 +35,7 @@ struct WsLayout {
   size_t gA_stride, gV_stride;   // doubles per CTA
   size_t slabs;                  // per-CTA slabs allocated at gA
   bool globalA;   // the matrix lives in a global slab (place != GP_PLACE_SMEM)
+  bool noscratch; // shared-memory placement in the scratch-free layout (gp_block.cuh): one more CTA per SM for N = 104 .. 127, 136 .. 159
   int place;      // GP_PLACE_*
   size_t smem_eval, smem_predict;
 };
@@ -62,6 +63,7 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   const size_t vec = gp_vec_doubles((int)np) * sizeof(double) + 16;
   const size_t full = gp_mat_doubles((int)np) * sizeof(double) + vec;
   w.globalA = full > kMaxSmem;
+  w.noscratch = false;
   // Residency: 228 KB of shared memory per SM, 1 KB reserved per CTA; the evaluation of a curve that fits shared memory is latency
   // bound, so as many curves per SM as fit, and the 512 threads the register file allows are split between them.
   // Longer curves keep the matrix in a per-CTA slab in global memory: up to N = 303 two 256-thread CTAs per SM run the 8x8 block code
@@ -83,11 +85,26 @@ void plan(const fulu_gp_batch& b, int P, int S, int window, int max_rounds, int 
   } else {
     w.smem_eval = full;
     occ = (int)((228 * 1024) / (w.smem_eval + 1024));
+    // The scratch-free layout where it turns two resident CTAs into three or one into two and no warp gets more than four rows of a
+    // block column of the inverse (N = 104 .. 127: 3 x 160 threads, N = 136 .. 159: 2 x 256).  FULU_GP_NO_SCRATCH=0 / 1: A/B switch.
+    const size_t full_ns = gp_mat_doubles_ns((int)np) * sizeof(double) + gp_vec_doubles_ns((int)np) * sizeof(double) + 16;
+    const int occ_ns = (int)((228 * 1024) / (full_ns + 1024));
+    const int warps_ns = occ_ns > 0 ? kEvalMaxThreads / occ_ns / 32 : 0;
+    const int T = (int)(np / GP_NB);
+    const char* e = getenv("FULU_GP_NO_SCRATCH");
+    const bool allowed = e ? atoi(e) != 0 : true;
+    if (allowed && occ >= 1 && occ <= 2 && occ_ns > occ && warps_ns >= 1 && (T - 2 + warps_ns) / warps_ns <= 4) {
+      w.noscratch = true;
+      w.smem_eval = full_ns;
+      occ = occ_ns;
+    }
   }
   // prediction: eight warps, each with its eight columns of V as T tiles (shared memory, or the CTA's global slab for long curves)
   const size_t vtiles = (size_t)(kPredictThreads / 32) * (np / GP_NB) * 64 * sizeof(double);
-  const bool globalV = w.globalA || w.smem_eval + vtiles > kMaxSmem;
-  if (w.place != GP_PLACE_TILED) w.smem_predict = globalV ? w.smem_eval : w.smem_eval + vtiles;
+  // (the prediction kernel always uses the scratch layout: `full`, or the vectors alone when the matrix is in a slab)
+  const size_t smem_factor = w.place == GP_PLACE_SMEM ? full : w.smem_eval;
+  const bool globalV = w.globalA || smem_factor + vtiles > kMaxSmem;
+  if (w.place != GP_PLACE_TILED) w.smem_predict = globalV ? smem_factor : smem_factor + vtiles;
   if (occ < 1) occ = 1;
   if (occ > 16) occ = 16;
   int threads = kEvalMaxThreads / occ / 32 * 32;
@@ -554,7 +571,7 @@ static int lml_impl(const fulu_gp_batch* batch, int32_t n_params, const double* 
   const int64_t B = n_active(*batch);
   unsigned grid = (unsigned)(B < w.grid_eval ? B : w.grid_eval);
   rc = family_ops(batch->kernel)->lml(w.place, grid, w.threads_eval, w.smem_eval, st, tab, B, n_params, theta, lml, grad,
-                                      at<double>(workspace, w.gA), w.gA_stride, marks);
+                                      at<double>(workspace, w.gA), w.gA_stride, marks, w.noscratch ? 1 : 0);
   if (rc) return rc;
   const unsigned g1 = (unsigned)((B + 255) / 256);
   if (scaler || ynorm) export_stats_kernel<<<g1, 256, 0, st>>>(B, tab.order, tab.stats, scaler, ynorm);
@@ -608,6 +625,7 @@ int fulu_gp_fit_batch(const fulu_gp_batch* batch, const fulu_gp_fit_options* opt
   d.starts_per_curve = opt->starts_per_curve != 0;
   d.gA = at<double>(workspace, w.gA);
   d.gA_stride = w.gA_stride;
+  d.noscratch = w.noscratch ? 1 : 0;
 
   const GpFamilyOps* ops = family_ops(batch->kernel);
   const bool use_tail = getenv("FULU_GP_NO_TAIL") == nullptr;

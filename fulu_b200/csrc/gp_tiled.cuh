@@ -414,6 +414,8 @@ GP_DEV GpSmem gp_tiled_dview(const GpTiled& g, int pw) {
   d.T = pw;
   d.np = 8 * pw;
   d.kslab = nullptr;
+  d.W = d.A + gp_tile(pw, 0);   // the block's own scratch column (gp_trtri)
+  d.stage = d.W;
   return d;
 }
 

@@ -21,7 +21,8 @@
  *     the fit on rounds of two launches to the end, FULU_GP_NO_KSLAB=1 recomputes K in the gradient pass instead of reading it back
  *     from the L2 slab, FULU_GP_FUSED=1 runs a fit as ONE persistent launch (evaluation groups + optimiser-stepping warps per SM,
  *     with FULU_GP_FUSED_SLOTS / _STEPPERS / _ROTATE as its geometry; same bits, measured slower: DESIGN.md section 6),
- *     FULU_GP_TILED_ABOVE=<np> moves the slab / tiled boundary; none changes which curves are processed or the meaning of any output;
+ *     FULU_GP_TILED_ABOVE=<np> moves the slab / tiled boundary, FULU_GP_NO_SCRATCH=0 keeps the N = 104..127 / 136..159 classes on the
+ *     layout with a scratch column (one CTA per SM less); none changes which curves are processed or the meaning of any output;
  *   - results are bitwise reproducible for a given curve and launch geometry; the geometry (shared memory, CTAs per SM, threads
  *     per CTA) is a function of n_max only.
  */

@@ -162,13 +162,14 @@ extern "C" int host_gp_prepare(int n, const double* t, const double* flux, const
 template <class Kern>
 static int lml_impl(int family, int n, const double* xs, const int32_t* band, const double* y, const double* al, const double* lam,
                     const double* theta, int nthr, double* lml, double* grad) {
-  std::vector<double> smem(gp_smem_doubles(n));
+  const int np = gp_pad(n);
+  const bool ns = (family & 0x400) != 0;   // bit 10: the scratch-free layout (exactly its own size: an access to a scratch column would be out of bounds)
+  std::vector<double> smem(ns ? gp_mat_doubles_ns(np) + gp_vec_doubles_ns(np) : gp_smem_doubles(n));
   std::vector<double> kslab(gp_mat_doubles(gp_pad(n)));
   GpCurveView cv{n, xs, band, y, al, lam};
   int okout = 0;
-  const int np = gp_pad(n);
   run_block(nthr, [&](HostCtx& c) {
-    GpSmem s = gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
+    GpSmem s = ns ? gp_carve(smem.data(), smem.data() + gp_mat_doubles_ns(np), n, false) : gp_carve(smem.data(), smem.data() + gp_mat_doubles(np), n);
     if (family & 0x200) s.kslab = kslab.data();   // bit 9: the gradient pass reads K back from a slab instead of recomputing it
     double l, g[Kern::P];
     bool ok;

@@ -126,3 +126,23 @@ def test_block_sizes_around_tile_boundaries(n):
         m, s, l3, st = H.predict_grid(p, th, len(g["loglam"]), 5, float(t.min()), float(t.max() + 1.0), nthr=64, family=kind)
         assert st == 0 and abs(l3 - l2) <= 1e-10 * max(1.0, abs(l2))
         assert relerr(m, mo, floor=1e-3 * gp.y_std) < 1e-9 and relerr(s, so, floor=1e-6 * gp.y_std) < 1e-8
+
+
+@pytest.mark.parametrize("name,nthr", [("csv34299", 160), ("csv34299", 256), ("plasticc_0", 128), ("readme_err", 32), ("ztf_5", 64)])
+def test_block_scratch_free_layout_is_bit_identical(name, nthr):
+    """The scratch-free shared-memory layout (gp_block.cuh: no scratch column, the triangular inverse forms its W tiles in place and holds
+    a block column's rows in registers across a barrier; the noise diagonal and y staged behind the vectors) - what the N = 104..127 and
+    136..159 length classes use to hold one more CTA per SM - gives the bits of the scratch layout: LML and every gradient entry, with the
+    K slab and without, at the thread counts those classes run with (160, 256) and others.  The harness allocates exactly the
+    scratch-free footprint."""
+    g = load_golden(name)
+    p = H.prepare(g["t"], g["flux"], g["flux_err"], g["band"], g["loglam"], bool(g["use_err"]), nthr=128)
+    if (p.n + 8) // 8 - 1 > 4 * (nthr // 32):
+        pytest.skip("more than four rows of a block column per warp: plan() keeps the scratch layout there")
+    for k in (0, 3, 6):
+        for fam in (0, 0x200):
+            a = H.lml_grad(p, g["thetas"][k], nthr=nthr, family=fam)
+            b = H.lml_grad(p, g["thetas"][k], nthr=nthr, family=fam | 0x400)
+            assert a[2] and b[2]
+            assert a[0] == b[0]
+            np.testing.assert_array_equal(a[1], b[1])
