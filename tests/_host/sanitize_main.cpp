@@ -30,7 +30,8 @@ int main(int argc, char** argv) {
   }
   int st = host_gp_prepare(n, t.data(), flux.data(), ferr.data(), band.data(), loglam.data(), n_bands, n > 2 ? 1 : 0, 1e-10, nthr, xs.data(), y.data(),
                            al.data(), lam.data(), stats.data());
-  const int P = 4 + ((family & 15) ? 1 : 0) + ((family >> 4) == 4 ? 2 : ((family >> 4) ? 1 : 0));
+  const int fam = family & 0xff;   // (bits above are layout options of the harness: 0x400 = the scratch-free shared-memory layout)
+  const int P = 4 + ((fam & 15) ? 1 : 0) + ((fam >> 4) == 4 ? 2 : ((fam >> 4) ? 1 : 0));
   std::vector<double> theta(P, 0.0), grad(P);
   theta[0] = 0.3; theta[P - 1] = -2.0;
   double lml = 0.0, lml2 = 0.0;
@@ -40,7 +41,7 @@ int main(int argc, char** argv) {
   std::vector<double> mean(m), stdv(m);
   int ps = tiled ? host_gp_predict_tiled(family, n, xs.data(), band.data(), y.data(), al.data(), lam.data(), theta.data(), stats.data(), m, n_obs, t[0],
                                          t[n - 1], nullptr, nullptr, nthr, mean.data(), stdv.data(), &lml2)
-                 : host_gp_predict(family, n, xs.data(), band.data(), y.data(), al.data(), lam.data(), theta.data(), stats.data(), m, n_obs, t[0],
+                 : host_gp_predict(fam, n, xs.data(), band.data(), y.data(), al.data(), lam.data(), theta.data(), stats.data(), m, n_obs, t[0],
                                    t[n - 1], nullptr, nullptr, nthr, mean.data(), stdv.data(), &lml2);
   double sum = 0.0;
   for (int q = 0; q < m; ++q) sum += mean[q] + stdv[q];

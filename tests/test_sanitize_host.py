@@ -44,7 +44,10 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 
 # (n, threads per block, family code F1 | EX << 4, K slab): the headline geometry, a border that opens its own tile-row
 # (n a multiple of 8), the smallest blocks, the notebook family (two Matern factors) and RationalQuadratic
-CASES = [(100, 128, 0, 1), (104, 256, 0, 0), (8, 32, 0, 1), (2, 128, 0, 0), (100, 128, 34, 0), (30, 256, 64, 0)]
+CASES = [(100, 128, 0, 1), (104, 256, 0, 0), (8, 32, 0, 1), (2, 128, 0, 0), (100, 128, 34, 0), (30, 256, 64, 0),
+         # the scratch-free layout (family bit 0x400) at the geometries plan() runs it with: its footprint has no scratch column (ASan), its
+         # triangular inverse holds a block column's rows in registers across a barrier between reading W and writing over it (TSan)
+         (120, 160, 0x400, 1), (150, 256, 0x400, 0)]
 
 
 @pytest.mark.parametrize("kind", ["asan", "tsan"])
